@@ -1,0 +1,184 @@
+/*
+ * pmp_edgecheck.h -- C ABI of the B200 edge-validation library (libpmp_edgecheck.so).
+ *
+ * The reference (UM-ARM-Lab/plant_motion_planning) is pure Python on top of PyBullet and has no FFI
+ * of its own; the entry points below are what a ctypes binding on the reference side would bind to
+ * replace its per-step PyBullet calls (see INTEGRATION.md for the stub).  Each entry point names the
+ * reference interface it stands in for (paths relative to plant_motion_planning/ in the reference).
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success and a negative
+ * PMP_E_* code on failure, with a message available from pmp_last_error().  "_dev" pointers are device
+ * memory on the context's GPU and are owned by the caller; nothing is allocated inside the *_dev calls.
+ * `stream` is a cudaStream_t passed as void* (NULL = default stream); device calls are asynchronous on it.
+ * A context is not thread-safe (the reference is single-threaded: one global Bullet client).
+ */
+#ifndef PMP_EDGECHECK_H
+#define PMP_EDGECHECK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMP_MAX_DOF 16
+#define PMP_MAX_SPHERES 32
+#define PMP_MAX_LINKS 64
+#define PMP_MAX_FIXED 16
+#define PMP_MAX_STEMS 32
+#define PMP_MAX_WORLD_BOXES 32
+#define PMP_MAX_SLOTS 8
+#define PMP_STEM_STRIDE 32 /* floats per stem record, layout in csrc/pmp_tables.h */
+#define PMP_BOX_STRIDE 16  /* floats per plant-base box record: R[9] t[3] half[3] pad */
+
+#define PMP_OK 0
+#define PMP_E_INVALID (-1)  /* bad argument / table out of capacity */
+#define PMP_E_CUDA (-2)     /* CUDA runtime error */
+#define PMP_E_STATE (-3)    /* robot / worlds / params not set */
+#define PMP_E_NOMEM (-4)
+
+#define PMP_MODE_OUR_METHOD 0 /* rigid obstacles + deflection limit   (scripts/multi_world_our_method.py) */
+#define PMP_MODE_AVOID_ALL 1  /* undeflected plants are obstacles too (env.py:75-77, avoid_all=True)      */
+#define PMP_MODE_IGNORE_ALL 2 /* rigid obstacles only                 (collision_fn_benchmark, env.py:112) */
+
+#define PMP_FLAG_RIGID 1    /* limits | self | fixed obstacle hit  (pybullet_tools/utils.py:3979-4016) */
+#define PMP_FLAG_EXCEEDED 2 /* some stem deflection > limit        (pybullet_tools/utils.py:3841-3843, gate NOT applied) */
+
+#define PMP_PRIM_BOX 0
+#define PMP_PRIM_CYLINDER 1
+#define PMP_PRIM_SPHERE 2
+
+typedef struct pmp_ctx pmp_ctx;
+
+/* Robot + static obstacles, host SoA arrays (copied by pmp_set_robot).
+ * Replaces the setup-time closure state of get_collision_fn_with_controls_v3
+ * (pybullet_tools/utils.py:3965-3977: check_link_pairs, moving_links, limits) and the loaded URDF. */
+typedef struct pmp_robot_desc {
+    int32_t dof;              /* planned joints D (<= PMP_MAX_DOF), one serial chain */
+    int32_t n_spheres;        /* arm collision spheres A (<= PMP_MAX_SPHERES), sorted by joint */
+    int32_t n_links;          /* links reported by pmp_fk (<= PMP_MAX_LINKS), PyBullet order */
+    int32_t n_fixed;          /* static primitives: obstacles then the robot's welded geometry */
+    const float* joint_C;     /* [D*9] row-major; R0*Rot(axis,q) = C + cos(q) A + sin(q) B */
+    const float* joint_A;     /* [D*9] */
+    const float* joint_B;     /* [D*9] */
+    const float* joint_t;     /* [D*3] joint origin in the previous joint frame */
+    const float* lower;       /* [D] */
+    const float* upper;       /* [D] */
+    const uint8_t* circular;  /* [D] 1 = continuous joint (difference wraps, no limit test) */
+    const float* base_R;      /* [9] world pose of the chain root */
+    const float* base_t;      /* [3] */
+    const int32_t* sph_joint; /* [A] joint the sphere rides on */
+    const float* sph_center;  /* [A*3] in that joint's frame */
+    const float* sph_radius;  /* [A] */
+    const uint32_t* self_mask;/* [A] bit b (b > a) set => test sphere pair (a, b) */
+    const int32_t* link_joint;/* [L] joint the link rides on, -1 = welded to the base */
+    const float* link_R;      /* [L*9] link frame in the joint frame (or root frame) */
+    const float* link_t;      /* [L*3] */
+    const float* link_com;    /* [L*3] inertial origin in the link frame */
+    int32_t ee_joint;         /* end-effector point for the path-length cost */
+    float ee_local[3];
+    const int32_t* fixed_kind;/* [F] PMP_PRIM_* */
+    const float* fixed_R;     /* [F*9] world */
+    const float* fixed_t;     /* [F*3] world */
+    const float* fixed_half;  /* [F*3] box half extents | (r, half_len, -) | (r, -, -) */
+    const uint32_t* fixed_mask;/* [F] bit a set => arm sphere a is tested against it */
+} pmp_robot_desc;
+
+/* Sampled plant worlds (copied by pmp_set_worlds).  Replaces the per-world Bullet bodies created by
+ * SinglePlantEnv.__init__ (env.py:63-73) and their CharacterizePlant observers. */
+typedef struct pmp_world_desc {
+    int32_t n_worlds;
+    int32_t max_stems;       /* row stride of `stems` in records (<= PMP_MAX_STEMS) */
+    int32_t max_boxes;       /* row stride of `boxes` in records (<= PMP_MAX_WORLD_BOXES) */
+    int32_t n_slots;         /* parent-frame register slots the stem records use (1..PMP_MAX_SLOTS) */
+    const int32_t* n_stems;  /* [W] */
+    const float* stems;      /* [W*max_stems*PMP_STEM_STRIDE] */
+    const int32_t* n_boxes;  /* [W] plant-base boxes (tested in PMP_MODE_AVOID_ALL only) */
+    const float* boxes;      /* [W*max_boxes*PMP_BOX_STRIDE] */
+} pmp_world_desc;
+
+/* Constants the reference hard-codes in closures / module scope. */
+typedef struct pmp_params {
+    double resolution;       /* DEFAULT_RESOLUTION = radians(3), pybullet_tools/utils.py:3660 */
+    float deflection_limit;  /* env.deflection_limit */
+    float alpha;             /* 0.1, kuka_primitives.py:476 */
+    float max_step;          /* per-iteration joint step cap of the plant solve (rad) */
+    float reg_eps;           /* Gauss-Newton regularisation (m^2) */
+    int32_t iterations;      /* K Gauss-Newton steps per stem */
+    int32_t mode;            /* PMP_MODE_* */
+    int32_t dense;           /* 1 = disable data-dependent early exits (every unit runs all K iterations
+                                on every stem: results identical, used to measure the FP32 roofline) */
+    int32_t reserved;
+} pmp_params;
+
+int pmp_create(pmp_ctx** out, int device);
+int pmp_destroy(pmp_ctx* ctx);
+const char* pmp_last_error(pmp_ctx* ctx); /* ctx may be NULL: last creation error */
+int pmp_set_robot(pmp_ctx* ctx, const pmp_robot_desc* robot);
+int pmp_set_worlds(pmp_ctx* ctx, const pmp_world_desc* worlds);
+int pmp_set_params(pmp_ctx* ctx, const pmp_params* params);
+int pmp_num_worlds(pmp_ctx* ctx);
+int pmp_max_stems(pmp_ctx* ctx);
+
+/* Batched forward kinematics: q_dev [B*D] -> link frame position [B*L*3], quaternion xyzw [B*L*4],
+ * COM position [B*L*3] (any output may be NULL).
+ * Replaces set_joint_positions + get_link_state per link (pybullet_tools/utils.py:1996, 2197-2203). */
+int pmp_fk(pmp_ctx* ctx, const float* q_dev, int32_t B, float* link_pos_dev, float* link_quat_dev,
+           float* com_pos_dev, void* stream);
+
+/* Explicit configurations x all worlds.
+ *   flags_dev [B*W] u8 (PMP_FLAG_*), defl_dev [B*W*max_stems] chained deflections (NULL ok),
+ *   theta_dev [B*W*max_stems*2] stem joint angles (NULL ok), ee_dev [B*3] (NULL ok).
+ * Replaces MultiPlantWorld.step(q) + per-world collision_fn(q) + plant_rep.observe_all()
+ * (env.py:212-238; pybullet_tools/utils.py:3836-3855; representation.py:268-294). */
+int pmp_check_configs(pmp_ctx* ctx, const float* q_dev, int32_t B, uint8_t* flags_dev, float* defl_dev,
+                      float* theta_dev, float* ee_dev, void* stream);
+
+/* Edge batches: E straight joint-space edges q0 -> q1, interpolated on the device at `resolution`
+ * (n = int(|dq/res|_2)+1 configurations; backward=0: q1 included, q0 excluded; backward=1: the reversed
+ * sequence of asymmetric_extend, q0 included, q1 excluded), every configuration checked in every world.
+ *   n_steps_dev   [E]      n (unclamped)
+ *   first_hit_dev [E]      first step with any flag in any world, min(n, max_steps) if none
+ *   max_defl_dev  [E*W]    max chained deflection over steps and stems          (NULL ok)
+ *   over_dev      [E*W]    sum over steps and stems of (deflection - limit)+    (NULL ok)
+ *   ee_len_dev    [E]      end-effector path length along the edge               (NULL ok)
+ *   cost_dev      [E]      ee_len + alpha * mean_w over[e,w]                      (NULL ok)
+ *   rigid_mask_dev / exceed_mask_dev [E*W*C] u32, C = ceil(max_steps/32): bit (s%32) of word s/32 is the
+ *                          raw flag of step s in world w -- what the host needs to replay the reference's
+ *                          5 % random pass-through in its sequential order     (NULL ok)
+ * Steps >= max_steps are not evaluated.
+ * Replaces the loop of extend_towards_with_angle_constraint_multi_world (motion_planners/motion_planners/
+ * primitives.py:196-255), check_forward_path_multi_world (rrt_connect_with_angle_constraints_v2.py:143-198)
+ * and the cost accumulation of Command.execute_multi_world (pybullet_tools/kuka_primitives.py:467-521). */
+int pmp_validate_edges(pmp_ctx* ctx, const float* q0_dev, const float* q1_dev, int32_t E, int32_t max_steps,
+                       int32_t backward, int32_t* first_hit_dev, int32_t* n_steps_dev, float* max_defl_dev,
+                       float* over_dev, float* ee_len_dev, float* cost_dev, uint32_t* rigid_mask_dev,
+                       uint32_t* exceed_mask_dev, void* stream);
+
+/* Same with HOST buffers: copies q0/q1 to the device, runs the kernel, copies the requested outputs back
+ * and synchronises.  This is the call a CPU-side planner makes. */
+int pmp_validate_edges_host(pmp_ctx* ctx, const float* q0, const float* q1, int32_t E, int32_t max_steps,
+                            int32_t backward, int32_t* first_hit, int32_t* n_steps, float* max_defl, float* over,
+                            float* ee_len, float* cost, uint32_t* rigid_mask, uint32_t* exceed_mask);
+
+/* Host-buffer version of pmp_check_configs (used by the scalar collision_fn adapter). */
+int pmp_check_configs_host(pmp_ctx* ctx, const float* q, int32_t B, uint8_t* flags, float* defl, float* theta,
+                           float* ee);
+
+/* Launch statistics of the last pmp_validate_edges / pmp_check_configs call. */
+typedef struct pmp_launch_info {
+    int32_t grid, block, smem_bytes, regs_per_thread;
+    int32_t worlds_in_smem;  /* 1 = world tables staged in shared memory, 0 = read through L1 */
+    int32_t n_sphere_pad, n_slot_pad;
+    int64_t kernel_launches; /* cumulative count of this library's kernel launches on the context */
+} pmp_launch_info;
+int pmp_get_launch_info(pmp_ctx* ctx, pmp_launch_info* out);
+
+/* FP32 FMA-pipe micro-benchmark (dependent FMA chains, 8 independent chains per thread) used as the
+ * measured roofline denominator: returns achieved TFLOP/s in *tflops and the kernel time in *ms. */
+int pmp_measure_fp32_peak(pmp_ctx* ctx, int32_t repeats, double* tflops, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMP_EDGECHECK_H */

@@ -1,0 +1,483 @@
+// C-ABI of libpmp_edgecheck.so (see include/pmp_edgecheck.h).  Host glue only: table upload,
+// kernel selection and launch.  No CPU compute path exists here -- without a CUDA device every call fails.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "pmp_kernels.cuh"
+
+struct pmp_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    std::string err;
+    bool has_robot = false, has_worlds = false, has_params = false;
+    PmpRobotTab h_robot;
+    PmpLinkTab h_links;
+    PmpRobotTab* d_robot = nullptr;
+    PmpLinkTab* d_links = nullptr;
+    float* d_stems = nullptr;
+    int32_t* d_nstems = nullptr;
+    float* d_boxes = nullptr;
+    int32_t* d_nboxes = nullptr;
+    int n_worlds = 0, max_stems = 0, max_boxes = 0, n_slots = 1;
+    PmpKernelParams prm;
+    pmp_launch_info info;
+    // scratch for the host-buffer entry points
+    cudaStream_t stream = nullptr;
+    void* d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+};
+
+static std::string g_create_err;
+
+static int fail(pmp_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_err = msg;
+    return code;
+}
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            return fail(ctx, PMP_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                 \
+    } while (0)
+
+extern "C" const char* pmp_last_error(pmp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int pmp_create(pmp_ctx** out, int device) {
+    pmp_ctx* ctx = nullptr;
+    if (!out) return fail(nullptr, PMP_E_INVALID, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(nullptr, PMP_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(nullptr, PMP_E_INVALID, "device index out of range");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, PMP_E_CUDA, cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(nullptr, PMP_E_CUDA, cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, PMP_E_CUDA, "this library carries sm_100a code only (Blackwell B200 required)");
+    ctx = new pmp_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    memset(&ctx->info, 0, sizeof(ctx->info));
+    memset(&ctx->prm, 0, sizeof(ctx->prm));
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, PMP_E_CUDA, "cudaStreamCreate failed");
+    }
+    *out = ctx;
+    return PMP_OK;
+}
+
+static void free_worlds(pmp_ctx* ctx) {
+    cudaFree(ctx->d_stems); cudaFree(ctx->d_nstems); cudaFree(ctx->d_boxes); cudaFree(ctx->d_nboxes);
+    ctx->d_stems = nullptr; ctx->d_nstems = nullptr; ctx->d_boxes = nullptr; ctx->d_nboxes = nullptr;
+}
+
+extern "C" int pmp_destroy(pmp_ctx* ctx) {
+    if (!ctx) return PMP_OK;
+    cudaSetDevice(ctx->device);
+    free_worlds(ctx);
+    cudaFree(ctx->d_robot); cudaFree(ctx->d_links); cudaFree(ctx->d_scratch);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return PMP_OK;
+}
+
+extern "C" int pmp_set_robot(pmp_ctx* ctx, const pmp_robot_desc* r) {
+    if (!ctx || !r) return fail(ctx, PMP_E_INVALID, "null argument");
+    if (r->dof < 1 || r->dof > PMP_MAX_DOF) return fail(ctx, PMP_E_INVALID, "dof out of range");
+    if (r->n_spheres < 1 || r->n_spheres > PMP_MAX_SPHERES) return fail(ctx, PMP_E_INVALID, "n_spheres out of range");
+    if (r->n_links < 0 || r->n_links > PMP_MAX_LINKS) return fail(ctx, PMP_E_INVALID, "n_links out of range");
+    if (r->n_fixed < 0 || r->n_fixed > PMP_MAX_FIXED) return fail(ctx, PMP_E_INVALID, "n_fixed out of range");
+    if (r->ee_joint < 0 || r->ee_joint >= r->dof) return fail(ctx, PMP_E_INVALID, "ee_joint out of range");
+    CK(cudaSetDevice(ctx->device));
+    PmpRobotTab& t = ctx->h_robot;
+    memset(&t, 0, sizeof(t));
+    const int D = r->dof, A = r->n_spheres, F = r->n_fixed, L = r->n_links;
+    memcpy(t.joint_C, r->joint_C, sizeof(float) * 9 * D);
+    memcpy(t.joint_A, r->joint_A, sizeof(float) * 9 * D);
+    memcpy(t.joint_B, r->joint_B, sizeof(float) * 9 * D);
+    memcpy(t.joint_t, r->joint_t, sizeof(float) * 3 * D);
+    memcpy(t.lower, r->lower, sizeof(float) * D);
+    memcpy(t.upper, r->upper, sizeof(float) * D);
+    memcpy(t.base_R, r->base_R, sizeof(float) * 9);
+    memcpy(t.base_t, r->base_t, sizeof(float) * 3);
+    memcpy(t.sph_center, r->sph_center, sizeof(float) * 3 * A);
+    memcpy(t.sph_radius, r->sph_radius, sizeof(float) * A);
+    memcpy(t.self_mask, r->self_mask, sizeof(uint32_t) * A);
+    memcpy(t.sph_joint, r->sph_joint, sizeof(int32_t) * A);
+    for (int a = A; a < PMP_MAX_SPHERES; ++a) { t.sph_joint[a] = -1; t.sph_radius[a] = -1.0e3f; }
+    for (int a = 0; a < A; ++a) {
+        if (t.sph_joint[a] < 0 || t.sph_joint[a] >= D) return fail(ctx, PMP_E_INVALID, "sph_joint out of range");
+        if (a && t.sph_joint[a] < t.sph_joint[a - 1]) return fail(ctx, PMP_E_INVALID, "spheres must be sorted by joint");
+    }
+    if (F) {
+        memcpy(t.fixed_R, r->fixed_R, sizeof(float) * 9 * F);
+        memcpy(t.fixed_t, r->fixed_t, sizeof(float) * 3 * F);
+        memcpy(t.fixed_half, r->fixed_half, sizeof(float) * 3 * F);
+        memcpy(t.fixed_mask, r->fixed_mask, sizeof(uint32_t) * F);
+        memcpy(t.fixed_kind, r->fixed_kind, sizeof(int32_t) * F);
+    }
+    memcpy(t.ee_local, r->ee_local, sizeof(float) * 3);
+    t.ee_joint = r->ee_joint; t.dof = D; t.n_spheres = A; t.n_fixed = F;
+    t.circular_mask = 0;
+    for (int j = 0; j < D; ++j) if (r->circular && r->circular[j]) t.circular_mask |= (1u << j);
+    PmpLinkTab& lt = ctx->h_links;
+    memset(&lt, 0, sizeof(lt));
+    lt.n_links = L;
+    if (L) {
+        memcpy(lt.link_joint, r->link_joint, sizeof(int32_t) * L);
+        memcpy(lt.link_R, r->link_R, sizeof(float) * 9 * L);
+        memcpy(lt.link_t, r->link_t, sizeof(float) * 3 * L);
+        memcpy(lt.link_com, r->link_com, sizeof(float) * 3 * L);
+    }
+    if (!ctx->d_robot) CK(cudaMalloc(&ctx->d_robot, sizeof(PmpRobotTab)));
+    if (!ctx->d_links) CK(cudaMalloc(&ctx->d_links, sizeof(PmpLinkTab)));
+    CK(cudaMemcpy(ctx->d_robot, &t, sizeof(t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_links, &lt, sizeof(lt), cudaMemcpyHostToDevice));
+    ctx->has_robot = true;
+    return PMP_OK;
+}
+
+extern "C" int pmp_set_worlds(pmp_ctx* ctx, const pmp_world_desc* w) {
+    if (!ctx || !w) return fail(ctx, PMP_E_INVALID, "null argument");
+    if (w->n_worlds < 1) return fail(ctx, PMP_E_INVALID, "n_worlds < 1");
+    if (w->max_stems < 1 || w->max_stems > PMP_MAX_STEMS) return fail(ctx, PMP_E_INVALID, "max_stems out of range");
+    if (w->max_boxes < 1 || w->max_boxes > PMP_MAX_WORLD_BOXES) return fail(ctx, PMP_E_INVALID, "max_boxes out of range");
+    if (w->n_slots < 1 || w->n_slots > 4)
+        return fail(ctx, PMP_E_INVALID, "n_slots must be 1..4 (plants deeper than 4 live parent frames are not compiled in)");
+    const int W = w->n_worlds, P = w->max_stems;
+    for (int i = 0; i < W; ++i) {
+        if (w->n_stems[i] < 0 || w->n_stems[i] > P) return fail(ctx, PMP_E_INVALID, "n_stems[w] out of range");
+        if (w->n_boxes[i] < 0 || w->n_boxes[i] > w->max_boxes) return fail(ctx, PMP_E_INVALID, "n_boxes[w] out of range");
+        for (int s = 0; s < w->n_stems[i]; ++s) {
+            const float* rec = w->stems + ((size_t)i * P + s) * PMP_STEM_STRIDE;
+            int32_t ps, os;
+            memcpy(&ps, rec + PMP_S_PSLOT, 4);
+            memcpy(&os, rec + PMP_S_OSLOT, 4);
+            if (ps < -1 || ps >= w->n_slots || os < -1 || os >= w->n_slots)
+                return fail(ctx, PMP_E_INVALID, "stem frame slot out of range");
+        }
+    }
+    CK(cudaSetDevice(ctx->device));
+    free_worlds(ctx);
+    const size_t sb = sizeof(float) * (size_t)W * P * PMP_STEM_STRIDE;
+    const size_t bb = sizeof(float) * (size_t)W * w->max_boxes * PMP_BOX_STRIDE;
+    CK(cudaMalloc(&ctx->d_stems, sb));
+    CK(cudaMalloc(&ctx->d_nstems, sizeof(int32_t) * W));
+    CK(cudaMalloc(&ctx->d_boxes, bb));
+    CK(cudaMalloc(&ctx->d_nboxes, sizeof(int32_t) * W));
+    CK(cudaMemcpy(ctx->d_stems, w->stems, sb, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_nstems, w->n_stems, sizeof(int32_t) * W, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_boxes, w->boxes, bb, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_nboxes, w->n_boxes, sizeof(int32_t) * W, cudaMemcpyHostToDevice));
+    ctx->n_worlds = W; ctx->max_stems = P; ctx->max_boxes = w->max_boxes; ctx->n_slots = w->n_slots;
+    ctx->has_worlds = true;
+    return PMP_OK;
+}
+
+extern "C" int pmp_set_params(pmp_ctx* ctx, const pmp_params* p) {
+    if (!ctx || !p) return fail(ctx, PMP_E_INVALID, "null argument");
+    if (!(p->resolution > 0.0)) return fail(ctx, PMP_E_INVALID, "resolution must be > 0");
+    if (p->iterations < 1 || p->iterations > 64) return fail(ctx, PMP_E_INVALID, "iterations out of range");
+    if (p->mode < 0 || p->mode > 2) return fail(ctx, PMP_E_INVALID, "unknown mode");
+    ctx->prm.resolution = p->resolution;
+    ctx->prm.deflection_limit = p->deflection_limit;
+    ctx->prm.alpha = p->alpha;
+    ctx->prm.max_step = p->max_step;
+    ctx->prm.reg_eps = p->reg_eps;
+    ctx->prm.iterations = p->iterations;
+    ctx->prm.mode = p->mode;
+    ctx->prm.dense = p->dense;
+    ctx->has_params = true;
+    return PMP_OK;
+}
+
+extern "C" int pmp_num_worlds(pmp_ctx* ctx) { return ctx ? ctx->n_worlds : 0; }
+extern "C" int pmp_max_stems(pmp_ctx* ctx) { return ctx ? ctx->max_stems : 0; }
+
+static int ready(pmp_ctx* ctx) {
+    if (!ctx) return PMP_E_INVALID;
+    if (!ctx->has_robot || !ctx->has_worlds || !ctx->has_params)
+        return fail(ctx, PMP_E_STATE, "robot, worlds and params must be set first");
+    ctx->prm.n_worlds = ctx->n_worlds;
+    ctx->prm.max_stems = ctx->max_stems;
+    ctx->prm.max_boxes = ctx->max_boxes;
+    return PMP_OK;
+}
+
+extern "C" int pmp_fk(pmp_ctx* ctx, const float* q_dev, int32_t B, float* pos, float* quat, float* com, void* stream) {
+    if (!ctx || !ctx->has_robot) return fail(ctx, PMP_E_STATE, "robot not set");
+    if (B < 0 || (B && !q_dev)) return fail(ctx, PMP_E_INVALID, "bad batch");
+    if (B == 0) return PMP_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int threads = 128;
+    const size_t smem = sizeof(PmpRobotTab) + sizeof(PmpLinkTab);
+    pmp_fk_kernel<<<(B + threads - 1) / threads, threads, smem, (cudaStream_t)stream>>>(ctx->d_robot, ctx->d_links, q_dev,
+                                                                                      B, pos, quat, com);
+    CK(cudaGetLastError());
+    ctx->info.kernel_launches++;
+    return PMP_OK;
+}
+
+// ---- kernel selection ---------------------------------------------------------------------------
+template <int A, int NS>
+static cudaError_t launch_edge(pmp_ctx* ctx, const PmpEdgeArgs& args, bool wsmem, int grid, int block, size_t smem,
+                               cudaStream_t st) {
+    cudaError_t e;
+    cudaFuncAttributes fa;
+    if (wsmem) {
+        e = cudaFuncSetAttribute(pmp_edge_kernel<A, NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        pmp_edge_kernel<A, NS, true><<<grid, block, smem, st>>>(args);
+        cudaFuncGetAttributes(&fa, pmp_edge_kernel<A, NS, true>);
+    } else {
+        e = cudaFuncSetAttribute(pmp_edge_kernel<A, NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        pmp_edge_kernel<A, NS, false><<<grid, block, smem, st>>>(args);
+        cudaFuncGetAttributes(&fa, pmp_edge_kernel<A, NS, false>);
+    }
+    ctx->info.regs_per_thread = fa.numRegs;
+    return cudaGetLastError();
+}
+
+template <int A, int NS>
+static cudaError_t launch_config(pmp_ctx* ctx, const PmpConfigArgs& args, int grid, int block, size_t smem,
+                                 cudaStream_t st) {
+    pmp_config_kernel<A, NS><<<grid, block, smem, st>>>(args);
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, pmp_config_kernel<A, NS>);
+    ctx->info.regs_per_thread = fa.numRegs;
+    return cudaGetLastError();
+}
+
+#define PMP_DISPATCH(FN, ...)                                                              \
+    do {                                                                                   \
+        const int ap_ = apad, ns_ = nspad;                                                 \
+        if (ap_ == 12 && ns_ == 1) err = FN<12, 1>(__VA_ARGS__);                           \
+        else if (ap_ == 12 && ns_ == 2) err = FN<12, 2>(__VA_ARGS__);                      \
+        else if (ap_ == 12 && ns_ == 4) err = FN<12, 4>(__VA_ARGS__);                      \
+        else if (ap_ == 16 && ns_ == 1) err = FN<16, 1>(__VA_ARGS__);                      \
+        else if (ap_ == 16 && ns_ == 2) err = FN<16, 2>(__VA_ARGS__);                      \
+        else if (ap_ == 16 && ns_ == 4) err = FN<16, 4>(__VA_ARGS__);                      \
+        else if (ap_ == 32 && ns_ == 1) err = FN<32, 1>(__VA_ARGS__);                      \
+        else if (ap_ == 32 && ns_ == 2) err = FN<32, 2>(__VA_ARGS__);                      \
+        else err = FN<32, 4>(__VA_ARGS__);                                                 \
+    } while (0)
+
+static void pads(pmp_ctx* ctx, int& apad, int& nspad) {
+    const int A = ctx->h_robot.n_spheres;
+    apad = A <= 12 ? 12 : (A <= 16 ? 16 : 32);
+    nspad = ctx->n_slots <= 1 ? 1 : (ctx->n_slots <= 2 ? 2 : 4);
+}
+
+extern "C" int pmp_validate_edges(pmp_ctx* ctx, const float* q0, const float* q1, int32_t E, int32_t max_steps,
+                                  int32_t backward, int32_t* first_hit, int32_t* n_steps, float* max_defl, float* over,
+                                  float* ee_len, float* cost, uint32_t* rigid_mask, uint32_t* exceed_mask, void* stream) {
+    int rc = ready(ctx);
+    if (rc) return rc;
+    if (E < 0 || max_steps < 1) return fail(ctx, PMP_E_INVALID, "bad E / max_steps");
+    if (E == 0) return PMP_OK;
+    if (!q0 || !q1 || !first_hit || !n_steps) return fail(ctx, PMP_E_INVALID, "q0, q1, first_hit, n_steps are required");
+    CK(cudaSetDevice(ctx->device));
+    PmpEdgeArgs a;
+    a.robot = ctx->d_robot; a.stems = ctx->d_stems; a.n_stems = ctx->d_nstems; a.boxes = ctx->d_boxes;
+    a.n_boxes = ctx->d_nboxes; a.prm = ctx->prm; a.q0 = q0; a.q1 = q1; a.E = E; a.max_steps = max_steps;
+    a.backward = backward ? 1 : 0; a.first_hit = first_hit; a.n_steps = n_steps; a.max_defl = max_defl; a.over = over;
+    a.ee_len = ee_len; a.cost = cost; a.rigid_mask = rigid_mask; a.exceed_mask = exceed_mask;
+
+    int apad, nspad;
+    pads(ctx, apad, nspad);
+    const int W = ctx->n_worlds;
+    const size_t world_bytes = sizeof(float) * (size_t)W * ctx->max_stems * PMP_STEM_STRIDE;
+    // geometry: 2 CTAs x 256 threads per SM when the world tables fit twice, else 1 x 512, else tables stay in L1/L2
+    int block = 256, per_sm = 2;
+    auto smem_for = [&](int blk, bool ws) {
+        const int warps = blk / 32;
+        return sizeof(PmpRobotTab) + (ws ? world_bytes : 0) + sizeof(int32_t) * ((W + 3) & ~3) +
+               (size_t)warps * PMP_MAX_DOF * (sizeof(double) + 3 * sizeof(float));
+    };
+    bool wsmem = true;
+    const size_t sm_total = 227 * 1024;
+    if (smem_for(256, true) + 1024 <= sm_total / 2 && smem_for(256, true) <= (size_t)ctx->max_smem_optin) {
+        block = 256; per_sm = 2;
+    } else if (smem_for(512, true) <= (size_t)ctx->max_smem_optin) {
+        block = 512; per_sm = 1;
+    } else {
+        wsmem = false; block = 256; per_sm = 2;
+    }
+    const size_t smem = smem_for(block, wsmem);
+    const int warps = block / 32;
+    int grid = (E + warps - 1) / warps;
+    const int cap = ctx->sm_count * per_sm;
+    if (grid > cap) grid = cap;
+    cudaError_t err;
+    PMP_DISPATCH(launch_edge, ctx, a, wsmem, grid, block, smem, (cudaStream_t)stream);
+    if (err != cudaSuccess) return fail(ctx, PMP_E_CUDA, std::string("edge kernel launch: ") + cudaGetErrorString(err));
+    ctx->info.grid = grid; ctx->info.block = block; ctx->info.smem_bytes = (int)smem;
+    ctx->info.worlds_in_smem = wsmem ? 1 : 0; ctx->info.n_sphere_pad = apad; ctx->info.n_slot_pad = nspad;
+    ctx->info.kernel_launches++;
+    return PMP_OK;
+}
+
+extern "C" int pmp_check_configs(pmp_ctx* ctx, const float* q, int32_t B, uint8_t* flags, float* defl, float* theta,
+                                 float* ee, void* stream) {
+    int rc = ready(ctx);
+    if (rc) return rc;
+    if (B < 0) return fail(ctx, PMP_E_INVALID, "bad B");
+    if (B == 0) return PMP_OK;
+    if (!q || !flags) return fail(ctx, PMP_E_INVALID, "q and flags are required");
+    CK(cudaSetDevice(ctx->device));
+    PmpConfigArgs a;
+    a.robot = ctx->d_robot; a.stems = ctx->d_stems; a.n_stems = ctx->d_nstems; a.boxes = ctx->d_boxes;
+    a.n_boxes = ctx->d_nboxes; a.prm = ctx->prm; a.q = q; a.B = B; a.flags = flags; a.defl = defl; a.theta = theta; a.ee = ee;
+    int apad, nspad;
+    pads(ctx, apad, nspad);
+    // small batches (the scalar collision_fn adapter) spread over SMs: 32 threads per CTA
+    const int block = B <= 32 * ctx->sm_count ? 32 : 128;
+    const int grid = (B + block - 1) / block;
+    const size_t smem = sizeof(PmpRobotTab);
+    cudaError_t err;
+    PMP_DISPATCH(launch_config, ctx, a, grid, block, smem, (cudaStream_t)stream);
+    if (err != cudaSuccess) return fail(ctx, PMP_E_CUDA, std::string("config kernel launch: ") + cudaGetErrorString(err));
+    ctx->info.grid = grid; ctx->info.block = block; ctx->info.smem_bytes = (int)smem; ctx->info.worlds_in_smem = 0;
+    ctx->info.n_sphere_pad = apad; ctx->info.n_slot_pad = nspad;
+    ctx->info.kernel_launches++;
+    return PMP_OK;
+}
+
+// ---- host-buffer entry points --------------------------------------------------------------------
+static int ensure_scratch(pmp_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->scratch_bytes) return PMP_OK;
+    cudaFree(ctx->d_scratch);
+    ctx->d_scratch = nullptr; ctx->scratch_bytes = 0;
+    size_t want = bytes + bytes / 4;
+    CK(cudaMalloc(&ctx->d_scratch, want));
+    ctx->scratch_bytes = want;
+    return PMP_OK;
+}
+static size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" int pmp_validate_edges_host(pmp_ctx* ctx, const float* q0, const float* q1, int32_t E, int32_t max_steps,
+                                       int32_t backward, int32_t* first_hit, int32_t* n_steps, float* max_defl,
+                                       float* over, float* ee_len, float* cost, uint32_t* rigid_mask,
+                                       uint32_t* exceed_mask) {
+    int rc = ready(ctx);
+    if (rc) return rc;
+    if (E < 0 || max_steps < 1) return fail(ctx, PMP_E_INVALID, "bad E / max_steps");
+    if (E == 0) return PMP_OK;
+    if (!q0 || !q1 || !first_hit || !n_steps) return fail(ctx, PMP_E_INVALID, "q0, q1, first_hit, n_steps are required");
+    CK(cudaSetDevice(ctx->device));
+    const int D = ctx->h_robot.dof, W = ctx->n_worlds, C = (max_steps + 31) / 32;
+    const size_t bq = up256(sizeof(float) * (size_t)E * D), bi = up256(sizeof(int32_t) * (size_t)E),
+                 bw = up256(sizeof(float) * (size_t)E * W), bm = up256(sizeof(uint32_t) * (size_t)E * W * C);
+    size_t total = 2 * bq + 2 * bi + (max_defl ? bw : 0) + (over ? bw : 0) + (ee_len ? bi : 0) + (cost ? bi : 0) +
+                   (rigid_mask ? bm : 0) + (exceed_mask ? bm : 0);
+    rc = ensure_scratch(ctx, total);
+    if (rc) return rc;
+    char* p = (char*)ctx->d_scratch;
+    auto take = [&](size_t b) { char* r = p; p += b; return r; };
+    float* dq0 = (float*)take(bq); float* dq1 = (float*)take(bq);
+    int32_t* dfh = (int32_t*)take(bi); int32_t* dns = (int32_t*)take(bi);
+    float* dmd = max_defl ? (float*)take(bw) : nullptr;
+    float* dov = over ? (float*)take(bw) : nullptr;
+    float* del = ee_len ? (float*)take(bi) : nullptr;
+    float* dco = cost ? (float*)take(bi) : nullptr;
+    uint32_t* drm = rigid_mask ? (uint32_t*)take(bm) : nullptr;
+    uint32_t* dxm = exceed_mask ? (uint32_t*)take(bm) : nullptr;
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(dq0, q0, sizeof(float) * (size_t)E * D, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dq1, q1, sizeof(float) * (size_t)E * D, cudaMemcpyHostToDevice, st));
+    rc = pmp_validate_edges(ctx, dq0, dq1, E, max_steps, backward, dfh, dns, dmd, dov, del, dco, drm, dxm, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(first_hit, dfh, sizeof(int32_t) * (size_t)E, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(n_steps, dns, sizeof(int32_t) * (size_t)E, cudaMemcpyDeviceToHost, st));
+    if (max_defl) CK(cudaMemcpyAsync(max_defl, dmd, sizeof(float) * (size_t)E * W, cudaMemcpyDeviceToHost, st));
+    if (over) CK(cudaMemcpyAsync(over, dov, sizeof(float) * (size_t)E * W, cudaMemcpyDeviceToHost, st));
+    if (ee_len) CK(cudaMemcpyAsync(ee_len, del, sizeof(float) * (size_t)E, cudaMemcpyDeviceToHost, st));
+    if (cost) CK(cudaMemcpyAsync(cost, dco, sizeof(float) * (size_t)E, cudaMemcpyDeviceToHost, st));
+    if (rigid_mask) CK(cudaMemcpyAsync(rigid_mask, drm, sizeof(uint32_t) * (size_t)E * W * C, cudaMemcpyDeviceToHost, st));
+    if (exceed_mask) CK(cudaMemcpyAsync(exceed_mask, dxm, sizeof(uint32_t) * (size_t)E * W * C, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PMP_OK;
+}
+
+extern "C" int pmp_check_configs_host(pmp_ctx* ctx, const float* q, int32_t B, uint8_t* flags, float* defl,
+                                      float* theta, float* ee) {
+    int rc = ready(ctx);
+    if (rc) return rc;
+    if (B < 0) return fail(ctx, PMP_E_INVALID, "bad B");
+    if (B == 0) return PMP_OK;
+    if (!q || !flags) return fail(ctx, PMP_E_INVALID, "q and flags are required");
+    CK(cudaSetDevice(ctx->device));
+    const int D = ctx->h_robot.dof, W = ctx->n_worlds, P = ctx->max_stems;
+    const size_t bq = up256(sizeof(float) * (size_t)B * D), bf = up256((size_t)B * W),
+                 bd = up256(sizeof(float) * (size_t)B * W * P), be = up256(sizeof(float) * (size_t)B * 3);
+    rc = ensure_scratch(ctx, bq + bf + (defl ? bd : 0) + (theta ? 2 * bd : 0) + (ee ? be : 0));
+    if (rc) return rc;
+    char* p = (char*)ctx->d_scratch;
+    auto take = [&](size_t b) { char* r = p; p += b; return r; };
+    float* dq = (float*)take(bq);
+    uint8_t* dfl = (uint8_t*)take(bf);
+    float* dd = defl ? (float*)take(bd) : nullptr;
+    float* dt = theta ? (float*)take(2 * bd) : nullptr;
+    float* de = ee ? (float*)take(be) : nullptr;
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(dq, q, sizeof(float) * (size_t)B * D, cudaMemcpyHostToDevice, st));
+    rc = pmp_check_configs(ctx, dq, B, dfl, dd, dt, de, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(flags, dfl, (size_t)B * W, cudaMemcpyDeviceToHost, st));
+    if (defl) CK(cudaMemcpyAsync(defl, dd, sizeof(float) * (size_t)B * W * P, cudaMemcpyDeviceToHost, st));
+    if (theta) CK(cudaMemcpyAsync(theta, dt, sizeof(float) * (size_t)B * W * P * 2, cudaMemcpyDeviceToHost, st));
+    if (ee) CK(cudaMemcpyAsync(ee, de, sizeof(float) * (size_t)B * 3, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PMP_OK;
+}
+
+extern "C" int pmp_get_launch_info(pmp_ctx* ctx, pmp_launch_info* out) {
+    if (!ctx || !out) return PMP_E_INVALID;
+    *out = ctx->info;
+    return PMP_OK;
+}
+
+extern "C" int pmp_measure_fp32_peak(pmp_ctx* ctx, int32_t repeats, double* tflops, double* ms) {
+    if (!ctx || !tflops || !ms) return fail(ctx, PMP_E_INVALID, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    const int block = 256, grid = ctx->sm_count * 8, iters = 4096;
+    float* d_out = nullptr;
+    CK(cudaMalloc(&d_out, sizeof(float) * (size_t)grid * block));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    cudaStream_t st = ctx->stream;
+    for (int i = 0; i < 3; ++i) pmp_fma_probe_kernel<<<grid, block, 0, st>>>(d_out, iters, 0.999f, 0.001f);
+    double best = 1e30;
+    if (repeats < 1) repeats = 1;
+    for (int r = 0; r < repeats; ++r) {
+        CK(cudaEventRecord(e0, st));
+        pmp_fma_probe_kernel<<<grid, block, 0, st>>>(d_out, iters, 0.999f, 0.001f);
+        CK(cudaEventRecord(e1, st));
+        CK(cudaEventSynchronize(e1));
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, e0, e1));
+        if (t < best) best = t;
+        ctx->info.kernel_launches++;
+    }
+    CK(cudaGetLastError());
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+    const double flops = 2.0 * 8.0 * 16.0 * (double)iters * (double)grid * block;
+    *ms = best;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    return PMP_OK;
+}

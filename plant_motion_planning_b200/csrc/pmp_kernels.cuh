@@ -1,0 +1,697 @@
+// Edge-validation kernels for sm_100a (FP32 CUDA cores; no tensor cores -- 3x3 transforms and
+// sphere/capsule distances are not dense contractions).
+//
+// Mapping (BASELINE.json north_star): one warp = one edge, lane = interpolation step (32-step chunks);
+// each lane runs the arm FK of its configuration once, keeps the A sphere centres in registers and
+// loops over all W worlds, whose stem tables are staged in shared memory (every lane of every warp
+// reads the same record at the same time -> conflict-free broadcast LDS).  Per-world results are
+// reduced over the 32 steps with warp votes / shuffles and written coalesced (lane = world).
+//
+// The arithmetic is the float32 twin of oracle/edgecheck_oracle.py (float64); every device function
+// names the oracle function it mirrors, and through it the reference lines.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pmp_tables.h"
+
+#define PMP_FULL 0xffffffffu
+#define PMP_FAR 1.0e6f
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pmp_mat_vec(const float* __restrict__ R, float x, float y, float z,
+                                            float& ox, float& oy, float& oz) {
+    ox = fmaf(R[0], x, fmaf(R[1], y, R[2] * z));
+    oy = fmaf(R[3], x, fmaf(R[4], y, R[5] * z));
+    oz = fmaf(R[6], x, fmaf(R[7], y, R[8] * z));
+}
+__device__ __forceinline__ void pmp_matT_vec(const float* __restrict__ R, float x, float y, float z,
+                                             float& ox, float& oy, float& oz) {
+    ox = fmaf(R[0], x, fmaf(R[3], y, R[6] * z));
+    oy = fmaf(R[1], x, fmaf(R[4], y, R[7] * z));
+    oz = fmaf(R[2], x, fmaf(R[5], y, R[8] * z));
+}
+__device__ __forceinline__ void pmp_mat_mul(const float* __restrict__ X, const float* __restrict__ Y,
+                                            float* __restrict__ O) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            O[3 * r + c] = fmaf(X[3 * r + 0], Y[c], fmaf(X[3 * r + 1], Y[3 + c], X[3 * r + 2] * Y[6 + c]));
+    }
+}
+__device__ __forceinline__ float pmp_clamp(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+
+// Sphere (centre c, radius r) against a static primitive: oracle _prim_hit.
+__device__ __forceinline__ bool pmp_prim_hit(int kind, const float* __restrict__ R, const float* __restrict__ t,
+                                             const float* __restrict__ h, float cx, float cy, float cz, float r) {
+    float lx, ly, lz;
+    pmp_matT_vec(R, cx - t[0], cy - t[1], cz - t[2], lx, ly, lz);
+    if (kind == PMP_PRIM_BOX) {
+        float ex = fmaxf(fabsf(lx) - h[0], 0.f), ey = fmaxf(fabsf(ly) - h[1], 0.f), ez = fmaxf(fabsf(lz) - h[2], 0.f);
+        return fmaf(ex, ex, fmaf(ey, ey, ez * ez)) <= r * r;
+    } else if (kind == PMP_PRIM_CYLINDER) {
+        float rho = sqrtf(fmaf(lx, lx, ly * ly));
+        float dr = fmaxf(rho - h[0], 0.f), dz = fmaxf(fabsf(lz) - h[1], 0.f);
+        return fmaf(dr, dr, dz * dz) <= r * r;
+    } else {
+        float rr = r + h[0];
+        return fmaf(lx, lx, fmaf(ly, ly, lz * lz)) <= rr * rr;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-configuration work shared by all worlds: arm FK, sphere centres, limits, self and fixed-obstacle
+// collisions.  Oracle: joint_frames / sphere_centers / ee_positions / rigid_hit
+// (reference: pybullet_tools/utils.py:3753-3762, 3965-4016).
+// QSRC: functor j -> joint value of this lane's configuration.
+// ------------------------------------------------------------------------------------------------
+template <int A, class QSRC>
+__device__ __forceinline__ bool pmp_config_eval(const PmpRobotTab& rt, QSRC qsrc, float (&c)[A][3], float (&ee)[3]) {
+    float R[9], p[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[k] = rt.base_R[k];
+    p[0] = rt.base_t[0]; p[1] = rt.base_t[1]; p[2] = rt.base_t[2];
+    bool hit = false;
+#pragma unroll
+    for (int a = 0; a < A; ++a) { c[a][0] = PMP_FAR; c[a][1] = PMP_FAR; c[a][2] = PMP_FAR; }
+    ee[0] = ee[1] = ee[2] = 0.f;
+    const int D = rt.dof;
+    for (int j = 0; j < D; ++j) {
+        const float qj = qsrc(j);
+        const bool circ = (rt.circular_mask >> j) & 1u;
+        hit |= (!circ) && !(qj >= rt.lower[j] && qj <= rt.upper[j]);
+        float s, co;
+        sincosf(qj, &s, &co);
+        const float* Cj = rt.joint_C + 9 * j;
+        const float* Aj = rt.joint_A + 9 * j;
+        const float* Bj = rt.joint_B + 9 * j;
+        float M[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) M[k] = fmaf(s, Bj[k], fmaf(co, Aj[k], Cj[k]));
+        float tx, ty, tz;
+        pmp_mat_vec(R, rt.joint_t[3 * j], rt.joint_t[3 * j + 1], rt.joint_t[3 * j + 2], tx, ty, tz);
+        p[0] += tx; p[1] += ty; p[2] += tz;
+        float Rn[9];
+        pmp_mat_mul(R, M, Rn);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R[k] = Rn[k];
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            if (a < rt.n_spheres && rt.sph_joint[a] == j) {   // warp-uniform
+                float x, y, z;
+                pmp_mat_vec(R, rt.sph_center[3 * a], rt.sph_center[3 * a + 1], rt.sph_center[3 * a + 2], x, y, z);
+                c[a][0] = x + p[0]; c[a][1] = y + p[1]; c[a][2] = z + p[2];
+            }
+        }
+        if (rt.ee_joint == j) {
+            float x, y, z;
+            pmp_mat_vec(R, rt.ee_local[0], rt.ee_local[1], rt.ee_local[2], x, y, z);
+            ee[0] = x + p[0]; ee[1] = y + p[1]; ee[2] = z + p[2];
+        }
+    }
+    // self collisions: sphere pairs named by the (warp-uniform) pair mask
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        const uint32_t m = (a < rt.n_spheres) ? rt.self_mask[a] : 0u;
+        if (m == 0u) continue;
+#pragma unroll
+        for (int b = a + 1; b < A; ++b) {
+            if ((m >> b) & 1u) {
+                float dx = c[a][0] - c[b][0], dy = c[a][1] - c[b][1], dz = c[a][2] - c[b][2];
+                float rr = rt.sph_radius[a] + rt.sph_radius[b];
+                hit |= fmaf(dx, dx, fmaf(dy, dy, dz * dz)) <= rr * rr;
+            }
+        }
+    }
+    // static primitives (floor, block, robot base geometry)
+    for (int f = 0; f < rt.n_fixed; ++f) {
+        const uint32_t m = rt.fixed_mask[f];
+        const int kind = rt.fixed_kind[f];
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            if ((m >> a) & 1u)
+                hit |= pmp_prim_hit(kind, rt.fixed_R + 9 * f, rt.fixed_t + 3 * f, rt.fixed_half + 3 * f,
+                                    c[a][0], c[a][1], c[a][2], rt.sph_radius[a]);
+        }
+    }
+    return hit;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One (configuration, world) unit: quasi-static plant solve + observers + chain rule.
+// Oracle: plant_equilibrium / raw_deflections / chain_deflections
+// (reference: env.py:127-163,212-219; representation.py:27-51,84-123,220-235,268-294).
+//   wt      : this world's stem records (shared or global memory), n_stems of them
+//   c       : arm sphere centres of this lane's configuration
+//   DETAIL  : also write per-stem deflection / theta (explicit-configuration API)
+// All 32 lanes must call it together (warp votes inside).
+// ------------------------------------------------------------------------------------------------
+struct PmpUnitOut {
+    bool plant_hit;   // arm touches the undeflected plant (avoid_all only)
+    bool exceeded;
+    float max_defl;
+    float over;
+};
+
+template <int A, int NSLOT, bool DETAIL>
+__device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ wt, int n_stems,
+                                                      const float* __restrict__ boxes, int n_boxes,
+                                                      const PmpRobotTab& rt, const PmpKernelParams& prm,
+                                                      const float (&c)[A][3], float* __restrict__ defl_out,
+                                                      float* __restrict__ theta_out) {
+    PmpUnitOut out;
+    out.plant_hit = false; out.exceeded = false; out.max_defl = 0.f; out.over = 0.f;
+    float FR[NSLOT][9], FT[NSLOT][3];
+    bool FM[NSLOT];            // frame moved away from its rest pose (this lane)
+#pragma unroll
+    for (int k = 0; k < NSLOT; ++k) {
+        FM[k] = false;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) FR[k][i] = 0.f;
+        FT[k][0] = FT[k][1] = FT[k][2] = 0.f;
+    }
+    const bool solve = prm.mode == PMP_MODE_OUR_METHOD;
+    const bool dense = prm.dense != 0;
+    const int K = solve ? prm.iterations : 1;
+    float last = 0.f;
+    for (int s = 0; s < n_stems; ++s) {
+        const float* rec = wt + s * PMP_STEM_STRIDE;
+        const int pslot = __float_as_int(rec[PMP_S_PSLOT]);
+        const int oslot = __float_as_int(rec[PMP_S_OSLOT]);
+        const int flags = __float_as_int(rec[PMP_S_FLAGS]);
+        float Rv[9], tv[3];
+        bool moved = false;
+        if (pslot < 0) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Rv[i] = rec[PMP_S_RO + i];
+            tv[0] = rec[PMP_S_TO]; tv[1] = rec[PMP_S_TO + 1]; tv[2] = rec[PMP_S_TO + 2];
+        } else {
+            float Rp[9], tp[3];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Rp[i] = FR[0][i];
+            tp[0] = FT[0][0]; tp[1] = FT[0][1]; tp[2] = FT[0][2];
+            moved = FM[0];
+#pragma unroll
+            for (int k = 1; k < NSLOT; ++k) {
+                if (pslot == k) {   // warp-uniform
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) Rp[i] = FR[k][i];
+                    tp[0] = FT[k][0]; tp[1] = FT[k][1]; tp[2] = FT[k][2];
+                    moved = FM[k];
+                }
+            }
+            float Ro[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Ro[i] = rec[PMP_S_RO + i];
+            pmp_mat_mul(Rp, Ro, Rv);
+            float x, y, z;
+            pmp_mat_vec(Rp, rec[PMP_S_TO], rec[PMP_S_TO + 1], rec[PMP_S_TO + 2], x, y, z);
+            tv[0] = x + tp[0]; tv[1] = y + tp[1]; tv[2] = z + tp[2];
+        }
+        const float z0 = rec[PMP_S_Z0], z1 = rec[PMP_S_Z1], rad = rec[PMP_S_RAD], lim = rec[PMP_S_LIM];
+        float thx = 0.f, thy = 0.f;
+        float cx = 1.f, sx = 0.f, cy = 1.f, sy = 0.f;
+        float ux, uy, uz;
+        for (int it = 0; it < K; ++it) {
+            // stem axis u = Rv (sy, -sx cy, cx cy);  joint axes ax = Rv ex, ay = Rv (0, cx, sx)
+            pmp_mat_vec(Rv, sy, -sx * cy, cx * cy, ux, uy, uz);
+            const float axx = Rv[0], axy = Rv[3], axz = Rv[6];
+            float ayx, ayy, ayz;
+            pmp_mat_vec(Rv, 0.f, cx, sx, ayx, ayy, ayz);
+            // b = axis x u
+            const float bxx = axy * uz - axz * uy, bxy = axz * ux - axx * uz, bxz = axx * uy - axy * ux;
+            const float byx = ayy * uz - ayz * uy, byy = ayz * ux - ayx * uz, byz = ayx * uy - ayy * ux;
+            float Hxx = 0.f, Hxy = 0.f, Hyy = 0.f, gx = 0.f, gy = 0.f, S = 0.f;
+#pragma unroll
+            for (int a = 0; a < A; ++a) {
+                const float wx = c[a][0] - tv[0], wy = c[a][1] - tv[1], wz = c[a][2] - tv[2];
+                const float tau = pmp_clamp(fmaf(wx, ux, fmaf(wy, uy, wz * uz)), z0, z1);
+                const float dx = fmaf(-tau, ux, wx), dy = fmaf(-tau, uy, wy), dz = fmaf(-tau, uz, wz);
+                const float d2 = fmaxf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)), 1e-24f);
+                const float inv = rsqrtf(d2);
+                const float pen = fmaxf((rt.sph_radius[a] + rad) - d2 * inv, 0.f);
+                const float sc = -tau * inv;
+                const float Jx = sc * fmaf(dx, bxx, fmaf(dy, bxy, dz * bxz));
+                const float Jy = sc * fmaf(dx, byx, fmaf(dy, byy, dz * byz));
+                const float pJx = pen * Jx, pJy = pen * Jy;
+                Hxx = fmaf(pJx, Jx, Hxx);
+                Hxy = fmaf(pJx, Jy, Hxy);
+                Hyy = fmaf(pJy, Jy, Hyy);
+                gx = fmaf(pen, pJx, gx);
+                gy = fmaf(pen, pJy, gy);
+                S += pen;
+            }
+            const bool act = S > 0.f;
+            if (!solve) { out.plant_hit |= act; break; }
+            if (!dense && !__any_sync(PMP_FULL, act)) break;   // no lane is pushing this stem: later steps are no-ops
+            const float lam = prm.reg_eps * S;
+            const float a11 = Hxx + lam, a22 = Hyy + lam;
+            const float det = fmaf(a11, a22, -Hxy * Hxy);
+            const float idet = act ? __frcp_rn(det) : 0.f;
+            float dtx = (a22 * gx - Hxy * gy) * idet;
+            float dty = (a11 * gy - Hxy * gx) * idet;
+            dtx = pmp_clamp(dtx, -prm.max_step, prm.max_step);
+            dty = pmp_clamp(dty, -prm.max_step, prm.max_step);
+            thx = pmp_clamp(thx + dtx, -lim, lim);
+            thy = pmp_clamp(thy + dty, -lim, lim);
+            __sincosf(thx, &sx, &cx);
+            __sincosf(thy, &sy, &cy);
+        }
+        const bool bent = (thx != 0.f) || (thy != 0.f);
+        moved |= bent;
+        // final link frame R_s = Rv Rx(thx) Ry(thy)
+        float Rs[9];
+        if (dense || __any_sync(PMP_FULL, bent)) {
+            float M[9];
+            M[0] = cy;       M[1] = 0.f; M[2] = sy;
+            M[3] = sx * sy;  M[4] = cx;  M[5] = -sx * cy;
+            M[6] = -cx * sy; M[7] = sx;  M[8] = cx * cy;
+            pmp_mat_mul(Rv, M, Rs);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Rs[i] = Rv[i];
+        }
+        // observer
+        float raw = 0.f;
+        if (dense || __any_sync(PMP_FULL, moved)) {
+            const float ox = rec[PMP_S_OBSV], oy = rec[PMP_S_OBSV + 1], oz = rec[PMP_S_OBSV + 2];
+            if (flags & PMP_SF_OBS_ANGLE) {
+                // angle between (COM - ref point) and the unit reference direction
+                const float cz_ = rec[PMP_S_COMZ];
+                float vx = fmaf(cz_, Rs[2], tv[0]) - rec[PMP_S_OBSP];
+                float vy = fmaf(cz_, Rs[5], tv[1]) - rec[PMP_S_OBSP + 1];
+                float vz = fmaf(cz_, Rs[8], tv[2]) - rec[PMP_S_OBSP + 2];
+                if (flags & PMP_SF_SNAP) {
+                    if (fabsf(vx) < 1e-5f) vx = 0.f;
+                    if (fabsf(vy) < 1e-5f) vy = 0.f;
+                }
+                const float kx = vy * oz - vz * oy, ky = vz * ox - vx * oz, kz = vx * oy - vy * ox;
+                const float sn = sqrtf(fmaf(kx, kx, fmaf(ky, ky, kz * kz)));
+                const float cs = fmaf(vx, ox, fmaf(vy, oy, vz * oz));
+                raw = atan2f(sn, cs);     // == acos(cos) of the reference, well conditioned near 0
+            } else {
+                float vx, vy, vz;
+                if (flags & PMP_SF_OBS_ROOT) {
+                    pmp_mat_vec(Rs, ox, oy, oz, vx, vy, vz);
+                } else {
+                    float Rp[9];
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) Rp[i] = FR[0][i];
+#pragma unroll
+                    for (int k = 1; k < NSLOT; ++k) {
+                        if (pslot == k) {
+#pragma unroll
+                            for (int i = 0; i < 9; ++i) Rp[i] = FR[k][i];
+                        }
+                    }
+                    float lx, ly, lz;
+                    pmp_matT_vec(Rs, ox, oy, oz, lx, ly, lz);
+                    pmp_mat_vec(Rp, lx, ly, lz, vx, vy, vz);
+                }
+                // third row of the difference rotation -> Bullet's roll / pitch (getEulerFromQuaternion)
+                const float sarg = -vx;
+                float roll, pitch;
+                if (sarg <= -0.99999f) { roll = 0.f; pitch = -1.57079632679f; }
+                else if (sarg >= 0.99999f) { roll = 0.f; pitch = 1.57079632679f; }
+                else { roll = atan2f(vy, vz); pitch = asinf(sarg); }
+                raw = sqrtf(fmaf(roll, roll, pitch * pitch));
+            }
+            if (!moved) raw = 0.f;   // untouched chain: exactly at rest
+        }
+        // chain rule (CharacterizePlant.observe_all)
+        if (flags & PMP_SF_PLANT_START) last = 0.f;
+        const float d = fmaxf(raw - last, 0.f);
+        if (flags & PMP_SF_IS_MAIN) last = d;
+        out.exceeded |= d > prm.deflection_limit;
+        out.max_defl = fmaxf(out.max_defl, d);
+        out.over += fmaxf(d - prm.deflection_limit, 0.f);
+        if (DETAIL) {
+            if (defl_out) defl_out[s] = d;
+            if (theta_out) { theta_out[2 * s] = thx; theta_out[2 * s + 1] = thy; }
+        }
+        // keep the frame for children
+#pragma unroll
+        for (int k = 0; k < NSLOT; ++k) {
+            if (oslot == k) {   // warp-uniform
+#pragma unroll
+                for (int i = 0; i < 9; ++i) FR[k][i] = Rs[i];
+                FT[k][0] = tv[0]; FT[k][1] = tv[1]; FT[k][2] = tv[2];
+                FM[k] = moved;
+            }
+        }
+    }
+    if (prm.mode == PMP_MODE_AVOID_ALL) {
+        // plant base boxes join the obstacle set (env.py:75-77)
+        for (int b = 0; b < n_boxes; ++b) {
+            const float* bx = boxes + b * PMP_BOX_STRIDE;
+#pragma unroll
+            for (int a = 0; a < A; ++a)
+                out.plant_hit |= pmp_prim_hit(PMP_PRIM_BOX, bx, bx + 9, bx + 12, c[a][0], c[a][1], c[a][2],
+                                              rt.sph_radius[a]);
+        }
+    }
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory staging
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pmp_stage_words(void* dst, const void* src, int n_words) {
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (n_words & 3) == 0) {
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        for (int i = threadIdx.x; i < (n_words >> 2); i += blockDim.x) d4[i] = __ldg(s4 + i);
+    } else {
+        for (int i = threadIdx.x; i < n_words; i += blockDim.x) d[i] = __ldg(s + i);
+    }
+}
+
+struct PmpEdgeArgs {
+    const PmpRobotTab* robot;
+    const float* stems;        // [W, max_stems, STRIDE]
+    const int32_t* n_stems;    // [W]
+    const float* boxes;        // [W, max_boxes, BOX_STRIDE]
+    const int32_t* n_boxes;    // [W]
+    PmpKernelParams prm;
+    const float* q0;           // [E, D]
+    const float* q1;           // [E, D]
+    int32_t E;
+    int32_t max_steps;
+    int32_t backward;
+    int32_t* first_hit;        // [E]
+    int32_t* n_steps;          // [E]
+    float* max_defl;           // [E, W] or null
+    float* over;               // [E, W] or null
+    float* ee_len;             // [E] or null
+    float* cost;               // [E] or null
+    uint32_t* rigid_mask;      // [E, W, C] or null
+    uint32_t* exceed_mask;     // [E, W, C] or null
+};
+
+// Edge-batch kernel.  Persistent CTAs; warp = edge, lane = step.
+template <int A, int NSLOT, bool WSMEM>
+__global__ void __launch_bounds__(512, 1) pmp_edge_kernel(const PmpEdgeArgs args) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PmpRobotTab& rt = *reinterpret_cast<PmpRobotTab*>(smem_raw);
+    float* sm_stems = reinterpret_cast<float*>(smem_raw + sizeof(PmpRobotTab));
+    const PmpKernelParams prm = args.prm;
+    const int W = prm.n_worlds;
+    const int stem_words = WSMEM ? W * prm.max_stems * PMP_STEM_STRIDE : 0;
+    int32_t* sm_nstems = reinterpret_cast<int32_t*>(sm_stems + stem_words);
+    const int nstem_words = (W + 3) & ~3;
+    // per-warp staging: q0[16] q1[16] dq[16] floats + sq[16] doubles
+    const int warps = blockDim.x >> 5;
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* sm_sq_all = reinterpret_cast<double*>(sm_nstems + nstem_words);
+    float* sm_q_all = reinterpret_cast<float*>(sm_sq_all + warps * PMP_MAX_DOF);
+    double* sm_sq = sm_sq_all + wid * PMP_MAX_DOF;
+    float* sm_q0 = sm_q_all + wid * (3 * PMP_MAX_DOF);
+    float* sm_q1 = sm_q0 + PMP_MAX_DOF;
+    float* sm_dq = sm_q1 + PMP_MAX_DOF;
+
+    pmp_stage_words(&rt, args.robot, sizeof(PmpRobotTab) / 4);
+    if (WSMEM) pmp_stage_words(sm_stems, args.stems, stem_words);
+    for (int i = threadIdx.x; i < W; i += blockDim.x) sm_nstems[i] = args.n_stems[i];
+    __syncthreads();
+
+    const int D = rt.dof;
+    const int C = (args.max_steps + 31) >> 5;
+    const int total_warps = gridDim.x * warps;
+    const float* stems_base = WSMEM ? sm_stems : args.stems;
+
+    for (int e = blockIdx.x * warps + wid; e < args.E; e += total_warps) {
+        // ---- interpolation set-up: oracle num_steps / edge_configs (pybullet_tools/utils.py:3604-3676) ----
+        __syncwarp();
+        if (lane < D) {
+            const float a = args.q0[(size_t)e * D + lane], b = args.q1[(size_t)e * D + lane];
+            double d = __dsub_rn((double)b, (double)a);
+            if ((rt.circular_mask >> lane) & 1u) {
+                const double two_pi = 6.283185307179586, pi = 3.141592653589793;
+                double x = d + pi;
+                x = x - two_pi * floor(x / two_pi);
+                d = x - pi;
+            }
+            const double v = __ddiv_rn(d, prm.resolution);
+            sm_sq[lane] = __dmul_rn(v, v);
+            sm_q0[lane] = a; sm_q1[lane] = b; sm_dq[lane] = (float)d;
+        }
+        __syncwarp();
+        double ssum = 0.0;
+        for (int j = 0; j < D; ++j) ssum = __dadd_rn(ssum, sm_sq[j]);
+        const double nd = floor(__dsqrt_rn(ssum));
+        const int n = (nd > 1.0e6 ? 1000000 : (int)nd) + 1;
+        const int nc = min(n, args.max_steps);
+        const int off = args.backward ? 0 : 1;
+        const float inv_n = 1.0f / (float)n;
+
+        int first = nc;
+        float ee_sum = 0.f, over_sum = 0.f;
+        float pe[3];   // end-effector point preceding this chunk's first step
+        {
+            float c0[A][3], e0[3];
+            pmp_config_eval<A>(rt, [&](int j) { return sm_q0[j]; }, c0, e0);
+            pe[0] = e0[0]; pe[1] = e0[1]; pe[2] = e0[2];
+        }
+        for (int base = 0, chunk = 0; base < nc; base += 32, ++chunk) {
+            const int i = base + lane;
+            const bool live = i < nc;
+            const int num = i + off;
+            const float t = (float)num * inv_n;
+            const bool at_end = (num == n);
+            float c[A][3], ee[3];
+            const uint32_t circ = rt.circular_mask;
+            bool rigid0 = pmp_config_eval<A>(
+                rt,
+                [&](int j) {
+                    return (at_end && !((circ >> j) & 1u)) ? sm_q1[j] : fmaf(sm_dq[j], t, sm_q0[j]);
+                },
+                c, ee);
+            rigid0 &= live;
+            if (!live) {
+#pragma unroll
+                for (int a = 0; a < A; ++a) { c[a][0] = PMP_FAR; c[a][1] = PMP_FAR; c[a][2] = PMP_FAR; }
+            }
+            // end-effector path length (kuka_primitives.py:504-508)
+            {
+                float px = __shfl_up_sync(PMP_FULL, ee[0], 1), py = __shfl_up_sync(PMP_FULL, ee[1], 1),
+                      pz = __shfl_up_sync(PMP_FULL, ee[2], 1);
+                if (lane == 0) { px = pe[0]; py = pe[1]; pz = pe[2]; }
+                const float dx = ee[0] - px, dy = ee[1] - py, dz = ee[2] - pz;
+                float seg = live ? sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz))) : 0.f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) seg += __shfl_xor_sync(PMP_FULL, seg, o);
+                ee_sum += seg;
+                pe[0] = __shfl_sync(PMP_FULL, ee[0], 31); pe[1] = __shfl_sync(PMP_FULL, ee[1], 31);
+                pe[2] = __shfl_sync(PMP_FULL, ee[2], 31);
+            }
+            const uint32_t rigid0_mask = __ballot_sync(PMP_FULL, rigid0);
+            uint32_t viol = rigid0_mask;
+            uint32_t keep_r = 0, keep_x = 0;
+            float keep_m = 0.f, keep_o = 0.f;
+            for (int w = 0; w < W; ++w) {
+                PmpUnitOut u;
+                u.plant_hit = false; u.exceeded = false; u.max_defl = 0.f; u.over = 0.f;
+                if (prm.mode != PMP_MODE_IGNORE_ALL) {
+                    u = pmp_world_eval<A, NSLOT, false>(
+                        stems_base + (size_t)w * prm.max_stems * PMP_STEM_STRIDE, sm_nstems[w],
+                        args.boxes + (size_t)w * prm.max_boxes * PMP_BOX_STRIDE,
+                        prm.mode == PMP_MODE_AVOID_ALL ? args.n_boxes[w] : 0, rt, prm, c, nullptr, nullptr);
+                }
+                const uint32_t rm = rigid0_mask | __ballot_sync(PMP_FULL, live && u.plant_hit);
+                const uint32_t xm = __ballot_sync(PMP_FULL, live && u.exceeded);
+                viol |= rm | xm;
+                const float md = __uint_as_float(__reduce_max_sync(PMP_FULL, __float_as_uint(live ? u.max_defl : 0.f)));
+                float ov = live ? u.over : 0.f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) ov += __shfl_xor_sync(PMP_FULL, ov, o);
+                over_sum += ov;
+                if ((w & 31) == lane) { keep_r = rm; keep_x = xm; keep_m = md; keep_o = ov; }
+                if ((w & 31) == 31 || w == W - 1) {
+                    const int ww = (w & ~31) + lane;
+                    if (ww <= w) {
+                        const size_t ew = (size_t)e * W + ww;
+                        if (args.rigid_mask) args.rigid_mask[ew * C + chunk] = keep_r;
+                        if (args.exceed_mask) args.exceed_mask[ew * C + chunk] = keep_x;
+                        if (args.max_defl) args.max_defl[ew] = chunk ? fmaxf(args.max_defl[ew], keep_m) : keep_m;
+                        if (args.over) args.over[ew] = chunk ? args.over[ew] + keep_o : keep_o;
+                    }
+                }
+            }
+            if (viol && first == nc) first = base + __ffs(viol) - 1;
+        }
+        // zero the mask words of chunks this edge did not reach
+        if (args.rigid_mask || args.exceed_mask) {
+            const int used = (nc + 31) >> 5;
+            for (int idx = lane; idx < W * (C - used); idx += 32) {
+                const int ww = idx / (C - used), ch = used + idx % (C - used);
+                const size_t o = ((size_t)e * W + ww) * C + ch;
+                if (args.rigid_mask) args.rigid_mask[o] = 0u;
+                if (args.exceed_mask) args.exceed_mask[o] = 0u;
+            }
+        }
+        if (lane == 0) {
+            args.first_hit[e] = first;
+            args.n_steps[e] = n;
+            if (args.ee_len) args.ee_len[e] = ee_sum;
+            if (args.cost) args.cost[e] = fmaf(prm.alpha, over_sum / (float)W, ee_sum);
+        }
+    }
+}
+
+struct PmpConfigArgs {
+    const PmpRobotTab* robot;
+    const float* stems;
+    const int32_t* n_stems;
+    const float* boxes;
+    const int32_t* n_boxes;
+    PmpKernelParams prm;
+    const float* q;            // [B, D]
+    int32_t B;
+    uint8_t* flags;            // [B, W]
+    float* defl;               // [B, W, max_stems] or null
+    float* theta;              // [B, W, max_stems, 2] or null
+    float* ee;                 // [B, 3] or null
+};
+
+// Explicit-configuration kernel: thread = configuration, all worlds.  Parity / scalar-adapter path.
+template <int A, int NSLOT>
+__global__ void __launch_bounds__(128, 2) pmp_config_kernel(const PmpConfigArgs args) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PmpRobotTab& rt = *reinterpret_cast<PmpRobotTab*>(smem_raw);
+    pmp_stage_words(&rt, args.robot, sizeof(PmpRobotTab) / 4);
+    __syncthreads();
+    const PmpKernelParams prm = args.prm;
+    const int W = prm.n_worlds, D = rt.dof, P = prm.max_stems;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = b < args.B;
+    const int bb = live ? b : 0;
+    float c[A][3], ee[3];
+    const float* q = args.q + (size_t)bb * D;
+    bool rigid0 = pmp_config_eval<A>(rt, [&](int j) { return __ldg(q + j); }, c, ee);
+    if (!live) {
+#pragma unroll
+        for (int a = 0; a < A; ++a) { c[a][0] = PMP_FAR; c[a][1] = PMP_FAR; c[a][2] = PMP_FAR; }
+    }
+    if (live && args.ee) { args.ee[3 * b] = ee[0]; args.ee[3 * b + 1] = ee[1]; args.ee[3 * b + 2] = ee[2]; }
+    for (int w = 0; w < W; ++w) {
+        PmpUnitOut u;
+        u.plant_hit = false; u.exceeded = false; u.max_defl = 0.f; u.over = 0.f;
+        const size_t bw = (size_t)bb * W + w;
+        float* dptr = (live && args.defl) ? args.defl + bw * P : nullptr;
+        float* tptr = (live && args.theta) ? args.theta + bw * P * 2 : nullptr;
+        const int ns = args.n_stems[w];
+        if (prm.mode != PMP_MODE_IGNORE_ALL) {
+            u = pmp_world_eval<A, NSLOT, true>(args.stems + (size_t)w * P * PMP_STEM_STRIDE, ns,
+                                               args.boxes + (size_t)w * prm.max_boxes * PMP_BOX_STRIDE,
+                                               prm.mode == PMP_MODE_AVOID_ALL ? args.n_boxes[w] : 0, rt, prm, c, dptr, tptr);
+        } else {
+            for (int s = 0; s < ns; ++s) {
+                if (dptr) dptr[s] = 0.f;
+                if (tptr) { tptr[2 * s] = 0.f; tptr[2 * s + 1] = 0.f; }
+            }
+        }
+        for (int s = ns; s < P; ++s) {
+            if (dptr) dptr[s] = 0.f;
+            if (tptr) { tptr[2 * s] = 0.f; tptr[2 * s + 1] = 0.f; }
+        }
+        if (live)
+            args.flags[bw] = (uint8_t)(((rigid0 || u.plant_hit) ? PMP_FLAG_RIGID : 0) | (u.exceeded ? PMP_FLAG_EXCEEDED : 0));
+    }
+}
+
+// Batched FK: thread = configuration.  Oracle link_poses (pybullet_tools/utils.py:2197-2203).
+__device__ __forceinline__ void pmp_mat_to_quat(const float* m, float* q) {
+    const float t = m[0] + m[4] + m[8];
+    float x, y, z, w;
+    if (t > 0.f) {
+        float s = sqrtf(t + 1.f) * 2.f;
+        x = (m[7] - m[5]) / s; y = (m[2] - m[6]) / s; z = (m[3] - m[1]) / s; w = 0.25f * s;
+    } else if (m[0] > m[4] && m[0] > m[8]) {
+        float s = sqrtf(1.f + m[0] - m[4] - m[8]) * 2.f;
+        x = 0.25f * s; y = (m[1] + m[3]) / s; z = (m[2] + m[6]) / s; w = (m[7] - m[5]) / s;
+    } else if (m[4] > m[8]) {
+        float s = sqrtf(1.f + m[4] - m[0] - m[8]) * 2.f;
+        x = (m[1] + m[3]) / s; y = 0.25f * s; z = (m[5] + m[7]) / s; w = (m[2] - m[6]) / s;
+    } else {
+        float s = sqrtf(1.f + m[8] - m[0] - m[4]) * 2.f;
+        x = (m[2] + m[6]) / s; y = (m[5] + m[7]) / s; z = 0.25f * s; w = (m[3] - m[1]) / s;
+    }
+    if (w < 0.f) { x = -x; y = -y; z = -z; w = -w; }
+    q[0] = x; q[1] = y; q[2] = z; q[3] = w;
+}
+
+__device__ __forceinline__ void pmp_emit_link(const PmpLinkTab& lt, int l, const float* R, const float* p, size_t b,
+                                              float* pos, float* quat, float* com) {
+    const int L = lt.n_links;
+    float Rl[9];
+    pmp_mat_mul(R, lt.link_R + 9 * l, Rl);
+    float x, y, z;
+    pmp_mat_vec(R, lt.link_t[3 * l], lt.link_t[3 * l + 1], lt.link_t[3 * l + 2], x, y, z);
+    x += p[0]; y += p[1]; z += p[2];
+    const size_t o = b * L + l;
+    if (pos) { pos[3 * o] = x; pos[3 * o + 1] = y; pos[3 * o + 2] = z; }
+    if (quat) pmp_mat_to_quat(Rl, quat + 4 * o);
+    if (com) {
+        float cx, cy, cz;
+        pmp_mat_vec(Rl, lt.link_com[3 * l], lt.link_com[3 * l + 1], lt.link_com[3 * l + 2], cx, cy, cz);
+        com[3 * o] = cx + x; com[3 * o + 1] = cy + y; com[3 * o + 2] = cz + z;
+    }
+}
+
+__global__ void __launch_bounds__(128) pmp_fk_kernel(const PmpRobotTab* __restrict__ robot,
+                                                      const PmpLinkTab* __restrict__ links,
+                                                      const float* __restrict__ q, int B, float* pos, float* quat,
+                                                      float* com) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PmpRobotTab& rt = *reinterpret_cast<PmpRobotTab*>(smem_raw);
+    PmpLinkTab& lt = *reinterpret_cast<PmpLinkTab*>(smem_raw + sizeof(PmpRobotTab));
+    pmp_stage_words(&rt, robot, sizeof(PmpRobotTab) / 4);
+    pmp_stage_words(&lt, links, sizeof(PmpLinkTab) / 4);
+    __syncthreads();
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float R[9], p[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[k] = rt.base_R[k];
+    p[0] = rt.base_t[0]; p[1] = rt.base_t[1]; p[2] = rt.base_t[2];
+    const int L = lt.n_links, D = rt.dof;
+    for (int l = 0; l < L; ++l)
+        if (lt.link_joint[l] < 0) pmp_emit_link(lt, l, R, p, b, pos, quat, com);
+    for (int j = 0; j < D; ++j) {
+        const float qj = q[(size_t)b * D + j];
+        float s, co;
+        sincosf(qj, &s, &co);
+        float M[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+            M[k] = fmaf(s, rt.joint_B[9 * j + k], fmaf(co, rt.joint_A[9 * j + k], rt.joint_C[9 * j + k]));
+        float tx, ty, tz;
+        pmp_mat_vec(R, rt.joint_t[3 * j], rt.joint_t[3 * j + 1], rt.joint_t[3 * j + 2], tx, ty, tz);
+        p[0] += tx; p[1] += ty; p[2] += tz;
+        float Rn[9];
+        pmp_mat_mul(R, M, Rn);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R[k] = Rn[k];
+        for (int l = 0; l < L; ++l)
+            if (lt.link_joint[l] == j) pmp_emit_link(lt, l, R, p, b, pos, quat, com);
+    }
+}
+
+// FP32 FMA-pipe probe: 8 independent dependent-FMA chains per thread.
+__global__ void __launch_bounds__(256) pmp_fma_probe_kernel(float* out, int iters, float a, float b) {
+    float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f,
+          x6 = x0 + 6.f, x7 = x0 + 7.f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    const float r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (r == 12345.678f) out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}

@@ -1,0 +1,296 @@
+"""EdgeChecker: the batched edge-validation engine (PyTorch tensors in, PyTorch tensors out).
+
+Host side of the hot path named in BASELINE.json: owns one C-ABI context (robot + obstacle tables,
+sampled plant worlds, constants) and launches the sm_100a kernels on torch's current stream.
+PyTorch is plumbing only (device memory, streams); all arithmetic is in csrc/.
+
+Additive batched surface:
+    validate_edges(q_from[E,D], q_to[E,D]) -> first_hit[E], n_steps[E], max_deflection[E,W],
+                                              over_limit[E,W], ee_len[E], cost[E], optional step masks
+    check_configs(q[B,D])                  -> flags[B,W], deflection[B,W,P], theta[B,W,P,2], ee[B,3]
+    fk(q[B,D])                             -> link positions / quaternions / COM positions
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, replace
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _capi
+from .model.plants import PlantWorld
+from .model.robot import FixedPrim, RobotModel
+from .model.tables import MODES, RobotTables, WorldTables, pack_robot, pack_worlds
+
+FLAG_RIGID = 1
+FLAG_EXCEEDED = 2
+
+
+@dataclass(frozen=True)
+class EdgeCheckConfig:
+    """Constants the reference hard-codes ("Config / flags")."""
+    resolution: float = math.radians(3)   # DEFAULT_RESOLUTION, pybullet_tools/utils.py:3660
+    deflection_limit: float = 0.30        # scripts/*: 0.30; multi_world_our_method.py: 2.0
+    alpha: float = 0.1                    # kuka_primitives.py:476
+    iterations: int = 4                   # Gauss-Newton steps of the quasi-static plant solve
+    max_step: float = 0.5                 # rad per step
+    reg_eps: float = 1e-4                 # m^2
+    stem_radius: Optional[float] = None   # None = area-equivalent capsule of the stem box
+    mode: str = "our_method"              # our_method | avoid_all | ignore_all
+    gate_probability: float = 0.95        # pybullet_tools/utils.py:3843 (applied by the host adapters only)
+    max_steps: int = 320                  # per-edge step capacity of validate_edges
+    dense: bool = False                   # disable data-dependent early exits (roofline measurements)
+
+
+@dataclass
+class EdgeBatchResult:
+    first_hit: "torch.Tensor"        # int32 [E]
+    n_steps: "torch.Tensor"          # int32 [E]
+    max_deflection: "torch.Tensor"   # float32 [E, W]
+    over_limit: "torch.Tensor"       # float32 [E, W]
+    ee_len: "torch.Tensor"           # float32 [E]
+    cost: "torch.Tensor"             # float32 [E]
+    rigid_mask: Optional["torch.Tensor"] = None    # uint32 as int32 [E, W, C]
+    exceed_mask: Optional["torch.Tensor"] = None
+
+    @property
+    def valid(self):
+        """True where the whole edge is free (success of extend_towards, primitives.py:254)."""
+        return self.first_hit >= self.n_steps
+
+
+@dataclass
+class ConfigBatchResult:
+    flags: "torch.Tensor"            # uint8 [B, W]  FLAG_RIGID | FLAG_EXCEEDED
+    deflection: "torch.Tensor"       # float32 [B, W, P]
+    theta: "torch.Tensor"            # float32 [B, W, P, 2]
+    ee: "torch.Tensor"               # float32 [B, 3]
+
+
+class EdgeChecker:
+    def __init__(self, robot: RobotModel, worlds: Sequence[PlantWorld],
+                 config: Optional[EdgeCheckConfig] = None,
+                 obstacles: Optional[Sequence[FixedPrim]] = None, device: int = 0):
+        self._lib = _capi.load()
+        self._ctx = C.c_void_p()
+        self.device_index = int(device)
+        rc = self._lib.pmp_create(C.byref(self._ctx), self.device_index)
+        if rc != 0:
+            msg = self._lib.pmp_last_error(None).decode()
+            self._ctx = C.c_void_p()
+            raise RuntimeError(f"pmp_create failed ({rc}): {msg}")
+        self.robot = robot
+        self.obstacles = obstacles
+        self.config = config or EdgeCheckConfig()
+        self._set_robot(robot, obstacles)
+        self.set_worlds(worlds)
+        self._push_params()
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc: int, what: str) -> None:
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): {self._lib.pmp_last_error(self._ctx).decode()}")
+
+    def close(self) -> None:
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self._lib.pmp_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _set_robot(self, robot: RobotModel, obstacles) -> None:
+        t: RobotTables = pack_robot(robot, obstacles)
+        self.robot_tables = t
+        d = _capi.RobotDesc()
+        d.dof, d.n_spheres, d.n_links, d.n_fixed = t.dof, t.n_spheres, t.n_links, t.n_fixed
+        d.joint_C, d.joint_A, d.joint_B = _capi.fptr(t.joint_C), _capi.fptr(t.joint_A), _capi.fptr(t.joint_B)
+        d.joint_t, d.lower, d.upper = _capi.fptr(t.joint_t), _capi.fptr(t.lower), _capi.fptr(t.upper)
+        d.circular = _capi.bptr(t.circular)
+        d.base_R, d.base_t = _capi.fptr(t.base_R), _capi.fptr(t.base_t)
+        d.sph_joint, d.sph_center = _capi.iptr(t.sph_joint), _capi.fptr(t.sph_center)
+        d.sph_radius, d.self_mask = _capi.fptr(t.sph_radius), _capi.uptr(t.self_mask)
+        d.link_joint, d.link_R = _capi.iptr(t.link_joint), _capi.fptr(t.link_R)
+        d.link_t, d.link_com = _capi.fptr(t.link_t), _capi.fptr(t.link_com)
+        d.ee_joint = t.ee_joint
+        d.ee_local = (C.c_float * 3)(*[float(v) for v in t.ee_local])
+        d.fixed_kind, d.fixed_R = _capi.iptr(t.fixed_kind), _capi.fptr(t.fixed_R)
+        d.fixed_t, d.fixed_half = _capi.fptr(t.fixed_t), _capi.fptr(t.fixed_half)
+        d.fixed_mask = _capi.uptr(t.fixed_mask)
+        self._check(self._lib.pmp_set_robot(self._ctx, C.byref(d)), "pmp_set_robot")
+
+    def set_worlds(self, worlds: Sequence[PlantWorld]) -> None:
+        self.worlds: List[PlantWorld] = list(worlds)
+        wt: WorldTables = pack_worlds(self.worlds, self.config.stem_radius)
+        self.world_tables = wt
+        d = _capi.WorldDesc()
+        d.n_worlds, d.max_stems, d.max_boxes, d.n_slots = wt.n_worlds, wt.max_stems, wt.max_boxes, wt.n_slots
+        stems = np.ascontiguousarray(wt.stems.reshape(-1))
+        boxes = np.ascontiguousarray(wt.boxes.reshape(-1))
+        d.n_stems, d.stems = _capi.iptr(wt.n_stems), _capi.fptr(stems)
+        d.n_boxes, d.boxes = _capi.iptr(wt.n_boxes), _capi.fptr(boxes)
+        self._check(self._lib.pmp_set_worlds(self._ctx, C.byref(d)), "pmp_set_worlds")
+
+    def _push_params(self) -> None:
+        c = self.config
+        if c.mode not in MODES:
+            raise ValueError(f"mode must be one of {sorted(MODES)}")
+        p = _capi.Params(c.resolution, c.deflection_limit, c.alpha, c.max_step, c.reg_eps, c.iterations,
+                         MODES[c.mode], 1 if c.dense else 0, 0)
+        self._check(self._lib.pmp_set_params(self._ctx, C.byref(p)), "pmp_set_params")
+
+    def set_config(self, **changes) -> None:
+        """Replace constants (e.g. mode='avoid_all', deflection_limit=2.0)."""
+        old = self.config
+        self.config = replace(self.config, **changes)
+        if self.config.stem_radius != old.stem_radius:
+            self.set_worlds(self.worlds)
+        self._push_params()
+
+    # ------------------------------------------------------------------ properties
+    @property
+    def dof(self) -> int:
+        return self.robot.dof
+
+    @property
+    def num_worlds(self) -> int:
+        return self.world_tables.n_worlds
+
+    @property
+    def max_stems(self) -> int:
+        return self.world_tables.max_stems
+
+    @property
+    def num_links(self) -> int:
+        return self.robot.num_links
+
+    def launch_info(self) -> dict:
+        info = _capi.LaunchInfo()
+        self._check(self._lib.pmp_get_launch_info(self._ctx, C.byref(info)), "pmp_get_launch_info")
+        return {k: int(getattr(info, k)) for k, _ in info._fields_}
+
+    def measure_fp32_peak(self, repeats: int = 5):
+        tf, ms = C.c_double(), C.c_double()
+        self._check(self._lib.pmp_measure_fp32_peak(self._ctx, repeats, C.byref(tf), C.byref(ms)),
+                    "pmp_measure_fp32_peak")
+        return tf.value, ms.value
+
+    # ------------------------------------------------------------------ device API (torch)
+    def _torch(self):
+        import torch
+        return torch
+
+    def _dev(self):
+        return self._torch().device("cuda", self.device_index)
+
+    def _prep(self, q, name: str):
+        torch = self._torch()
+        if not isinstance(q, torch.Tensor):
+            q = torch.as_tensor(np.asarray(q, dtype=np.float32))
+        if q.dim() == 1:
+            q = q[None]
+        if q.dim() != 2 or q.shape[1] != self.dof:
+            raise ValueError(f"{name} must be [N, {self.dof}]")
+        return q.to(device=self._dev(), dtype=torch.float32).contiguous()
+
+    def _stream(self):
+        return C.c_void_p(self._torch().cuda.current_stream(self._dev()).cuda_stream)
+
+    @staticmethod
+    def _p(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p()
+
+    def fk(self, q):
+        """Link frames for a batch of configurations: (pos [B,L,3], quat xyzw [B,L,4], com [B,L,3])."""
+        torch = self._torch()
+        q = self._prep(q, "q")
+        B, L = q.shape[0], self.num_links
+        with torch.cuda.device(self._dev()):
+            pos = torch.empty((B, L, 3), device=q.device, dtype=torch.float32)
+            quat = torch.empty((B, L, 4), device=q.device, dtype=torch.float32)
+            com = torch.empty((B, L, 3), device=q.device, dtype=torch.float32)
+            self._check(self._lib.pmp_fk(self._ctx, self._p(q), B, self._p(pos), self._p(quat), self._p(com),
+                                         self._stream()), "pmp_fk")
+        return pos, quat, com
+
+    def check_configs(self, q, detail: bool = True) -> ConfigBatchResult:
+        torch = self._torch()
+        q = self._prep(q, "q")
+        B, W, P = q.shape[0], self.num_worlds, self.max_stems
+        with torch.cuda.device(self._dev()):
+            flags = torch.empty((B, W), device=q.device, dtype=torch.uint8)
+            defl = torch.empty((B, W, P), device=q.device, dtype=torch.float32) if detail else None
+            theta = torch.empty((B, W, P, 2), device=q.device, dtype=torch.float32) if detail else None
+            ee = torch.empty((B, 3), device=q.device, dtype=torch.float32)
+            self._check(self._lib.pmp_check_configs(self._ctx, self._p(q), B, self._p(flags), self._p(defl),
+                                                    self._p(theta), self._p(ee), self._stream()),
+                        "pmp_check_configs")
+        return ConfigBatchResult(flags, defl, theta, ee)
+
+    def validate_edges(self, q_from, q_to, backward: bool = False, want_masks: bool = False,
+                       max_steps: Optional[int] = None, out: Optional[EdgeBatchResult] = None) -> EdgeBatchResult:
+        torch = self._torch()
+        q0 = self._prep(q_from, "q_from")
+        q1 = self._prep(q_to, "q_to")
+        if q0.shape != q1.shape:
+            raise ValueError("q_from and q_to must have the same shape")
+        E, W = q0.shape[0], self.num_worlds
+        ms = int(max_steps or self.config.max_steps)
+        Cw = (ms + 31) // 32
+        with torch.cuda.device(self._dev()):
+            if out is None:
+                mk = lambda shape, dt: torch.empty(shape, device=q0.device, dtype=dt)
+                out = EdgeBatchResult(mk((E,), torch.int32), mk((E,), torch.int32), mk((E, W), torch.float32),
+                                      mk((E, W), torch.float32), mk((E,), torch.float32), mk((E,), torch.float32))
+                if want_masks:
+                    out.rigid_mask = mk((E, W, Cw), torch.int32)
+                    out.exceed_mask = mk((E, W, Cw), torch.int32)
+            self._check(self._lib.pmp_validate_edges(
+                self._ctx, self._p(q0), self._p(q1), E, ms, 1 if backward else 0, self._p(out.first_hit),
+                self._p(out.n_steps), self._p(out.max_deflection), self._p(out.over_limit), self._p(out.ee_len),
+                self._p(out.cost), self._p(out.rigid_mask), self._p(out.exceed_mask), self._stream()),
+                "pmp_validate_edges")
+        return out
+
+    # ------------------------------------------------------------------ host API (numpy; the C-ABI *_host calls)
+    def validate_edges_host(self, q_from: np.ndarray, q_to: np.ndarray, backward: bool = False,
+                            want_masks: bool = False, max_steps: Optional[int] = None, out: Optional[dict] = None) -> dict:
+        """HOST buffers in, HOST buffers out: H2D, kernel, D2H and the synchronisation happen inside the
+        C-ABI call -- the entry a CPU-side planner uses."""
+        q0 = np.ascontiguousarray(q_from, dtype=np.float32).reshape(-1, self.dof)
+        q1 = np.ascontiguousarray(q_to, dtype=np.float32).reshape(-1, self.dof)
+        E, W = q0.shape[0], self.num_worlds
+        ms = int(max_steps or self.config.max_steps)
+        Cw = (ms + 31) // 32
+        if out is None:
+            out = {
+                "first_hit": np.empty(E, np.int32), "n_steps": np.empty(E, np.int32),
+                "max_deflection": np.empty((E, W), np.float32), "over_limit": np.empty((E, W), np.float32),
+                "ee_len": np.empty(E, np.float32), "cost": np.empty(E, np.float32),
+            }
+            if want_masks:
+                out["rigid_mask"] = np.empty((E, W, Cw), np.uint32)
+                out["exceed_mask"] = np.empty((E, W, Cw), np.uint32)
+        vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p()
+        self._check(self._lib.pmp_validate_edges_host(
+            self._ctx, vp(q0), vp(q1), E, ms, 1 if backward else 0, vp(out["first_hit"]), vp(out["n_steps"]),
+            vp(out["max_deflection"]), vp(out["over_limit"]), vp(out["ee_len"]), vp(out["cost"]),
+            vp(out.get("rigid_mask")), vp(out.get("exceed_mask"))), "pmp_validate_edges_host")
+        return out
+
+    def check_configs_host(self, q: np.ndarray, detail: bool = True) -> dict:
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.dof)
+        B, W, P = q.shape[0], self.num_worlds, self.max_stems
+        out = {"flags": np.empty((B, W), np.uint8), "ee": np.empty((B, 3), np.float32)}
+        if detail:
+            out["deflection"] = np.empty((B, W, P), np.float32)
+            out["theta"] = np.empty((B, W, P, 2), np.float32)
+        vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p()
+        self._check(self._lib.pmp_check_configs_host(self._ctx, vp(q), B, vp(out["flags"]), vp(out.get("deflection")),
+                                                     vp(out.get("theta")), vp(out["ee"])), "pmp_check_configs_host")
+        return out
