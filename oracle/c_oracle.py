@@ -1,0 +1,121 @@
+"""ctypes loader for the C twin of the oracle (oracle/edgecheck_oracle.c).   *** TEST INFRASTRUCTURE ***
+
+Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) may import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional, Sequence
+
+import numpy as np
+
+from plant_motion_planning_b200 import _capi
+from plant_motion_planning_b200.model.tables import MODES, pack_robot, pack_worlds
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_build", "liboracle_edgecheck.so")
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(HERE, "edgecheck_oracle.c")
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
+        # -march=native binaries are rebuilt on the machine that runs them when possible
+        subprocess.run(["make", "-C", HERE, "-B"], check=True, capture_output=True)
+    return LIB
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            build()
+        try:
+            _lib = C.CDLL(LIB)
+        except OSError:
+            build(force=True)
+            _lib = C.CDLL(LIB)
+        vp = C.c_void_p
+        _lib.pmp_oracle_validate_edges.argtypes = [C.POINTER(_capi.RobotDesc), C.POINTER(_capi.WorldDesc),
+                                                   C.POINTER(_capi.Params), vp, vp, C.c_int32, C.c_int32, C.c_int32] + \
+            [vp] * 8 + [C.c_int32]
+        _lib.pmp_oracle_check_configs.argtypes = [C.POINTER(_capi.RobotDesc), C.POINTER(_capi.WorldDesc),
+                                                  C.POINTER(_capi.Params), vp, C.c_int32, vp, vp, vp, vp, C.c_int32]
+        _lib.pmp_oracle_validate_edges.restype = C.c_int
+        _lib.pmp_oracle_check_configs.restype = C.c_int
+        _lib.pmp_oracle_max_threads.restype = C.c_int
+    return _lib
+
+
+class COracle:
+    """Holds the packed tables (same packer as the CUDA path) and calls the C twin."""
+
+    def __init__(self, robot, worlds, obstacles=None, resolution=np.radians(3), deflection_limit=0.30, alpha=0.1,
+                 iterations=4, max_step=0.5, reg_eps=1e-4, stem_radius=None, mode="our_method", dense=False):
+        self.lib = load()
+        self.rt = pack_robot(robot, obstacles)
+        self.wt = pack_worlds(list(worlds), stem_radius)
+        t = self.rt
+        d = _capi.RobotDesc()
+        d.dof, d.n_spheres, d.n_links, d.n_fixed = t.dof, t.n_spheres, t.n_links, t.n_fixed
+        d.joint_C, d.joint_A, d.joint_B = _capi.fptr(t.joint_C), _capi.fptr(t.joint_A), _capi.fptr(t.joint_B)
+        d.joint_t, d.lower, d.upper = _capi.fptr(t.joint_t), _capi.fptr(t.lower), _capi.fptr(t.upper)
+        d.circular = _capi.bptr(t.circular)
+        d.base_R, d.base_t = _capi.fptr(t.base_R), _capi.fptr(t.base_t)
+        d.sph_joint, d.sph_center = _capi.iptr(t.sph_joint), _capi.fptr(t.sph_center)
+        d.sph_radius, d.self_mask = _capi.fptr(t.sph_radius), _capi.uptr(t.self_mask)
+        d.link_joint, d.link_R = _capi.iptr(t.link_joint), _capi.fptr(t.link_R)
+        d.link_t, d.link_com = _capi.fptr(t.link_t), _capi.fptr(t.link_com)
+        d.ee_joint = t.ee_joint
+        d.ee_local = (C.c_float * 3)(*[float(v) for v in t.ee_local])
+        d.fixed_kind, d.fixed_R = _capi.iptr(t.fixed_kind), _capi.fptr(t.fixed_R)
+        d.fixed_t, d.fixed_half = _capi.fptr(t.fixed_t), _capi.fptr(t.fixed_half)
+        d.fixed_mask = _capi.uptr(t.fixed_mask)
+        self.rd = d
+        w = _capi.WorldDesc()
+        self._stems = np.ascontiguousarray(self.wt.stems.reshape(-1))
+        self._boxes = np.ascontiguousarray(self.wt.boxes.reshape(-1))
+        w.n_worlds, w.max_stems, w.max_boxes, w.n_slots = self.wt.n_worlds, self.wt.max_stems, self.wt.max_boxes, self.wt.n_slots
+        w.n_stems, w.stems = _capi.iptr(self.wt.n_stems), _capi.fptr(self._stems)
+        w.n_boxes, w.boxes = _capi.iptr(self.wt.n_boxes), _capi.fptr(self._boxes)
+        self.wd = w
+        self.prm = _capi.Params(float(resolution), deflection_limit, alpha, max_step, reg_eps, iterations, MODES[mode],
+                                1 if dense else 0, 0)
+
+    @property
+    def max_threads(self) -> int:
+        return int(self.lib.pmp_oracle_max_threads())
+
+    def validate_edges(self, q0, q1, backward=False, max_steps=320, want_masks=False, n_threads=0) -> dict:
+        q0 = np.ascontiguousarray(q0, dtype=np.float32).reshape(-1, self.rt.dof)
+        q1 = np.ascontiguousarray(q1, dtype=np.float32).reshape(-1, self.rt.dof)
+        E, W, Cw = q0.shape[0], self.wt.n_worlds, (max_steps + 31) // 32
+        out = {"first_hit": np.empty(E, np.int32), "n_steps": np.empty(E, np.int32),
+               "max_deflection": np.empty((E, W), np.float32), "over_limit": np.empty((E, W), np.float32),
+               "ee_len": np.empty(E, np.float32), "cost": np.empty(E, np.float32)}
+        if want_masks:
+            out["rigid_mask"] = np.zeros((E, W, Cw), np.uint32)
+            out["exceed_mask"] = np.zeros((E, W, Cw), np.uint32)
+        vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p()
+        rc = self.lib.pmp_oracle_validate_edges(
+            C.byref(self.rd), C.byref(self.wd), C.byref(self.prm), vp(q0), vp(q1), E, max_steps, 1 if backward else 0,
+            vp(out["first_hit"]), vp(out["n_steps"]), vp(out["max_deflection"]), vp(out["over_limit"]), vp(out["ee_len"]),
+            vp(out["cost"]), vp(out.get("rigid_mask")), vp(out.get("exceed_mask")), int(n_threads))
+        assert rc == 0
+        return out
+
+    def check_configs(self, q, n_threads=0) -> dict:
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.rt.dof)
+        B, W, P = q.shape[0], self.wt.n_worlds, self.wt.max_stems
+        out = {"flags": np.empty((B, W), np.uint8), "deflection": np.empty((B, W, P), np.float64),
+               "theta": np.empty((B, W, P, 2), np.float64), "ee": np.empty((B, 3), np.float64)}
+        vp = lambda a: C.c_void_p(a.ctypes.data)
+        rc = self.lib.pmp_oracle_check_configs(C.byref(self.rd), C.byref(self.wd), C.byref(self.prm), vp(q), B,
+                                               vp(out["flags"]), vp(out["deflection"]), vp(out["theta"]), vp(out["ee"]),
+                                               int(n_threads))
+        assert rc == 0
+        return out

@@ -1,0 +1,461 @@
+/*
+ * C twin (float64, scalar, pthreads over edges) of oracle/edgecheck_oracle.py.   *** TEST INFRASTRUCTURE ***
+ *
+ * Used (a) by tests/ as a second, faster checker at sizes the numpy oracle cannot reach and (b) by bench.py as
+ * the timed CPU baseline ("port": the reference's PyBullet path cannot run in this image).
+ * The product path never links or loads this file.
+ *
+ * It consumes the same packed tables as the CUDA library (include/pmp_edgecheck.h) and evaluates the same
+ * definitions in double precision with libm.  Reference lines restated (paths relative to
+ * /root/reference/plant_motion_planning/):
+ *   interpolation ........ pybullet_tools/utils.py:3604-3610, 3641-3651, 3667-3676; motion_planners/motion_planners/primitives.py:16-19
+ *   limits ............... pybullet_tools/utils.py:3753-3762
+ *   rigid collision ...... pybullet_tools/utils.py:3390-3441, 3965-4016 (on the URDF's sphere model)
+ *   plant response ....... env.py:127-163, 212-219  (quasi-static model, see the .py docstring)
+ *   observers ............ representation.py:27-51, 84-123, 220-235, 268-294
+ *   world / edge loops ... env.py:230-255; motion_planners/motion_planners/primitives.py:196-255
+ *   cost ................. pybullet_tools/kuka_primitives.py:467-521
+ * PARITY STATUS: as the .py oracle (sampler / interpolation / observers pinned; Bullet collision and dynamics unpinned).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include <stdatomic.h>
+#include <unistd.h>
+
+#include "../include/pmp_edgecheck.h"
+
+#define S_RO 0
+#define S_TO 9
+#define S_Z0 12
+#define S_Z1 13
+#define S_RAD 14
+#define S_LIM 15
+#define S_OBSV 16
+#define S_OBSP 19
+#define S_COMZ 22
+#define S_PSLOT 24
+#define S_OSLOT 25
+#define S_FLAGS 26
+#define SF_PLANT_START 1
+#define SF_IS_MAIN 2
+#define SF_OBS_ANGLE 4
+#define SF_OBS_ROOT 8
+#define SF_SNAP 16
+
+typedef struct {
+    double c[PMP_MAX_SPHERES][3];
+    double ee[3];
+    int rigid;
+} config_t;
+
+static void mat_vec(const double* R, const double* v, double* o) {
+    o[0] = R[0] * v[0] + R[1] * v[1] + R[2] * v[2];
+    o[1] = R[3] * v[0] + R[4] * v[1] + R[5] * v[2];
+    o[2] = R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
+}
+static void matT_vec(const double* R, const double* v, double* o) {
+    o[0] = R[0] * v[0] + R[3] * v[1] + R[6] * v[2];
+    o[1] = R[1] * v[0] + R[4] * v[1] + R[7] * v[2];
+    o[2] = R[2] * v[0] + R[5] * v[1] + R[8] * v[2];
+}
+static void mat_mul(const double* X, const double* Y, double* O) {
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) O[3 * r + c] = X[3 * r] * Y[c] + X[3 * r + 1] * Y[3 + c] + X[3 * r + 2] * Y[6 + c];
+}
+static double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+static int prim_hit(int kind, const float* Rf, const float* tf, const float* hf, const double* c, double r) {
+    double R[9], d[3], l[3];
+    for (int i = 0; i < 9; ++i) R[i] = Rf[i];
+    for (int i = 0; i < 3; ++i) d[i] = c[i] - (double)tf[i];
+    matT_vec(R, d, l);
+    if (kind == PMP_PRIM_BOX) {
+        double e2 = 0;
+        for (int i = 0; i < 3; ++i) {
+            double e = fabs(l[i]) - (double)hf[i];
+            if (e > 0) e2 += e * e;
+        }
+        return e2 <= r * r;
+    } else if (kind == PMP_PRIM_CYLINDER) {
+        double rho = sqrt(l[0] * l[0] + l[1] * l[1]);
+        double dr = rho - (double)hf[0], dz = fabs(l[2]) - (double)hf[1];
+        if (dr < 0) dr = 0;
+        if (dz < 0) dz = 0;
+        return dr * dr + dz * dz <= r * r;
+    }
+    double rr = r + (double)hf[0];
+    return l[0] * l[0] + l[1] * l[1] + l[2] * l[2] <= rr * rr;
+}
+
+/* arm FK + spheres + world-independent rigid test */
+static void config_eval(const pmp_robot_desc* rb, const double* q, config_t* out) {
+    double R[9], p[3];
+    for (int i = 0; i < 9; ++i) R[i] = rb->base_R[i];
+    for (int i = 0; i < 3; ++i) p[i] = rb->base_t[i];
+    int hit = 0;
+    const int D = rb->dof, A = rb->n_spheres;
+    for (int j = 0; j < D; ++j) {
+        const int circ = rb->circular && rb->circular[j];
+        if (!circ && !(q[j] >= (double)rb->lower[j] && q[j] <= (double)rb->upper[j])) hit = 1;
+        const double s = sin(q[j]), c = cos(q[j]);
+        double M[9], t[3], tj[3], Rn[9];
+        for (int k = 0; k < 9; ++k)
+            M[k] = (double)rb->joint_C[9 * j + k] + c * (double)rb->joint_A[9 * j + k] + s * (double)rb->joint_B[9 * j + k];
+        for (int k = 0; k < 3; ++k) tj[k] = rb->joint_t[3 * j + k];
+        mat_vec(R, tj, t);
+        for (int k = 0; k < 3; ++k) p[k] += t[k];
+        mat_mul(R, M, Rn);
+        memcpy(R, Rn, sizeof(R));
+        for (int a = 0; a < A; ++a) {
+            if (rb->sph_joint[a] == j) {
+                double l[3] = {rb->sph_center[3 * a], rb->sph_center[3 * a + 1], rb->sph_center[3 * a + 2]}, w[3];
+                mat_vec(R, l, w);
+                for (int k = 0; k < 3; ++k) out->c[a][k] = w[k] + p[k];
+            }
+        }
+        if (rb->ee_joint == j) {
+            double l[3] = {rb->ee_local[0], rb->ee_local[1], rb->ee_local[2]}, w[3];
+            mat_vec(R, l, w);
+            for (int k = 0; k < 3; ++k) out->ee[k] = w[k] + p[k];
+        }
+    }
+    for (int a = 0; a < A && !hit; ++a) {
+        const uint32_t m = rb->self_mask[a];
+        for (int b = a + 1; b < A; ++b) {
+            if ((m >> b) & 1u) {
+                double dx = out->c[a][0] - out->c[b][0], dy = out->c[a][1] - out->c[b][1], dz = out->c[a][2] - out->c[b][2];
+                double rr = (double)rb->sph_radius[a] + (double)rb->sph_radius[b];
+                if (dx * dx + dy * dy + dz * dz <= rr * rr) { hit = 1; break; }
+            }
+        }
+    }
+    for (int f = 0; f < rb->n_fixed && !hit; ++f) {
+        for (int a = 0; a < A; ++a) {
+            if ((rb->fixed_mask[f] >> a) & 1u) {
+                if (prim_hit(rb->fixed_kind[f], rb->fixed_R + 9 * f, rb->fixed_t + 3 * f, rb->fixed_half + 3 * f,
+                             out->c[a], (double)rb->sph_radius[a])) { hit = 1; break; }
+            }
+        }
+    }
+    out->rigid = hit;
+}
+
+typedef struct {
+    int plant_hit, exceeded;
+    double max_defl, over;
+} unit_t;
+
+static int as_int(float f) { int32_t i; memcpy(&i, &f, 4); return i; }
+
+/* one (configuration, world) unit */
+static void world_eval(const pmp_robot_desc* rb, const pmp_world_desc* wd, const pmp_params* prm, int w,
+                       const config_t* cf, unit_t* out, double* defl_out, double* theta_out) {
+    const int A = rb->n_spheres;
+    const float* wt = wd->stems + (size_t)w * wd->max_stems * PMP_STEM_STRIDE;
+    const int ns = wd->n_stems[w];
+    double FR[PMP_MAX_SLOTS][9], FT[PMP_MAX_SLOTS][3];
+    int FM[PMP_MAX_SLOTS];
+    memset(FM, 0, sizeof(FM));
+    const int solve = prm->mode == PMP_MODE_OUR_METHOD;
+    const int K = solve ? prm->iterations : 1;
+    double last = 0.0;
+    out->plant_hit = 0; out->exceeded = 0; out->max_defl = 0.0; out->over = 0.0;
+    for (int s = 0; s < ns; ++s) {
+        const float* rec = wt + s * PMP_STEM_STRIDE;
+        const int pslot = as_int(rec[S_PSLOT]), oslot = as_int(rec[S_OSLOT]), flags = as_int(rec[S_FLAGS]);
+        double Ro[9], to[3], Rv[9], tv[3];
+        for (int i = 0; i < 9; ++i) Ro[i] = rec[S_RO + i];
+        for (int i = 0; i < 3; ++i) to[i] = rec[S_TO + i];
+        int moved = 0;
+        if (pslot < 0) {
+            memcpy(Rv, Ro, sizeof(Rv));
+            memcpy(tv, to, sizeof(tv));
+        } else {
+            double x[3];
+            mat_mul(FR[pslot], Ro, Rv);
+            mat_vec(FR[pslot], to, x);
+            for (int i = 0; i < 3; ++i) tv[i] = x[i] + FT[pslot][i];
+            moved = FM[pslot];
+        }
+        const double z0 = rec[S_Z0], z1 = rec[S_Z1], rad = rec[S_RAD], lim = rec[S_LIM];
+        double thx = 0, thy = 0;
+        for (int it = 0; it < K; ++it) {
+            const double cx = cos(thx), sx = sin(thx), cy = cos(thy), sy = sin(thy);
+            double ul[3] = {sy, -sx * cy, cx * cy}, u[3], ayl[3] = {0, cx, sx}, ay[3];
+            mat_vec(Rv, ul, u);
+            mat_vec(Rv, ayl, ay);
+            const double ax[3] = {Rv[0], Rv[3], Rv[6]};
+            const double bx[3] = {ax[1] * u[2] - ax[2] * u[1], ax[2] * u[0] - ax[0] * u[2], ax[0] * u[1] - ax[1] * u[0]};
+            const double by[3] = {ay[1] * u[2] - ay[2] * u[1], ay[2] * u[0] - ay[0] * u[2], ay[0] * u[1] - ay[1] * u[0]};
+            double Hxx = 0, Hxy = 0, Hyy = 0, gx = 0, gy = 0, S = 0;
+            for (int a = 0; a < A; ++a) {
+                const double wv[3] = {cf->c[a][0] - tv[0], cf->c[a][1] - tv[1], cf->c[a][2] - tv[2]};
+                const double tau = clampd(wv[0] * u[0] + wv[1] * u[1] + wv[2] * u[2], z0, z1);
+                const double dv[3] = {wv[0] - tau * u[0], wv[1] - tau * u[1], wv[2] - tau * u[2]};
+                const double dist = sqrt(dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2]);
+                double pen = (double)rb->sph_radius[a] + rad - dist;
+                if (pen <= 0) continue;
+                const double sc = -tau / (dist > 1e-12 ? dist : 1e-12);
+                const double Jx = sc * (dv[0] * bx[0] + dv[1] * bx[1] + dv[2] * bx[2]);
+                const double Jy = sc * (dv[0] * by[0] + dv[1] * by[1] + dv[2] * by[2]);
+                Hxx += pen * Jx * Jx; Hxy += pen * Jx * Jy; Hyy += pen * Jy * Jy;
+                gx += pen * pen * Jx; gy += pen * pen * Jy; S += pen;
+            }
+            if (!solve) { if (S > 0) out->plant_hit = 1; break; }
+            if (!(S > 0)) { if (prm->dense) continue; else break; }
+            const double lam = (double)prm->reg_eps * S, a11 = Hxx + lam, a22 = Hyy + lam;
+            const double det = a11 * a22 - Hxy * Hxy;
+            double dx = (a22 * gx - Hxy * gy) / det, dy = (a11 * gy - Hxy * gx) / det;
+            dx = clampd(dx, -(double)prm->max_step, (double)prm->max_step);
+            dy = clampd(dy, -(double)prm->max_step, (double)prm->max_step);
+            thx = clampd(thx + dx, -lim, lim);
+            thy = clampd(thy + dy, -lim, lim);
+        }
+        if (thx != 0 || thy != 0) moved = 1;
+        double Rs[9];
+        {
+            const double cx = cos(thx), sx = sin(thx), cy = cos(thy), sy = sin(thy);
+            const double M[9] = {cy, 0, sy, sx * sy, cx, -sx * cy, -cx * sy, sx, cx * cy};
+            mat_mul(Rv, M, Rs);
+        }
+        double raw = 0.0;
+        if (moved || prm->dense) {
+            const double o[3] = {rec[S_OBSV], rec[S_OBSV + 1], rec[S_OBSV + 2]};
+            if (flags & SF_OBS_ANGLE) {
+                const double cz = rec[S_COMZ];
+                double v[3] = {cz * Rs[2] + tv[0] - (double)rec[S_OBSP], cz * Rs[5] + tv[1] - (double)rec[S_OBSP + 1],
+                               cz * Rs[8] + tv[2] - (double)rec[S_OBSP + 2]};
+                if (flags & SF_SNAP) {
+                    if (fabs(v[0]) < 1e-5) v[0] = 0;
+                    if (fabs(v[1]) < 1e-5) v[1] = 0;
+                }
+                const double nv = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+                double cs = (v[0] * o[0] + v[1] * o[1] + v[2] * o[2]) / nv;
+                raw = acos(clampd(cs, -1.0, 1.0));
+            } else {
+                double v[3];
+                if (flags & SF_OBS_ROOT) {
+                    mat_vec(Rs, o, v);
+                } else {
+                    double l[3];
+                    matT_vec(Rs, o, l);
+                    mat_vec(FR[pslot], l, v);
+                }
+                const double sarg = -v[0];
+                double roll, pitch;
+                if (sarg <= -0.99999) { roll = 0; pitch = -1.5707963267948966; }
+                else if (sarg >= 0.99999) { roll = 0; pitch = 1.5707963267948966; }
+                else { roll = atan2(v[1], v[2]); pitch = asin(sarg); }
+                raw = sqrt(roll * roll + pitch * pitch);
+            }
+            if (!moved) raw = 0.0;
+        }
+        if (flags & SF_PLANT_START) last = 0.0;
+        double d = raw - last;
+        if (d < 0) d = 0;
+        if (flags & SF_IS_MAIN) last = d;
+        if (d > (double)prm->deflection_limit) { out->exceeded = 1; out->over += d - (double)prm->deflection_limit; }
+        if (d > out->max_defl) out->max_defl = d;
+        if (defl_out) defl_out[s] = d;
+        if (theta_out) { theta_out[2 * s] = thx; theta_out[2 * s + 1] = thy; }
+        if (oslot >= 0) {
+            memcpy(FR[oslot], Rs, sizeof(Rs));
+            memcpy(FT[oslot], tv, sizeof(tv));
+            FM[oslot] = moved;
+        }
+    }
+    if (prm->mode == PMP_MODE_AVOID_ALL) {
+        const float* bx = wd->boxes + (size_t)w * wd->max_boxes * PMP_BOX_STRIDE;
+        for (int b = 0; b < wd->n_boxes[w] && !out->plant_hit; ++b)
+            for (int a = 0; a < A; ++a)
+                if (prim_hit(PMP_PRIM_BOX, bx + b * PMP_BOX_STRIDE, bx + b * PMP_BOX_STRIDE + 9,
+                             bx + b * PMP_BOX_STRIDE + 12, cf->c[a], (double)rb->sph_radius[a])) { out->plant_hit = 1; break; }
+    }
+}
+
+static int edge_steps(const pmp_robot_desc* rb, const pmp_params* prm, const float* q0, const float* q1, double* dq) {
+    double ssum = 0.0;
+    for (int j = 0; j < rb->dof; ++j) {
+        double d = (double)q1[j] - (double)q0[j];
+        if (rb->circular && rb->circular[j]) {
+            const double two_pi = 6.283185307179586, pi = 3.141592653589793;
+            double x = d + pi;
+            x = x - two_pi * floor(x / two_pi);
+            d = x - pi;
+        }
+        dq[j] = d;
+        const double v = d / prm->resolution;
+        ssum = ssum + v * v;
+    }
+    const double nd = floor(sqrt(ssum));
+    return (nd > 1.0e6 ? 1000000 : (int)nd) + 1;
+}
+
+typedef struct {
+    const pmp_robot_desc* rb; const pmp_world_desc* wd; const pmp_params* prm;
+    const float* q0; const float* q1; int32_t E, max_steps, backward;
+    int32_t* first_hit; int32_t* n_steps; float* max_defl; float* over; float* ee_len; float* cost;
+    uint32_t* rigid_mask; uint32_t* exceed_mask;
+    /* explicit configurations */
+    const float* q; int32_t B; uint8_t* flags; double* defl; double* theta; double* ee;
+    atomic_int next;
+    int chunk;
+} job_t;
+
+static void one_edge(const job_t* jb, int e) {
+    const pmp_robot_desc* rb = jb->rb; const pmp_world_desc* wd = jb->wd; const pmp_params* prm = jb->prm;
+    const float* q0 = jb->q0; const float* q1 = jb->q1;
+    const int32_t max_steps = jb->max_steps, backward = jb->backward;
+    int32_t* first_hit = jb->first_hit; int32_t* n_steps = jb->n_steps;
+    float* max_defl = jb->max_defl; float* over = jb->over; float* ee_len = jb->ee_len; float* cost = jb->cost;
+    uint32_t* rigid_mask = jb->rigid_mask; uint32_t* exceed_mask = jb->exceed_mask;
+    const int D = rb->dof, W = wd->n_worlds, C = (max_steps + 31) / 32;
+        double dq[PMP_MAX_DOF], q[PMP_MAX_DOF];
+        const float* a = q0 + (size_t)e * D;
+        const float* b = q1 + (size_t)e * D;
+        const int n = edge_steps(rb, prm, a, b, dq);
+        const int nc = n < max_steps ? n : max_steps;
+        const int off = backward ? 0 : 1;
+        double* md = (double*)calloc((size_t)2 * W, sizeof(double));
+        double* ov = md + W;
+        config_t cf;
+        memset(&cf, 0, sizeof(cf));
+        for (int j = 0; j < D; ++j) q[j] = a[j];
+        config_eval(rb, q, &cf);
+        double prev[3] = {cf.ee[0], cf.ee[1], cf.ee[2]};
+        double eel = 0.0;
+        int first = nc;
+        if (rigid_mask) memset(rigid_mask + (size_t)e * W * C, 0, sizeof(uint32_t) * W * C);
+        if (exceed_mask) memset(exceed_mask + (size_t)e * W * C, 0, sizeof(uint32_t) * W * C);
+        for (int i = 0; i < nc; ++i) {
+            const int num = i + off;
+            for (int j = 0; j < D; ++j) {
+                const int circ = rb->circular && rb->circular[j];
+                q[j] = (num == n && !circ) ? (double)b[j] : (double)a[j] + dq[j] * ((double)num / (double)n);
+            }
+            config_eval(rb, q, &cf);
+            const double dx = cf.ee[0] - prev[0], dy = cf.ee[1] - prev[1], dz = cf.ee[2] - prev[2];
+            eel += sqrt(dx * dx + dy * dy + dz * dz);
+            prev[0] = cf.ee[0]; prev[1] = cf.ee[1]; prev[2] = cf.ee[2];
+            int viol = cf.rigid;
+            for (int w = 0; w < W; ++w) {
+                unit_t u;
+                u.plant_hit = 0; u.exceeded = 0; u.max_defl = 0; u.over = 0;
+                if (prm->mode != PMP_MODE_IGNORE_ALL) world_eval(rb, wd, prm, w, &cf, &u, NULL, NULL);
+                const int r = cf.rigid || u.plant_hit;
+                viol |= r | u.exceeded;
+                if (u.max_defl > md[w]) md[w] = u.max_defl;
+                ov[w] += u.over;
+                const size_t o = ((size_t)e * W + w) * C + (i >> 5);
+                if (rigid_mask && r) rigid_mask[o] |= 1u << (i & 31);
+                if (exceed_mask && u.exceeded) exceed_mask[o] |= 1u << (i & 31);
+            }
+            if (viol && first == nc) first = i;
+        }
+        double osum = 0.0;
+        for (int w = 0; w < W; ++w) {
+            if (max_defl) max_defl[(size_t)e * W + w] = (float)md[w];
+            if (over) over[(size_t)e * W + w] = (float)ov[w];
+            osum += ov[w];
+        }
+        first_hit[e] = first;
+        n_steps[e] = n;
+        if (ee_len) ee_len[e] = (float)eel;
+        if (cost) cost[e] = (float)(eel + (double)prm->alpha * osum / (double)W);
+        free(md);
+}
+
+static int hw_threads(void) {
+    long n = sysconf(_SC_NPROCESSORS_ONLN);
+    return n < 1 ? 1 : (int)n;
+}
+
+static void* edge_worker(void* arg) {
+    job_t* jb = (job_t*)arg;
+    for (;;) {
+        const int lo = atomic_fetch_add(&jb->next, jb->chunk);
+        if (lo >= jb->E) break;
+        const int hi = lo + jb->chunk < jb->E ? lo + jb->chunk : jb->E;
+        for (int e = lo; e < hi; ++e) one_edge(jb, e);
+    }
+    return NULL;
+}
+
+static void run_threads(job_t* jb, void* (*fn)(void*), int n_threads) {
+    if (n_threads <= 0) n_threads = hw_threads();
+    if (n_threads > 256) n_threads = 256;
+    if (n_threads == 1) { fn(jb); return; }
+    pthread_t th[256];
+    int started = 0;
+    for (int i = 0; i < n_threads; ++i)
+        if (pthread_create(&th[started], NULL, fn, jb) == 0) ++started;
+    if (started == 0) fn(jb);
+    for (int i = 0; i < started; ++i) pthread_join(th[i], NULL);
+}
+
+/* Same contract as pmp_validate_edges_host (include/pmp_edgecheck.h), double accumulators, float outputs.
+ * n_threads <= 0: one thread per online core.  Returns 0. */
+int pmp_oracle_validate_edges(const pmp_robot_desc* rb, const pmp_world_desc* wd, const pmp_params* prm, const float* q0,
+                              const float* q1, int32_t E, int32_t max_steps, int32_t backward, int32_t* first_hit,
+                              int32_t* n_steps, float* max_defl, float* over, float* ee_len, float* cost,
+                              uint32_t* rigid_mask, uint32_t* exceed_mask, int32_t n_threads) {
+    job_t jb;
+    memset(&jb, 0, sizeof(jb));
+    jb.rb = rb; jb.wd = wd; jb.prm = prm; jb.q0 = q0; jb.q1 = q1; jb.E = E; jb.max_steps = max_steps; jb.backward = backward;
+    jb.first_hit = first_hit; jb.n_steps = n_steps; jb.max_defl = max_defl; jb.over = over; jb.ee_len = ee_len; jb.cost = cost;
+    jb.rigid_mask = rigid_mask; jb.exceed_mask = exceed_mask; jb.chunk = 4;
+    atomic_init(&jb.next, 0);
+    run_threads(&jb, edge_worker, n_threads);
+    return 0;
+}
+
+static void one_config(const job_t* jb, int b) {
+    const pmp_robot_desc* rb = jb->rb; const pmp_world_desc* wd = jb->wd; const pmp_params* prm = jb->prm;
+    const float* q = jb->q; uint8_t* flags = jb->flags; double* defl = jb->defl; double* theta = jb->theta; double* ee = jb->ee;
+    const int D = rb->dof, W = wd->n_worlds, P = wd->max_stems;
+        double qd[PMP_MAX_DOF];
+        config_t cf;
+        memset(&cf, 0, sizeof(cf));
+        for (int j = 0; j < D; ++j) qd[j] = q[(size_t)b * D + j];
+        config_eval(rb, qd, &cf);
+        if (ee) for (int k = 0; k < 3; ++k) ee[3 * (size_t)b + k] = cf.ee[k];
+        for (int w = 0; w < W; ++w) {
+            unit_t u;
+            u.plant_hit = 0; u.exceeded = 0; u.max_defl = 0; u.over = 0;
+            const size_t bw = (size_t)b * W + w;
+            double* dptr = defl ? defl + bw * P : NULL;
+            double* tptr = theta ? theta + bw * P * 2 : NULL;
+            if (dptr) memset(dptr, 0, sizeof(double) * P);
+            if (tptr) memset(tptr, 0, sizeof(double) * P * 2);
+            if (prm->mode != PMP_MODE_IGNORE_ALL) world_eval(rb, wd, prm, w, &cf, &u, dptr, tptr);
+            flags[bw] = (uint8_t)(((cf.rigid || u.plant_hit) ? PMP_FLAG_RIGID : 0) | (u.exceeded ? PMP_FLAG_EXCEEDED : 0));
+        }
+}
+
+static void* config_worker(void* arg) {
+    job_t* jb = (job_t*)arg;
+    for (;;) {
+        const int lo = atomic_fetch_add(&jb->next, jb->chunk);
+        if (lo >= jb->B) break;
+        const int hi = lo + jb->chunk < jb->B ? lo + jb->chunk : jb->B;
+        for (int b = lo; b < hi; ++b) one_config(jb, b);
+    }
+    return NULL;
+}
+
+/* Same contract as pmp_check_configs_host; defl / theta / ee in double for tight comparisons. */
+int pmp_oracle_check_configs(const pmp_robot_desc* rb, const pmp_world_desc* wd, const pmp_params* prm, const float* q,
+                             int32_t B, uint8_t* flags, double* defl, double* theta, double* ee, int32_t n_threads) {
+    job_t jb;
+    memset(&jb, 0, sizeof(jb));
+    jb.rb = rb; jb.wd = wd; jb.prm = prm; jb.q = q; jb.B = B; jb.flags = flags; jb.defl = defl; jb.theta = theta; jb.ee = ee;
+    jb.chunk = 16;
+    atomic_init(&jb.next, 0);
+    run_threads(&jb, config_worker, n_threads);
+    return 0;
+}
+
+int pmp_oracle_max_threads(void) { return hw_threads(); }

@@ -345,6 +345,24 @@ def plant_equilibrium(world: PlantWorld, centers: np.ndarray, radii: np.ndarray,
     return theta, Rs, ts, rest_pen
 
 
+def frames_from_theta(world: PlantWorld, theta: np.ndarray):
+    """Stem link frames (R [B,P,3,3], t [B,P,3]) for given stem angles theta [B,P,2] (URDF/createMultiBody
+    composition: child joint frame = parent link frame . origin; joints Rx then Ry)."""
+    theta = np.asarray(theta, dtype=np.float64)
+    B, P = theta.shape[0], world.num_stems
+    Rs = np.zeros((B, P, 3, 3))
+    ts = np.zeros((B, P, 3))
+    for s, stem in enumerate(world.stems):
+        if stem.parent < 0:
+            Rp = np.broadcast_to(np.eye(3), (B, 3, 3))
+            tp = np.zeros((B, 3))
+        else:
+            Rp, tp = Rs[:, stem.parent], ts[:, stem.parent]
+        Rs[:, s] = Rp @ stem.origin.R[None] @ _rx_ry(theta[:, s, 0], theta[:, s, 1])
+        ts[:, s] = np.einsum("bij,j->bi", Rp, stem.origin.t) + tp
+    return Rs, ts
+
+
 def quat_difference(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     """pybullet.getDifferenceQuaternion(a, b) = nearest(b) * inverse(a)   (Bullet b3GetQuaternionDifference)."""
     b = np.asarray(b, dtype=np.float64)

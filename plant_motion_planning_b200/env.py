@@ -1,0 +1,228 @@
+"""MultiPlantWorld / SinglePlantEnv facade with the reference's surface (plant_motion_planning/env.py:30-255),
+backed by the GPU edge checker instead of a Bullet world.
+
+What the reference's RRT fork calls and what it gets here:
+  env.step(q, set_joint_pos=False)            evaluates q in ALL worlds with one kernel launch (the quasi-static
+                                              stand-in for 50 x stepSimulation) and caches flags + deflections
+  env.step_after_restoring(q), step_no_action same evaluation (the model is stateless)
+  env.net_constraint_violation_checker_forward(q)    OR over worlds in construction order with early exit;
+                                              per world: limits(q) | rigid | (exceeded & rand() < 0.95), drawing
+                                              np.random.rand() exactly where the reference does (utils.py:3836-3855)
+  ..._backward(q) / ..._benchmark(q)          rigid obstacles only (env.py:96-120, 241-255)
+  env.envs[(x, y)].plant_rep.observe_all() / .deflections / .observe_all_and_check(limit)
+  save_state() / restore_state(id)            no-ops returning ids: nothing to snapshot (pybullet_tools/utils.py:1517-1523)
+Additive: env.checker (EdgeChecker), env.validate_edges(...) for batched use.
+
+Like the reference's collision closures, the checkers test the state left by the last ``step`` and use their
+argument only for the joint-limit test (pybullet_tools/utils.py:3979-4014).
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .edgecheck import FLAG_EXCEEDED, FLAG_RIGID, EdgeCheckConfig, EdgeChecker
+from .model.plants import PlantWorld, load_plant, sample_world
+from .model.robot import RobotModel
+from .planner_fns import GATE_PROBABILITY, get_limits_fn
+from .robots import load_iiwa14
+
+_STATE_COUNTER = [0]
+
+
+def save_state() -> int:
+    """pybullet_tools/utils.py:1517-1519 -- the quasi-static model has no state; ids only keep callers happy."""
+    _STATE_COUNTER[0] += 1
+    return _STATE_COUNTER[0]
+
+
+def restore_state(state_id: int) -> None:
+    """pybullet_tools/utils.py:1521-1523."""
+    return None
+
+
+class PlantRepresentation:
+    """CharacterizePlant / CharacterizePlant2 view of one world (representation.py:248-418)."""
+
+    def __init__(self, owner: "MultiPlantWorld", world_index: int, n_stems: int):
+        self._owner = owner
+        self._w = world_index
+        self._n = n_stems
+        self.deflections: List[float] = []
+
+    def observe_all(self) -> None:
+        d = self._owner._deflections()
+        self.deflections.clear()
+        self.deflections.extend(float(v) for v in d[self._w, :self._n])
+
+    def observe_all_and_check(self, deflection_limit: float) -> bool:
+        self.observe_all()
+        return any(d > deflection_limit for d in self.deflections)
+
+
+class SinglePlantEnv:
+    """One sampled world.  Constructed by MultiPlantWorld (which owns the shared GPU context)."""
+
+    def __init__(self, owner: "MultiPlantWorld", world_index: int, world: PlantWorld, base_offset_xy, avoid_all: bool):
+        self._owner = owner
+        self._w = world_index
+        self.world = world
+        self.base_offset_xy = tuple(base_offset_xy)
+        self.robot = owner.sample_robot
+        self.joints = list(range(owner.sample_robot.dof))
+        self.plant_rep = PlantRepresentation(owner, world_index, world.num_stems)
+        self.plant_id = ("plant", world_index)
+        self.base_id = self.plant_id
+        self.joint_list = list(world.joint_list)
+        self.fixed = ["floor", "block"] + ([self.plant_id] if avoid_all else [])
+        self.movable = [self.plant_rep]
+        self.deflection_limit = owner.deflection_limit
+        self.avoid_all = avoid_all
+
+    # -- the three closures of env.py:96-120 ---------------------------------------------------
+    def collision_fn(self, q, verbose: bool = False) -> bool:
+        """get_collision_fn_with_angle_constraints_v4 with movable=[plant_rep] (utils.py:3836-3855)."""
+        if self._owner._rigid(self._w, q):
+            return True
+        for b in self.movable:
+            if b.observe_all_and_check(self.deflection_limit) and np.random.rand() < GATE_PROBABILITY:
+                return True
+        return False
+
+    def collision_fn_back(self, q, verbose: bool = False) -> bool:
+        """Same closure with movable=[] (env.py:104-110)."""
+        return self._owner._rigid(self._w, q)
+
+    def collision_fn_benchmark(self, q, verbose: bool = False) -> bool:
+        """get_collision_fn_with_controls_benchmark_multiworld (utils.py:4019-4062)."""
+        return self._owner._rigid(self._w, q)
+
+    def constraint_violation_checker_forward(self, q):
+        return self.collision_fn(q)
+
+    def constraint_violation_checker_backward(self, q):
+        return self.collision_fn_back(q)
+
+    def constraint_violation_checker_benchmark(self, q):
+        return self.collision_fn_benchmark(q)
+
+    def step(self, action, set_joint_pos: bool = False):
+        self._owner.step(action, set_joint_pos)
+
+    def step_after_restoring(self, action, set_joint_pos: bool = True):
+        self._owner._set_action(action)
+
+    def state(self):
+        return self.plant_rep.deflections
+
+
+class MultiPlantWorld:
+    """Multi-world environment (env.py:187-255): one world per (x, y) offset, x outer / y inner."""
+
+    def __init__(self, xs: Sequence[float], ys: Sequence[float], deflection_limit: float,
+                 num_branches_per_stem: Optional[int] = None, total_num_vert_stems: Optional[int] = None,
+                 total_num_extensions: Optional[int] = None, plant_pos_xy_limits=((0, 1), (0, 1)),
+                 loadPath: Optional[str] = None, physicsClientId=None, avoid_all: bool = False, *,
+                 robot: Optional[RobotModel] = None, worlds: Optional[Sequence[PlantWorld]] = None,
+                 config: Optional[EdgeCheckConfig] = None, device: int = 0, stem_base_spacing: float = 0.0):
+        self.sample_robot = robot if robot is not None else load_iiwa14()
+        self.joints = list(range(self.sample_robot.dof))
+        self.deflection_limit = deflection_limit
+        self.avoid_all = avoid_all
+        offsets = [(x, y) for x in xs for y in ys]
+        if worlds is None:
+            worlds = []
+            for xy in offsets:
+                if loadPath is None:
+                    # same draws, same order as SinglePlantEnv.__init__ (env.py:63-70)
+                    worlds.append(sample_world(num_branches_per_stem, total_num_vert_stems, total_num_extensions,
+                                               plant_pos_xy_limits, base_offset_xy=xy,
+                                               stem_base_spacing=stem_base_spacing))
+                else:
+                    worlds.append(load_plant(os.path.join(loadPath, "plant.urdf"),
+                                             os.path.join(loadPath, "plant_params.pkl"), xy))
+        elif len(worlds) != len(offsets):
+            raise ValueError("need one PlantWorld per (x, y) offset")
+        base = config or EdgeCheckConfig()
+        from dataclasses import replace
+        self.config = replace(base, deflection_limit=float(deflection_limit),
+                              mode="avoid_all" if avoid_all else "our_method")
+        self.checker = EdgeChecker(self.sample_robot, list(worlds), self.config, device=device)
+        self._limits_fn = get_limits_fn(self.sample_robot)
+        self.envs: Dict[Tuple[float, float], SinglePlantEnv] = {}
+        for i, (xy, w) in enumerate(zip(offsets, worlds)):
+            self.envs[xy] = SinglePlantEnv(self, i, w, xy, avoid_all)
+        self.fixed = self.envs[offsets[0]].fixed
+        self._action: Optional[Tuple[float, ...]] = None
+        self._cache_q: Optional[Tuple[float, ...]] = None
+        self._cache = None
+        self.kernel_evaluations = 0
+
+    # -- state ------------------------------------------------------------------------------------
+    def _set_action(self, action) -> None:
+        self._action = tuple(float(v) for v in action)
+
+    def _evaluate(self):
+        if self._action is None:
+            raise RuntimeError("step(q) must be called before the checkers (as in the reference)")
+        if self._cache_q != self._action:
+            out = self.checker.check_configs_host(np.asarray(self._action, dtype=np.float32)[None], detail=True)
+            self._cache = (out["flags"][0], out["deflection"][0])
+            self._cache_q = self._action
+            self.kernel_evaluations += 1
+        return self._cache
+
+    def _deflections(self) -> np.ndarray:
+        return self._evaluate()[1]
+
+    def _rigid(self, w: int, q) -> bool:
+        if self._action is None:
+            self._set_action(q)
+        if self._limits_fn(q):
+            return True
+        return bool(self._evaluate()[0][w] & FLAG_RIGID)
+
+    # -- reference surface ------------------------------------------------------------------------
+    def step(self, action, set_joint_pos: bool = False) -> None:
+        self._set_action(action)
+
+    def step_after_restoring(self, action) -> None:
+        self._set_action(action)
+
+    def step_no_action(self) -> None:
+        return None
+
+    def net_constraint_violation_checker_forward(self, q) -> bool:
+        for env in self.envs.values():
+            if env.collision_fn(q):
+                return True
+        return False
+
+    def net_constraint_violation_checker_backward(self, q) -> bool:
+        for env in self.envs.values():
+            if env.collision_fn_back(q):
+                return True
+        return False
+
+    def net_constraint_violation_checker_benchmark(self, q) -> bool:
+        for env in self.envs.values():
+            if env.collision_fn_benchmark(q):
+                return True
+        return False
+
+    # -- additive batched surface -----------------------------------------------------------------
+    def validate_edges(self, q_from, q_to, **kw):
+        return self.checker.validate_edges(q_from, q_to, **kw)
+
+    def path_cost(self, init_conf, path: Sequence[Sequence[float]]):
+        """Command.execute_multi_world's cost (kuka_primitives.py:467-521) for a list of waypoints visited by
+        env.step: (ee_len, over[W], total[W]) with total = ee_len + alpha * over."""
+        Q = np.asarray([init_conf] + [tuple(p) for p in path], dtype=np.float32)
+        out = self.checker.check_configs_host(Q, detail=True)
+        ee = out["ee"].astype(np.float64)
+        ee_len = float(np.sum(np.linalg.norm(ee[1:] - ee[:-1], axis=1)))
+        d = out["deflection"][1:].astype(np.float64)
+        over = np.sum(np.maximum(d - self.deflection_limit, 0.0), axis=(0, 2))
+        return ee_len, over, ee_len + self.config.alpha * over

