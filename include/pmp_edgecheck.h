@@ -28,7 +28,7 @@ extern "C" {
 #define PMP_MAX_STEMS 32
 #define PMP_MAX_WORLD_BOXES 32
 #define PMP_MAX_SLOTS 8
-#define PMP_STEM_STRIDE 32 /* floats per stem record, layout in csrc/pmp_tables.h */
+#define PMP_STEM_STRIDE 48 /* floats per stem record, layout in csrc/pmp_tables.h */
 #define PMP_BOX_STRIDE 16  /* floats per plant-base box record: R[9] t[3] half[3] pad */
 
 #define PMP_OK 0

@@ -19,8 +19,8 @@ LIB = os.path.join(HERE, "_build", "liboracle_edgecheck.so")
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(HERE, "edgecheck_oracle.c")
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
+    deps = [os.path.join(HERE, "edgecheck_oracle.c"), os.path.join(HERE, "..", "include", "pmp_edgecheck.h")]
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
         # -march=native binaries are rebuilt on the machine that runs them when possible
         subprocess.run(["make", "-C", HERE, "-B"], check=True, capture_output=True)
     return LIB

@@ -66,7 +66,8 @@ _lib: Optional[C.CDLL] = None
 
 
 def library_path() -> str:
-    return _build.LIB_PATH
+    # PMP_LIB: load another build of the same library (kernel tuning experiments only)
+    return os.environ.get("PMP_LIB") or _build.LIB_PATH
 
 
 def load() -> C.CDLL:

@@ -262,6 +262,13 @@ static cudaError_t launch_config(pmp_ctx* ctx, const PmpConfigArgs& args, int gr
     return cudaGetLastError();
 }
 
+#ifdef PMP_FAST_BUILD   /* development builds: only the iiwa14 / (1,2,1)-plant instantiation */
+#define PMP_DISPATCH(FN, ...)                                                              \
+    do {                                                                                   \
+        if (apad == 12 && nspad == 2) err = FN<12, 2>(__VA_ARGS__);                        \
+        else err = cudaErrorNotSupported;                                                  \
+    } while (0)
+#else
 #define PMP_DISPATCH(FN, ...)                                                              \
     do {                                                                                   \
         const int ap_ = apad, ns_ = nspad;                                                 \
@@ -275,6 +282,7 @@ static cudaError_t launch_config(pmp_ctx* ctx, const PmpConfigArgs& args, int gr
         else if (ap_ == 32 && ns_ == 2) err = FN<32, 2>(__VA_ARGS__);                      \
         else err = FN<32, 4>(__VA_ARGS__);                                                 \
     } while (0)
+#endif
 
 static void pads(pmp_ctx* ctx, int& apad, int& nspad) {
     const int A = ctx->h_robot.n_spheres;
@@ -301,22 +309,24 @@ extern "C" int pmp_validate_edges(pmp_ctx* ctx, const float* q0, const float* q1
     pads(ctx, apad, nspad);
     const int W = ctx->n_worlds;
     const size_t world_bytes = sizeof(float) * (size_t)W * ctx->max_stems * PMP_STEM_STRIDE;
-    // geometry: 2 CTAs x 256 threads per SM when the world tables fit twice, else 1 x 512, else tables stay in L1/L2
-    int block = 256, per_sm = 2;
+    // geometry: one persistent CTA per SM with up to 16 warps (128 registers/thread fill the register file; measured
+    // best on B200, profiles/r01_tuning.md); small batches use smaller CTAs so that they still spread over the SMs.
+    // World tables go to shared memory when they fit, else they are read through L1.
     auto smem_for = [&](int blk, bool ws) {
         const int warps = blk / 32;
         return sizeof(PmpRobotTab) + (ws ? world_bytes : 0) + sizeof(int32_t) * ((W + 3) & ~3) +
                (size_t)warps * PMP_MAX_DOF * (sizeof(double) + 3 * sizeof(float));
     };
-    bool wsmem = true;
-    const size_t sm_total = 227 * 1024;
-    if (smem_for(256, true) + 1024 <= sm_total / 2 && smem_for(256, true) <= (size_t)ctx->max_smem_optin) {
-        block = 256; per_sm = 2;
-    } else if (smem_for(512, true) <= (size_t)ctx->max_smem_optin) {
-        block = 512; per_sm = 1;
-    } else {
-        wsmem = false; block = 256; per_sm = 2;
-    }
+    int wpc = (E + ctx->sm_count - 1) / ctx->sm_count;      // warps (= edges in flight) per CTA
+    if (wpc > 16) wpc = 16;
+    if (wpc < 1) wpc = 1;
+    int block = 32 * wpc, per_sm = 1;
+    // a CTA of fewer than 4 warps would spend longer staging the tables than using them
+    bool wsmem = wpc >= 4 && smem_for(block, true) <= (size_t)ctx->max_smem_optin;
+    // tuning knobs (profiling only): PMP_EDGE_BLOCK = threads per CTA, PMP_EDGE_PER_SM = resident CTAs per SM
+    if (const char* eb = getenv("PMP_EDGE_BLOCK")) { int v = atoi(eb); if (v >= 32 && v <= PMP_EDGE_MAXT && v % 32 == 0) block = v; }
+    if (const char* ep = getenv("PMP_EDGE_PER_SM")) { int v = atoi(ep); if (v >= 1 && v <= 16) per_sm = v; }
+    if (smem_for(block, wsmem) > (size_t)ctx->max_smem_optin) wsmem = false;
     const size_t smem = smem_for(block, wsmem);
     const int warps = block / 32;
     int grid = (E + warps - 1) / warps;

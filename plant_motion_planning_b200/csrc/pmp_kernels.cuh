@@ -174,104 +174,133 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
     }
     const bool solve = prm.mode == PMP_MODE_OUR_METHOD;
     const bool dense = prm.dense != 0;
-    const int K = solve ? prm.iterations : 1;
+    const int K = prm.iterations;
     float last = 0.f;
     for (int s = 0; s < n_stems; ++s) {
         const float* rec = wt + s * PMP_STEM_STRIDE;
         const int pslot = __float_as_int(rec[PMP_S_PSLOT]);
         const int oslot = __float_as_int(rec[PMP_S_OSLOT]);
         const int flags = __float_as_int(rec[PMP_S_FLAGS]);
+        // ---- joint frame: rest pose from the table while the ancestor chain is undeflected ----
         float Rv[9], tv[3];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Rv[i] = rec[PMP_S_RW0 + i];
+        tv[0] = rec[PMP_S_TW0]; tv[1] = rec[PMP_S_TW0 + 1]; tv[2] = rec[PMP_S_TW0 + 2];
         bool moved = false;
-        if (pslot < 0) {
-#pragma unroll
-            for (int i = 0; i < 9; ++i) Rv[i] = rec[PMP_S_RO + i];
-            tv[0] = rec[PMP_S_TO]; tv[1] = rec[PMP_S_TO + 1]; tv[2] = rec[PMP_S_TO + 2];
-        } else {
-            float Rp[9], tp[3];
-#pragma unroll
-            for (int i = 0; i < 9; ++i) Rp[i] = FR[0][i];
-            tp[0] = FT[0][0]; tp[1] = FT[0][1]; tp[2] = FT[0][2];
+        if (pslot >= 0) {
             moved = FM[0];
 #pragma unroll
-            for (int k = 1; k < NSLOT; ++k) {
-                if (pslot == k) {   // warp-uniform
+            for (int k = 1; k < NSLOT; ++k)
+                if (pslot == k) moved = FM[k];   // warp-uniform
+            if (dense || __any_sync(PMP_FULL, moved)) {
+                float Rp[9], tp[3];
 #pragma unroll
-                    for (int i = 0; i < 9; ++i) Rp[i] = FR[k][i];
-                    tp[0] = FT[k][0]; tp[1] = FT[k][1]; tp[2] = FT[k][2];
-                    moved = FM[k];
+                for (int i = 0; i < 9; ++i) Rp[i] = FR[0][i];
+                tp[0] = FT[0][0]; tp[1] = FT[0][1]; tp[2] = FT[0][2];
+#pragma unroll
+                for (int k = 1; k < NSLOT; ++k) {
+                    if (pslot == k) {
+#pragma unroll
+                        for (int i = 0; i < 9; ++i) Rp[i] = FR[k][i];
+                        tp[0] = FT[k][0]; tp[1] = FT[k][1]; tp[2] = FT[k][2];
+                    }
+                }
+                float Ro[9], Rc[9];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) Ro[i] = rec[PMP_S_RO + i];
+                pmp_mat_mul(Rp, Ro, Rc);
+                float x, y, z;
+                pmp_mat_vec(Rp, rec[PMP_S_TO], rec[PMP_S_TO + 1], rec[PMP_S_TO + 2], x, y, z);
+                if (moved) {
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) Rv[i] = Rc[i];
+                    tv[0] = x + tp[0]; tv[1] = y + tp[1]; tv[2] = z + tp[2];
                 }
             }
-            float Ro[9];
-#pragma unroll
-            for (int i = 0; i < 9; ++i) Ro[i] = rec[PMP_S_RO + i];
-            pmp_mat_mul(Rp, Ro, Rv);
-            float x, y, z;
-            pmp_mat_vec(Rp, rec[PMP_S_TO], rec[PMP_S_TO + 1], rec[PMP_S_TO + 2], x, y, z);
-            tv[0] = x + tp[0]; tv[1] = y + tp[1]; tv[2] = z + tp[2];
         }
         const float z0 = rec[PMP_S_Z0], z1 = rec[PMP_S_Z1], rad = rec[PMP_S_RAD], lim = rec[PMP_S_LIM];
-        float thx = 0.f, thy = 0.f;
-        float cx = 1.f, sx = 0.f, cy = 1.f, sy = 0.f;
-        float ux, uy, uz;
-        for (int it = 0; it < K; ++it) {
-            // stem axis u = Rv (sy, -sx cy, cx cy);  joint axes ax = Rv ex, ay = Rv (0, cx, sx)
-            pmp_mat_vec(Rv, sy, -sx * cy, cx * cy, ux, uy, uz);
-            const float axx = Rv[0], axy = Rv[3], axz = Rv[6];
-            float ayx, ayy, ayz;
-            pmp_mat_vec(Rv, 0.f, cx, sx, ayx, ayy, ayz);
-            // b = axis x u
-            const float bxx = axy * uz - axz * uy, bxy = axz * ux - axx * uz, bxz = axx * uy - axy * ux;
-            const float byx = ayy * uz - ayz * uy, byy = ayz * ux - ayx * uz, byz = ayx * uy - ayy * ux;
-            float Hxx = 0.f, Hxy = 0.f, Hyy = 0.f, gx = 0.f, gy = 0.f, S = 0.f;
+        // ---- phase 1: does any arm sphere touch the stem in its initial pose?  (exact, no rsqrt / Jacobian) ----
+        bool touch = false;
+        {
+            const float ux = Rv[2], uy = Rv[5], uz = Rv[8];
 #pragma unroll
             for (int a = 0; a < A; ++a) {
                 const float wx = c[a][0] - tv[0], wy = c[a][1] - tv[1], wz = c[a][2] - tv[2];
                 const float tau = pmp_clamp(fmaf(wx, ux, fmaf(wy, uy, wz * uz)), z0, z1);
                 const float dx = fmaf(-tau, ux, wx), dy = fmaf(-tau, uy, wy), dz = fmaf(-tau, uz, wz);
-                const float d2 = fmaxf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)), 1e-24f);
-                const float inv = rsqrtf(d2);
-                const float pen = fmaxf((rt.sph_radius[a] + rad) - d2 * inv, 0.f);
-                const float sc = -tau * inv;
-                const float Jx = sc * fmaf(dx, bxx, fmaf(dy, bxy, dz * bxz));
-                const float Jy = sc * fmaf(dx, byx, fmaf(dy, byy, dz * byz));
-                const float pJx = pen * Jx, pJy = pen * Jy;
-                Hxx = fmaf(pJx, Jx, Hxx);
-                Hxy = fmaf(pJx, Jy, Hxy);
-                Hyy = fmaf(pJy, Jy, Hyy);
-                gx = fmaf(pen, pJx, gx);
-                gy = fmaf(pen, pJy, gy);
-                S += pen;
+                const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                const float rr = rt.sph_radius[a] + rad;
+                touch |= d2 < rr * rr;
             }
-            const bool act = S > 0.f;
-            if (!solve) { out.plant_hit |= act; break; }
-            if (!dense && !__any_sync(PMP_FULL, act)) break;   // no lane is pushing this stem: later steps are no-ops
-            const float lam = prm.reg_eps * S;
-            const float a11 = Hxx + lam, a22 = Hyy + lam;
-            const float det = fmaf(a11, a22, -Hxy * Hxy);
-            const float idet = act ? __frcp_rn(det) : 0.f;
-            float dtx = (a22 * gx - Hxy * gy) * idet;
-            float dty = (a11 * gy - Hxy * gx) * idet;
-            dtx = pmp_clamp(dtx, -prm.max_step, prm.max_step);
-            dty = pmp_clamp(dty, -prm.max_step, prm.max_step);
-            thx = pmp_clamp(thx + dtx, -lim, lim);
-            thy = pmp_clamp(thy + dty, -lim, lim);
-            __sincosf(thx, &sx, &cx);
-            __sincosf(thy, &sy, &cy);
+        }
+        float thx = 0.f, thy = 0.f;
+        float cx = 1.f, sx = 0.f, cy = 1.f, sy = 0.f;
+        if (!solve) {
+            out.plant_hit |= touch;          // avoid_all: the undeflected plant is an obstacle (env.py:75-77)
+        } else if (dense || __any_sync(PMP_FULL, touch)) {
+            // ---- phase 2: K damped Gauss-Newton steps (oracle plant_equilibrium) ----
+            for (int it = 0; it < K; ++it) {
+                // stem axis u = Rv (sy, -sx cy, cx cy);  joint axes ax = Rv ex, ay = Rv (0, cx, sx)
+                float ux, uy, uz;
+                pmp_mat_vec(Rv, sy, -sx * cy, cx * cy, ux, uy, uz);
+                const float axx = Rv[0], axy = Rv[3], axz = Rv[6];
+                float ayx, ayy, ayz;
+                pmp_mat_vec(Rv, 0.f, cx, sx, ayx, ayy, ayz);
+                const float bxx = axy * uz - axz * uy, bxy = axz * ux - axx * uz, bxz = axx * uy - axy * ux;
+                const float byx = ayy * uz - ayz * uy, byy = ayz * ux - ayx * uz, byz = ayx * uy - ayy * ux;
+                float Hxx = 0.f, Hxy = 0.f, Hyy = 0.f, gx = 0.f, gy = 0.f, S = 0.f;
+#pragma unroll
+                for (int a = 0; a < A; ++a) {
+                    const float wx = c[a][0] - tv[0], wy = c[a][1] - tv[1], wz = c[a][2] - tv[2];
+                    const float tau = pmp_clamp(fmaf(wx, ux, fmaf(wy, uy, wz * uz)), z0, z1);
+                    const float dx = fmaf(-tau, ux, wx), dy = fmaf(-tau, uy, wy), dz = fmaf(-tau, uz, wz);
+                    const float d2 = fmaxf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)), 1e-24f);
+                    const float inv = rsqrtf(d2);
+                    const float pen = fmaxf((rt.sph_radius[a] + rad) - d2 * inv, 0.f);
+                    const float sc = -tau * inv;
+                    const float Jx = sc * fmaf(dx, bxx, fmaf(dy, bxy, dz * bxz));
+                    const float Jy = sc * fmaf(dx, byx, fmaf(dy, byy, dz * byz));
+                    const float pJx = pen * Jx, pJy = pen * Jy;
+                    Hxx = fmaf(pJx, Jx, Hxx);
+                    Hxy = fmaf(pJx, Jy, Hxy);
+                    Hyy = fmaf(pJy, Jy, Hyy);
+                    gx = fmaf(pen, pJx, gx);
+                    gy = fmaf(pen, pJy, gy);
+                    S += pen;
+                }
+                // a stem that nothing touches in its initial pose is never pushed: it stays at theta = 0
+                const bool act = touch && (S > 0.f);
+                if (!dense && !__any_sync(PMP_FULL, act)) break;   // later steps would be no-ops for every lane
+                const float lam = prm.reg_eps * S;
+                const float a11 = Hxx + lam, a22 = Hyy + lam;
+                const float det = fmaf(a11, a22, -Hxy * Hxy);
+                const float idet = act ? __frcp_rn(det) : 0.f;
+                float dtx = (a22 * gx - Hxy * gy) * idet;
+                float dty = (a11 * gy - Hxy * gx) * idet;
+                dtx = pmp_clamp(dtx, -prm.max_step, prm.max_step);
+                dty = pmp_clamp(dty, -prm.max_step, prm.max_step);
+                thx = pmp_clamp(thx + dtx, -lim, lim);
+                thy = pmp_clamp(thy + dty, -lim, lim);
+                __sincosf(thx, &sx, &cx);
+                __sincosf(thy, &sy, &cy);
+            }
         }
         const bool bent = (thx != 0.f) || (thy != 0.f);
         moved |= bent;
         // final link frame R_s = Rv Rx(thx) Ry(thy)
         float Rs[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Rs[i] = Rv[i];
         if (dense || __any_sync(PMP_FULL, bent)) {
-            float M[9];
+            float M[9], Rb[9];
             M[0] = cy;       M[1] = 0.f; M[2] = sy;
             M[3] = sx * sy;  M[4] = cx;  M[5] = -sx * cy;
             M[6] = -cx * sy; M[7] = sx;  M[8] = cx * cy;
-            pmp_mat_mul(Rv, M, Rs);
-        } else {
+            pmp_mat_mul(Rv, M, Rb);
+            if (bent) {
 #pragma unroll
-            for (int i = 0; i < 9; ++i) Rs[i] = Rv[i];
+                for (int i = 0; i < 9; ++i) Rs[i] = Rb[i];
+            }
         }
         // observer
         float raw = 0.f;
@@ -331,7 +360,7 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
             if (defl_out) defl_out[s] = d;
             if (theta_out) { theta_out[2 * s] = thx; theta_out[2 * s + 1] = thy; }
         }
-        // keep the frame for children
+        // keep the frame for children (always: the slot register file has no notion of "rest")
 #pragma unroll
         for (int k = 0; k < NSLOT; ++k) {
             if (oslot == k) {   // warp-uniform
@@ -393,8 +422,14 @@ struct PmpEdgeArgs {
 };
 
 // Edge-batch kernel.  Persistent CTAs; warp = edge, lane = step.
+#ifndef PMP_EDGE_MAXT
+#define PMP_EDGE_MAXT 512
+#endif
+#ifndef PMP_EDGE_MINB
+#define PMP_EDGE_MINB 1
+#endif
 template <int A, int NSLOT, bool WSMEM>
-__global__ void __launch_bounds__(512, 1) pmp_edge_kernel(const PmpEdgeArgs args) {
+__global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(const PmpEdgeArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PmpRobotTab& rt = *reinterpret_cast<PmpRobotTab*>(smem_raw);
     float* sm_stems = reinterpret_cast<float*>(smem_raw + sizeof(PmpRobotTab));

@@ -13,6 +13,8 @@
 //  [19..21] observer reference point (ANGLE only)
 //  [22] COM offset along local z     [23] unused
 //  [24] int parent frame slot (-1 = root)   [25] int own frame slot (-1 = leaf)   [26] int flags
+//  [32..40] Rw0  [41..43] tw0   world pose of the joint frame with every stem at rest (used while the
+//           whole ancestor chain is undeflected, so untouched plants never compose frames)
 #define PMP_S_RO 0
 #define PMP_S_TO 9
 #define PMP_S_Z0 12
@@ -25,6 +27,8 @@
 #define PMP_S_PSLOT 24
 #define PMP_S_OSLOT 25
 #define PMP_S_FLAGS 26
+#define PMP_S_RW0 32
+#define PMP_S_TW0 41
 
 #define PMP_SF_PLANT_START 1  // observer chain restarts here           (representation.py:270)
 #define PMP_SF_IS_MAIN 2      // updates the running main-stem angle    (representation.py:289)

@@ -18,7 +18,7 @@ from .plants import DEFAULT_STEM_RADIUS, OBS_ANGLE, OBS_MOD3, PlantWorld, Stem
 from .robot import (MAX_FIXED_PRIMS, PRIM_BOX, FixedPrim, RobotModel, joint_constant_matrices)
 from .transforms import Frame, rot_x, rot_y, rpy_to_matrix
 
-STEM_STRIDE = 32          # floats per stem record
+STEM_STRIDE = 48          # floats per stem record
 BOX_STRIDE = 16           # floats per world box record
 MAX_STEMS = 32            # per world
 MAX_WORLD_BOXES = 32
@@ -27,6 +27,7 @@ MAX_SLOTS = 8
 # stem record field offsets (floats)
 S_RO, S_TO, S_Z0, S_Z1, S_RAD, S_LIM, S_OBSV, S_OBSP, S_COMZ = 0, 9, 12, 13, 14, 15, 16, 19, 22
 S_PSLOT, S_OSLOT, S_FLAGS = 24, 25, 26
+S_RW0, S_TW0 = 32, 41
 F_PLANT_START, F_IS_MAIN, F_OBS_ANGLE, F_OBS_ROOT, F_SNAP, F_HAS_PARENT = 1, 2, 4, 8, 16, 32
 
 MODE_OUR_METHOD, MODE_AVOID_ALL, MODE_IGNORE_ALL = 0, 1, 2
@@ -195,6 +196,8 @@ def pack_stem_records(world: PlantWorld, stem_radius: Optional[float] = None) ->
         rec[i, S_TO:S_TO + 3] = s.origin.t
         rec[i, S_Z0], rec[i, S_Z1], rec[i, S_RAD], rec[i, S_LIM] = z0, z1, r, s.limit
         rec[i, S_COMZ] = s.com_z
+        rec[i, S_RW0:S_RW0 + 9] = rest[i].R.reshape(-1)
+        rec[i, S_TW0:S_TW0 + 3] = rest[i].t
         flags = 0
         if s.plant_start:
             flags |= F_PLANT_START
