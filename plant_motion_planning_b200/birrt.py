@@ -1,0 +1,179 @@
+"""Multi-world BiRRT driver on top of the GPU edge checker  (the callers of the hot path).
+
+Control flow restated from the lab's fork so that decisions can be compared edge by edge:
+  extend_towards ............ motion_planners/motion_planners/primitives.py:196-255 (extend_towards_with_angle_constraint_multi_world)
+  check_forward_path ........ motion_planners/motion_planners/rrt_connect_with_angle_constraints_v2.py:143-198
+  rrt_connect_multi_world ... same file :202-280 (swap alternation, max_iterations forced to 2000)
+  forward re-check + EE length  motion_planners/motion_planners/meta.py:222-248
+What changes is the cost of one extension: the reference spends N x (50 stepSimulation + W collision closures);
+here one extension is ONE kernel launch over its N configurations x W worlds, and `extend_many` validates a whole
+batch of candidate extensions in one launch (additive API).
+
+The random 5 % pass-through of exceeded deflections (pybullet_tools/utils.py:3843) is replayed on the host from the
+raw per-(step, world) flags, drawing np.random.rand() in the reference's order, so runs are reproducible from the
+same seeds regardless of the backend that produced the flags.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .edgecheck import FLAG_EXCEEDED, FLAG_RIGID
+from .planner_fns import GATE_PROBABILITY, asymmetric_extend
+
+Conf = Tuple[float, ...]
+
+
+class TreeNode:
+    """TreeNode_v2 without the Bullet snapshot (motion_planners/motion_planners/rrt.py:7-35)."""
+    __slots__ = ("config", "parent")
+
+    def __init__(self, config: Conf, parent: Optional["TreeNode"] = None):
+        self.config = config
+        self.parent = parent
+
+    def retrace(self) -> List["TreeNode"]:
+        seq, node = [], self
+        while node is not None:
+            seq.append(node)
+            node = node.parent
+        return seq[::-1]
+
+
+class FlagBackend:
+    """Anything that maps a list of configurations to raw flags uint8 [n, W] (bit0 rigid, bit1 exceeded)."""
+
+    def flags(self, configs: Sequence[Conf]) -> np.ndarray:  # pragma: no cover - interface
+        raise NotImplementedError
+
+
+class GpuBackend(FlagBackend):
+    def __init__(self, checker):
+        self.checker = checker
+        self.launches = 0
+
+    def flags(self, configs: Sequence[Conf]) -> np.ndarray:
+        self.launches += 1
+        q = np.asarray(configs, dtype=np.float32).reshape(-1, self.checker.dof)
+        return self.checker.check_configs_host(q, detail=False)["flags"]
+
+
+def first_violation(flags: np.ndarray, forward: bool, probability: float = GATE_PROBABILITY,
+                    rand: Optional[Callable[[], float]] = None) -> int:
+    """Index of the first configuration the reference's checker would reject (len(flags) if none):
+    worlds in construction order with early exit (env.py:230-247), forward checker = rigid | (exceeded & gate),
+    backward checker = rigid only."""
+    rand = np.random.rand if rand is None else rand
+    n, W = flags.shape
+    for i in range(n):
+        for w in range(W):
+            f = flags[i, w]
+            if f & FLAG_RIGID:
+                return i
+            if forward and (f & FLAG_EXCEEDED) and rand() < probability:
+                return i
+    return n
+
+
+@dataclass
+class PlanLog:
+    """Every edge the planner proposed: (kind, n configurations, first violation)."""
+    edges: List[Tuple[str, int, int]] = field(default_factory=list)
+    iterations: int = 0
+
+
+def extend_towards(tree: List[TreeNode], target: Conf, distance_fn, extend_fn, backend: FlagBackend, forward: bool,
+                   swap: bool, log: Optional[PlanLog] = None) -> Tuple[TreeNode, bool]:
+    scores = [distance_fn(n.config, target) for n in tree]
+    last = tree[scores.index(min(scores))]
+    extend = list(asymmetric_extend(last.config, target, extend_fn, backward=swap))
+    k = first_violation(backend.flags(extend), forward) if extend else 0
+    if log is not None:
+        log.edges.append(("fwd" if forward else "back", len(extend), k))
+    for q in extend[:k]:
+        last = TreeNode(q, parent=last)
+        tree.append(last)
+    return last, k == len(extend)
+
+
+def check_forward_path(path2: List[TreeNode], backend: FlagBackend, nodes1: List[TreeNode], nodes2: List[TreeNode],
+                       log: Optional[PlanLog] = None) -> bool:
+    """Re-validate the backward tree's half with the forward (plant-aware) checker."""
+    last = nodes1[-1]
+    nodes2.clear()
+    tail = [n.config for n in path2[1:]]
+    k = first_violation(backend.flags(tail), True) if tail else 0
+    if log is not None:
+        log.edges.append(("recheck", len(tail), k))
+    for q in tail[:k]:
+        last = TreeNode(q, parent=last)
+        nodes1.append(last)
+    if k < len(tail):
+        nodes2.extend(path2[k + 1:])
+        return False
+    return True
+
+
+def rrt_connect_multi_world(start: Conf, goal: Conf, distance_fn, sample_fn, extend_fn, backend: FlagBackend,
+                            max_iterations: int = 2000, log: Optional[PlanLog] = None):
+    """Returns (path of configurations, node path) or (None, None)."""
+    if first_violation(backend.flags([start]), True) == 0:
+        return None
+    nodes1, nodes2 = [TreeNode(start)], [TreeNode(goal)]
+    swap = True
+    for it in range(max_iterations):
+        if log is not None:
+            log.iterations = it + 1
+        swap = not swap
+        target = sample_fn()
+        last1, _ = extend_towards(nodes1, target, distance_fn, extend_fn, backend, True, swap, log)
+        last2, success = extend_towards(nodes2, last1.config, distance_fn, extend_fn, backend, False, not swap, log)
+        if success:
+            path1, path2 = last1.retrace(), last2.retrace()[::-1]
+            if check_forward_path(path2, backend, nodes1, nodes2, log):
+                node_path = path1[:-1] + path2
+                return [n.config for n in node_path], node_path
+            if not nodes2:
+                # the reference leaves tree2 with the unreached remainder; if nothing remains, regrow from the goal
+                nodes2.append(TreeNode(goal))
+            swap = True
+    return None, None
+
+
+def plan(env, start: Conf, goal: Conf, distance_fn, sample_fn, extend_fn, backend: Optional[FlagBackend] = None,
+         max_iterations: int = 2000, log: Optional[PlanLog] = None):
+    """check_initial_end_multi_world + rrt_connect + forward re-check with EE path length
+    (pybullet_tools/utils.py:4358-4380; meta.py:222-248).  Returns (path, ee_len, over[W]) or None."""
+    backend = backend or GpuBackend(env.checker)
+    for name, q in (("Initial", start), ("End", goal)):
+        if first_violation(backend.flags([q]), True) == 0:
+            raise ValueError(f"{name} configuration is in collision")       # the reference exit()s here
+    res = rrt_connect_multi_world(start, goal, distance_fn, sample_fn, extend_fn, backend, max_iterations, log)
+    if res is None or res[0] is None:
+        return None
+    path = res[0]
+    k = first_violation(backend.flags(path), True)
+    if log is not None:
+        log.edges.append(("final", len(path), k))
+    if k < len(path):
+        return None
+    ee_len, over, _ = env.path_cost(start, path)
+    return path, ee_len, over
+
+
+# ------------------------------------------------------------------------------------------------ batched proposals
+def extend_many(checker, q_from: np.ndarray, q_to: np.ndarray, backward: bool = False, forward_checker: bool = True,
+                probability: float = GATE_PROBABILITY, rand: Optional[Callable[[], float]] = None):
+    """Validate a batch of candidate extensions / shortcuts in ONE launch (pmp_validate_edges_host) and apply the
+    gate per edge in batch order.  Returns (first_violation[E], n_steps[E], result dict)."""
+    from .planner_fns import replay_gate
+    out = checker.validate_edges_host(q_from, q_to, backward=backward, want_masks=True)
+    E = out["n_steps"].shape[0]
+    cap = out["rigid_mask"].shape[2] * 32
+    first = np.empty(E, np.int32)
+    for e in range(E):
+        n = min(int(out["n_steps"][e]), cap)
+        first[e] = replay_gate(n, out["rigid_mask"][e], out["exceed_mask"][e], probability, rand, forward_checker)
+    return first, out["n_steps"], out
