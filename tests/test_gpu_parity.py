@@ -279,6 +279,43 @@ def test_full_sweep_shape_checksum_against_oracle_sample(sweep):
     assert np.percentile(md, 99.5) <= 1e-4
 
 
+def test_many_worlds_tables_outside_shared_memory(ctx):
+    """BASELINE config 5 shape (W = 256): the stem tables (295 KB) no longer fit in shared memory and are read
+    through L1; results must not depend on where the tables live."""
+    from oracle.c_oracle import COracle
+    from plant_motion_planning_b200 import EdgeCheckConfig, EdgeChecker
+    from plant_motion_planning_b200.workloads import synthetic_edges, synthetic_worlds
+    torch, model = ctx["torch"], ctx["model"]
+    worlds = synthetic_worlds(256, seed_base=1)
+    chk = EdgeChecker(model, worlds, EdgeCheckConfig(max_steps=32))
+    q0, q1 = synthetic_edges(model, 4096, seed=1)
+    out = chk.validate_edges(torch.from_numpy(q0), torch.from_numpy(q1))
+    torch.cuda.synchronize()
+    assert chk.launch_info()["worlds_in_smem"] == 0
+    idx = np.arange(0, 4096, 64)
+    c = COracle(model, worlds).validate_edges(q0[idx], q1[idx], max_steps=32)
+    assert (out.first_hit.cpu().numpy()[idx] != c["first_hit"]).mean() <= 0.02
+    md = np.abs(out.max_deflection.cpu().numpy()[idx] - c["max_deflection"])
+    assert np.percentile(md, 99.5) <= 1e-4
+    # same worlds, first 64 only, tables in shared memory: identical columns
+    chk64 = EdgeChecker(model, worlds[:64], EdgeCheckConfig(max_steps=32))
+    o64 = chk64.validate_edges(torch.from_numpy(q0), torch.from_numpy(q1))
+    assert chk64.launch_info()["worlds_in_smem"] == 1
+    assert torch.equal(o64.max_deflection, out.max_deflection[:, :64])
+    assert torch.equal(o64.over_limit, out.over_limit[:, :64])
+
+
+def test_small_batches_spread_over_sms(ctx):
+    torch, chk = ctx["torch"], ctx["chk"]
+    from plant_motion_planning_b200.workloads import random_edges
+    q0, q1 = random_edges(ctx["model"], 40, seed=2)
+    a = chk.validate_edges(torch.from_numpy(q0), torch.from_numpy(q1))
+    info = chk.launch_info()
+    assert info["grid"] == 40 and info["block"] == 32
+    b = chk.validate_edges(torch.from_numpy(np.tile(q0, (100, 1))), torch.from_numpy(np.tile(q1, (100, 1))))
+    assert torch.equal(a.first_hit, b.first_hit[:40]) and torch.equal(a.max_deflection, b.max_deflection[:40])
+
+
 # ---------------------------------------------------------------- fixtures of the reference and other world kinds
 def test_saved_multi_branch_fixtures(ctx):
     """environments/multi_branch/env1..4 (URDF + pickle -> CharacterizePlant / _mod observer)."""

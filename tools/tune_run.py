@@ -39,10 +39,11 @@ for lib in libs:
     maxt = int(name.split("_")[0][1:])
     minb = int(name.split("_")[1][1:])
     combos = {(maxt, minb)}
-    if maxt >= 256:
-        combos.add((256, max(1, minb * maxt // 256)))
-    if maxt >= 128:
-        combos.add((128, max(1, minb * maxt // 128)))
+    if os.environ.get("TUNE_ALL_SPLITS"):
+        if maxt >= 256:
+            combos.add((256, max(1, minb * maxt // 256)))
+        if maxt >= 128:
+            combos.add((128, max(1, minb * maxt // 128)))
     for block, per_sm in sorted(combos):
         env = dict(os.environ, PMP_LIB=lib, PMP_EDGE_BLOCK=str(block), PMP_EDGE_PER_SM=str(per_sm))
         p = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)
