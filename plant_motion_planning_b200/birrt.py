@@ -163,6 +163,105 @@ def plan(env, start: Conf, goal: Conf, distance_fn, sample_fn, extend_fn, backen
     return path, ee_len, over
 
 
+# ------------------------------------------------------------------------------------------------ shortcut smoothing
+def _path_length(waypoints: Sequence[Conf], distance_fn) -> float:
+    return sum(distance_fn(a, b) for a, b in zip(waypoints[:-1], waypoints[1:]))
+
+
+def waypoints_from_path(path: Sequence[Conf], tolerance: float = 1e-3) -> List[Conf]:
+    """Corner points of a dense path (motion_planners/motion_planners/utils.py:229-260, waypoints_from_path_v4):
+    consecutive duplicates dropped, a waypoint kept wherever the unit direction changes by more than `tolerance`."""
+    pts = [tuple(path[0])]
+    for q in path[1:]:
+        if not np.allclose(q, pts[-1], atol=tolerance, rtol=0):
+            pts.append(tuple(q))
+    if len(pts) < 3:
+        return pts
+    unit = lambda a, b: (np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(np.asarray(a) - np.asarray(b)), 1e-300)
+    way = [pts[0]]
+    last_conf = pts[1]
+    last_dir = unit(last_conf, way[-1])
+    for conf in pts[2:]:
+        d = unit(conf, way[-1])
+        if not np.allclose(last_dir, d, atol=tolerance, rtol=0):
+            way.append(last_conf)
+            d = unit(conf, way[-1])
+        last_conf, last_dir = conf, d
+    way.append(last_conf)
+    return way
+
+
+def smooth_path_multi_world(path: Sequence[Conf], extend_fn, distance_fn, backend: FlagBackend, max_iterations: int = 20,
+                            log: Optional[PlanLog] = None) -> List[Conf]:
+    """Shortcut smoother of the lab's fork (motion_planners/motion_planners/smoothing.py:55-141): per iteration two
+    segments are drawn with probability proportional to their length (np.random.choice), a point is drawn on each
+    (random.random), and the shortcut between them is kept if it shortens the path and passes the forward checker.
+    One kernel launch per tried shortcut."""
+    import random as _random
+    way = waypoints_from_path(path)
+    for _ in range(max_iterations):
+        if len(way) <= 2:
+            break
+        segs = list(zip(range(len(way) - 1), range(1, len(way))))
+        dists = [distance_fn(way[i], way[j]) for i, j in segs]
+        total = sum(dists)
+        i1, i2 = np.random.choice(list(range(len(segs))), size=2, replace=True, p=np.array(dists) / total)
+        if i1 == i2:
+            continue
+        if i2 < i1:
+            i1, i2 = i2, i1
+        pts = []
+        for (i, j) in (segs[i1], segs[i2]):
+            w = _random.random()
+            pts.append(tuple((1 - w) * np.array(way[i]) + w * np.array(way[j])))
+        p1, p2 = pts
+        new_way = way[:segs[i1][0] + 1] + [p1, p2] + way[segs[i2][1]:]
+        if _path_length(new_way, distance_fn) >= total:
+            continue
+        cfgs = list(extend_fn(p1, p2))
+        k = first_violation(backend.flags(cfgs), True) if cfgs else 0
+        if log is not None:
+            log.edges.append(("shortcut", len(cfgs), k))
+        if k == len(cfgs):
+            way = new_way
+    out = [way[0]]
+    for a, b in zip(way[:-1], way[1:]):
+        out.extend(extend_fn(a, b))
+    return out
+
+
+def smooth_path_batched(checker, path: Sequence[Conf], distance_fn, rounds: int = 10, proposals: int = 256,
+                        seed: int = 0) -> List[Conf]:
+    """Additive batched smoother: every round proposes `proposals` random shortcuts between points of the current
+    waypoint polyline, validates ALL of them in one pmp_validate_edges launch (gate applied in batch order) and
+    applies the valid one that shortens the path most."""
+    rng = np.random.RandomState(seed)
+    way = [np.asarray(w, dtype=np.float64) for w in waypoints_from_path(path)]
+    for _ in range(rounds):
+        if len(way) <= 2:
+            break
+        seg_len = np.array([distance_fn(tuple(a), tuple(b)) for a, b in zip(way[:-1], way[1:])])
+        cum = np.concatenate([[0.0], np.cumsum(seg_len)])
+        s = np.sort(rng.uniform(0.0, cum[-1], size=(proposals, 2)), axis=1)
+        seg = np.clip(np.searchsorted(cum, s, side="right") - 1, 0, len(seg_len) - 1)
+        frac = (s - cum[seg]) / np.maximum(seg_len[seg], 1e-300)
+        W = np.stack(way)
+        P = W[seg] * (1 - frac[..., None]) + W[seg + 1] * frac[..., None]          # [proposals, 2, D]
+        direct = np.array([distance_fn(tuple(P[k, 0]), tuple(P[k, 1])) for k in range(proposals)])
+        gain = (s[:, 1] - s[:, 0]) - direct
+        ok = (seg[:, 0] != seg[:, 1]) & (gain > 1e-9)
+        if not ok.any():
+            continue
+        idx = np.nonzero(ok)[0]
+        first, n, _ = extend_many(checker, P[idx, 0].astype(np.float32), P[idx, 1].astype(np.float32))
+        valid = first >= n
+        if not valid.any():
+            continue
+        best = idx[valid][np.argmax(gain[idx][valid])]
+        way = way[:seg[best, 0] + 1] + [P[best, 0], P[best, 1]] + way[seg[best, 1] + 1:]
+    return [tuple(float(v) for v in w) for w in way]
+
+
 # ------------------------------------------------------------------------------------------------ batched proposals
 def extend_many(checker, q_from: np.ndarray, q_to: np.ndarray, backward: bool = False, forward_checker: bool = True,
                 probability: float = GATE_PROBABILITY, rand: Optional[Callable[[], float]] = None):

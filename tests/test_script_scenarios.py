@@ -106,3 +106,38 @@ def test_batched_extension_equals_sequential():
         seq.append(birrt.first_violation(be.flags(cfgs), True))
     assert after_batched == np.random.rand()
     assert list(first) == seq
+
+
+def test_smoothing_sequential_parity_and_batched_validity():
+    """Shortcut smoothing after a plan: the sequential smoother makes identical decisions on GPU and oracle flags;
+    the batched smoother (one launch per round) returns a shorter path that the oracle also accepts."""
+    from plant_motion_planning_b200 import EdgeCheckConfig, EdgeChecker, birrt, load_iiwa14, planner_fns as F
+    from plant_motion_planning_b200.scenarios import GOAL, START, script_worlds
+    worlds, cfg = script_worlds("multi_world_our_method")
+    robot = load_iiwa14()
+    chk = EdgeChecker(robot, worlds, EdgeCheckConfig(mode=cfg["mode"], deflection_limit=cfg["deflection_limit"]))
+    dist, ext, samp = F.get_distance_fn(robot), F.get_extend_fn(robot), F.get_sample_fn(robot)
+    np.random.seed(1)
+    random.seed(1)
+    path, _ = birrt.rrt_connect_multi_world(START, GOAL, dist, samp, ext, birrt.GpuBackend(chk), max_iterations=400)
+    assert path is not None
+    logs = []
+    outs = []
+    for backend in (birrt.GpuBackend(chk), OracleBackend(robot, worlds, mode=cfg["mode"], deflection_limit=cfg["deflection_limit"])):
+        np.random.seed(7)
+        random.seed(7)
+        log = birrt.PlanLog()
+        outs.append(birrt.smooth_path_multi_world(path, ext, dist, backend, max_iterations=20, log=log))
+        logs.append(log.edges)
+    assert logs[0] == logs[1] and outs[0] == outs[1]
+    length = lambda p: sum(dist(a, b) for a, b in zip(p[:-1], p[1:]))
+    assert length(outs[0]) <= length(path) + 1e-9
+    np.random.seed(3)
+    way = birrt.smooth_path_batched(chk, path, dist, rounds=6, proposals=128, seed=2)
+    assert way[0] == tuple(path[0]) and np.allclose(way[-1], path[-1])
+    assert length(way) <= length(birrt.waypoints_from_path(path)) + 1e-9
+    ob = OracleBackend(robot, worlds, mode=cfg["mode"], deflection_limit=cfg["deflection_limit"])
+    for a, b in zip(way[:-1], way[1:]):
+        cfgs = list(ext(a, b))
+        fl = ob.flags(cfgs)
+        assert not (fl & 1).any(), "batched smoother produced a segment the oracle rejects"
