@@ -119,7 +119,7 @@ def run_reference(args, rank: int) -> None:
         return
     from oracle.c_oracle import COracle
     model, worlds, q0, q1 = workload(argparse.Namespace(**{**vars(args), "edges": min(args.edges, 1 << 15)}), seed=0)
-    co = COracle(model, worlds, iterations=args.iterations)
+    co = COracle(model, worlds, iterations=args.iterations, native=True)
     cores = co.max_threads
     # bounded sample: calibrate on 256 edges, then size a step for ~args.cpu_seconds / (steps + warmup)
     t0 = time.perf_counter()
@@ -315,7 +315,7 @@ def main() -> None:
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle.c_oracle import COracle
-        co = COracle(model, worlds, iterations=args.iterations)
+        co = COracle(model, worlds, iterations=args.iterations, native=True)
         t0 = time.perf_counter()
         co.validate_edges(q0[:256], q1[:256], max_steps=args.edge_steps)
         dt = max(time.perf_counter() - t0, 1e-4)

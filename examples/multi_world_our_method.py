@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""scripts/multi_world_our_method.py of the reference, on the B200 edge checker (needs a GPU).
+
+    python examples/multi_world_our_method.py [--script multi_world_our_method|multi_world_avoid_all|multi_world_ignore_all]
+                                              [--deflection_limit X] [--iterations N] [--smooth]
+
+Same seeds, plant sampler and planner control flow as the reference script (seed 1, limits ((0,0),(0.35,0.35)),
+plant (1,2,1), deflection limit 2.0, one world); the robot is the vendored iiwa14 instead of the non-vendored Val.
+Prints the path length, the end-effector path cost and the per-world deflection-over-limit
+(Command.execute_multi_world's report, pybullet_tools/kuka_primitives.py:511-521).
+"""
+import argparse
+import os
+import random
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from plant_motion_planning_b200 import birrt, planner_fns as F  # noqa: E402
+from plant_motion_planning_b200.env import MultiPlantWorld  # noqa: E402
+from plant_motion_planning_b200.scenarios import GOAL, SCRIPTS, START  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--script", default="multi_world_our_method", choices=sorted(SCRIPTS))
+    ap.add_argument("--deflection_limit", type=float, default=None)
+    ap.add_argument("--iterations", type=int, default=2000)
+    ap.add_argument("--smooth", action="store_true")
+    args = ap.parse_args()
+    cfg = SCRIPTS[args.script]
+    limit = cfg["deflection_limit"] if args.deflection_limit is None else args.deflection_limit
+
+    np.random.seed(cfg["seed"])
+    random.seed(cfg["seed"])
+    env = MultiPlantWorld(cfg["xs"], cfg["ys"], limit, *cfg["args"], cfg["limits"], avoid_all=cfg["avoid_all"])
+    if cfg["mode"] == "ignore_all":
+        env.checker.set_config(mode="ignore_all")
+    robot = env.sample_robot
+    dist, samp, ext = F.get_distance_fn(robot), F.get_sample_fn(robot), F.get_extend_fn(robot)
+    backend = birrt.GpuBackend(env.checker)
+    log = birrt.PlanLog()
+    t0 = time.time()
+    res = None
+    for attempt in range(200):                      # planner.py:36-48
+        res = birrt.plan(env, START, GOAL, dist, samp, ext, backend, max_iterations=args.iterations, log=log)
+        if res is not None:
+            break
+    if res is None:
+        print("Unable to find a plan!")
+        return 1
+    path, ee_len, over = res
+    print(f"plan: {len(path)} configurations, {len(log.edges)} edges checked in {backend.launches} kernel launches, "
+          f"{time.time() - t0:.2f} s")
+    if args.smooth:
+        path = birrt.smooth_path_multi_world(path, ext, dist, backend, max_iterations=20)
+        ee_len, over, _ = env.path_cost(START, path)
+        print(f"smoothed: {len(path)} configurations")
+    print("====================================================")
+    print("total path cost: ", ee_len)
+    print("total Deflection over limit: ", over)
+    print("alpha: ", env.config.alpha)
+    print("====================================================")
+    print("Total cost: ", ee_len + env.config.alpha * over)
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

@@ -27,15 +27,28 @@ def build(force: bool = False) -> str:
 
 
 _lib = None
+NATIVE_LIB = os.path.join(HERE, "_build", "liboracle_edgecheck_native.so")
 
 
-def load():
+def build_native() -> bool:
+    """Rebuild with -march=native on THIS machine (used by bench.py for the timed CPU baseline)."""
+    try:
+        subprocess.run(["make", "-C", HERE, "native"], check=True, capture_output=True)
+        return os.path.exists(NATIVE_LIB)
+    except Exception:
+        return False
+
+
+def load(native: bool = False):
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB):
+        path = LIB
+        if native and build_native():
+            path = NATIVE_LIB
+        elif not os.path.exists(LIB):
             build()
         try:
-            _lib = C.CDLL(LIB)
+            _lib = C.CDLL(path)
         except OSError:
             build(force=True)
             _lib = C.CDLL(LIB)
@@ -55,8 +68,9 @@ class COracle:
     """Holds the packed tables (same packer as the CUDA path) and calls the C twin."""
 
     def __init__(self, robot, worlds, obstacles=None, resolution=np.radians(3), deflection_limit=0.30, alpha=0.1,
-                 iterations=4, max_step=0.5, reg_eps=1e-4, stem_radius=None, mode="our_method", dense=False):
-        self.lib = load()
+                 iterations=4, max_step=0.5, reg_eps=1e-4, stem_radius=None, mode="our_method", dense=False,
+                 native=False):
+        self.lib = load(native)
         self.rt = pack_robot(robot, obstacles)
         self.wt = pack_worlds(list(worlds), stem_radius)
         t = self.rt
