@@ -15,6 +15,7 @@ Everything that is *arithmetic of the reference* runs unmodified from /root/refe
                                observe_all_and_check (representation.py) on link poses served by the stub
   reference_gate.json          get_collision_fn_with_angle_constraints_v4 (pybullet_tools/utils.py:3827-3857):
                                result and number of np.random draws for scripted (rigid, exceeded) flags
+  reference_fk.json            iiwa14 link frames composed with the reference's pybullet_tools/transformations.py
   seed1_plant.json             models/plant.urdf + models/plant_params.pkl (the one artefact of the reference that
                                carries sampler outputs) as plain numbers
   plant_fixtures.json          environments/multi_branch/env1..4 (URDF numbers + pickle) as input fixtures
@@ -414,6 +415,56 @@ def gen_gate(out):
     out["reference_gate.json"] = {"gate_probability": 0.95, "cases": cases}
 
 
+def gen_fk(out):
+    """Link frames of the iiwa14 URDF composed with the REFERENCE's transformations.py (euler_matrix /
+    rotation_matrix / translation_matrix / quaternion_from_matrix): an implementation of URDF forward kinematics
+    that shares no code with the oracle or the kernels."""
+    urdf = os.path.join(REF, "models/drake/iiwa_description/urdf/iiwa14_spheres_collision.urdf")
+    tree = parse_urdf(urdf)
+    rng = np.random.RandomState(21)
+    movable = [j for j in tree.joints if j.kind == "revolute"]
+    lower = np.array([j.lower for j in movable])
+    upper = np.array([j.upper for j in movable])
+    cases = []
+    import xml.etree.ElementTree as ET
+    root = ET.parse(urdf).getroot()
+    origin = {}
+    for je in root.findall("joint"):
+        if je.find("parent") is None:
+            continue
+        o = je.find("origin")
+        xyz = [float(v) for v in o.get("xyz").split()]
+        rpy = [float(v) for v in o.get("rpy").split()]
+        ax = je.find("axis")
+        axis = [float(v) for v in ax.get("xyz").split()] if ax is not None else [1.0, 0.0, 0.0]
+        origin[je.get("name")] = (xyz, rpy, axis)
+    inertial = {}
+    for le in root.findall("link"):
+        ine = le.find("inertial")
+        xyz = [0.0, 0.0, 0.0]
+        if ine is not None and ine.find("origin") is not None:
+            xyz = [float(v) for v in ine.find("origin").get("xyz").split()]
+        inertial[le.get("name")] = xyz
+    for k in range(24):
+        q = rng.uniform(lower, upper) if k else np.zeros(7)
+        qmap = {j.name: float(v) for j, v in zip(movable, q)}
+        world = {tree.root: np.eye(4)}
+        pos, quat, com = [], [], []
+        for j in tree.joints:
+            xyz, rpy, axis = origin[j.name]
+            M = T.concatenate_matrices(T.translation_matrix(xyz), T.euler_matrix(rpy[0], rpy[1], rpy[2], axes="sxyz"))
+            if j.kind == "revolute":
+                M = T.concatenate_matrices(M, T.rotation_matrix(qmap[j.name], axis))
+            W = world[j.parent] @ M
+            world[j.child] = W
+            pos.append([float(v) for v in W[:3, 3]])
+            quat.append([float(v) for v in T.quaternion_from_matrix(W)])       # x, y, z, w in this fork
+            com.append([float(v) for v in (W @ np.array(inertial[j.child] + [1.0]))[:3]])
+        cases.append({"q": [float(v) for v in q], "link_pos": pos, "link_quat": quat, "com_pos": com})
+    out["reference_fk.json"] = {"urdf": "models/drake/iiwa_description/urdf/iiwa14_spheres_collision.urdf",
+                                "links": [j.child for j in tree.joints], "cases": cases}
+
+
 def gen_fixtures(out):
     def plant_numbers(urdf_path, pkl_path):
         tree = parse_urdf(urdf_path)
@@ -442,6 +493,7 @@ def main():
     gen_sampler(out)
     gen_observers(out)
     gen_gate(out)
+    gen_fk(out)
     gen_fixtures(out)
     for name, obj in out.items():
         path = os.path.join(HERE, name)

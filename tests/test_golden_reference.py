@@ -197,3 +197,19 @@ def test_gate_replay_matches_reference_closure():
             hit = PF.replay_gate(1, rigid, exc, d["gate_probability"]) == 0
             assert hit == s["result"]
         assert float(np.random.rand()) == c["next_uniform_after"]
+
+
+def test_fk_matches_urdf_composition_with_reference_transformations():
+    """iiwa14 link frames composed with the reference's pybullet_tools/transformations.py (no shared code)."""
+    d = _load("reference_fk.json")
+    model = load_iiwa14()
+    assert d["links"] == model.link_names
+    Q = np.array([c["q"] for c in d["cases"]])
+    pos, quat, com = O.link_poses(model, Q)
+    rp = np.array([c["link_pos"] for c in d["cases"]])
+    rq = np.array([c["link_quat"] for c in d["cases"]])
+    rc = np.array([c["com_pos"] for c in d["cases"]])
+    sg = np.sign((quat * rq).sum(-1, keepdims=True))
+    assert np.abs(pos - rp).max() < 1e-12 and np.abs(quat * sg - rq).max() < 1e-12 and np.abs(com - rc).max() < 1e-12
+    # end-effector point of the cost term = COM of PyBullet link 9 (iiwa_link_ee)
+    assert np.abs(O.ee_positions(model, Q) - rc[:, 9]).max() < 1e-12

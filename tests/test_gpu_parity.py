@@ -58,6 +58,22 @@ def test_fk_within_1e5(ctx):
     assert np.abs(ee - ocom[:, 9]).max() <= 1e-5
 
 
+def test_fk_against_reference_transformations_golden(ctx):
+    """pmp_fk vs link frames composed with the reference's transformations.py (tests/golden/reference_fk.json)."""
+    with open(os.path.join(G, "reference_fk.json")) as fp:
+        d = json.load(fp)
+    Q = np.array([c["q"] for c in d["cases"]], dtype=np.float32)
+    pos, quat, com = ctx["chk"].fk(ctx["torch"].from_numpy(Q))
+    rp = np.array([c["link_pos"] for c in d["cases"]])
+    rq = np.array([c["link_quat"] for c in d["cases"]])
+    rc = np.array([c["com_pos"] for c in d["cases"]])
+    qg = quat.cpu().numpy()
+    sg = np.sign((qg * rq).sum(-1, keepdims=True))
+    assert np.abs(pos.cpu().numpy() - rp).max() <= 1e-5
+    assert np.abs(com.cpu().numpy() - rc).max() <= 1e-5
+    assert np.abs(qg * sg - rq).max() <= 1e-5
+
+
 @pytest.mark.parametrize("mode", ["our_method", "avoid_all", "ignore_all"])
 def test_config_flags_and_deflections(ctx, mode):
     from oracle import edgecheck_oracle as O
