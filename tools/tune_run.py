@@ -36,8 +36,9 @@ rows = []
 libs = sorted(glob.glob(os.path.join(ROOT, "plant_motion_planning_b200/_lib/variants/*.so")))
 for lib in libs:
     name = os.path.basename(lib)[7:-3]
-    maxt = int(name.split("_")[0][1:])
-    minb = int(name.split("_")[1][1:])
+    import re
+    mm = re.match(r"t(\d+)_b(\d+)", name)
+    maxt, minb = int(mm.group(1)), int(mm.group(2))
     combos = {(maxt, minb)}
     if os.environ.get("TUNE_ALL_SPLITS"):
         if maxt >= 256:
