@@ -42,6 +42,42 @@ class TreeNode:
         return seq[::-1]
 
 
+class ConfigTree(list):
+    """A list of TreeNode that also keeps the configurations in one float64 array, so that the nearest-node search
+    of every extension (`argmin(distance_fn(n.config, target))`, primitives.py:207 -- an O(|tree|) Python loop in the
+    reference) is one vectorised pass.  Ties resolve to the first minimum, like the reference's argmin
+    (motion_planners/motion_planners/utils.py:47-53)."""
+
+    def __init__(self, nodes=(), circular=None):
+        super().__init__()
+        self._buf = None
+        self._circ = None if circular is None else np.asarray(circular, dtype=bool)
+        for n in nodes:
+            self.append(n)
+
+    def append(self, node: TreeNode) -> None:
+        k = len(self)
+        if self._buf is None:
+            self._buf = np.empty((64, len(node.config)), dtype=np.float64)
+        elif k == self._buf.shape[0]:
+            self._buf = np.concatenate([self._buf, np.empty_like(self._buf)], axis=0)
+        self._buf[k] = node.config
+        super().append(node)
+
+    def extend(self, nodes) -> None:
+        for n in nodes:
+            self.append(n)
+
+    def clear(self) -> None:
+        super().clear()
+
+    def nearest(self, target: Conf) -> TreeNode:
+        diff = np.asarray(target, dtype=np.float64)[None] - self._buf[:len(self)]
+        if self._circ is not None and self._circ.any():
+            diff = np.where(self._circ[None], (diff + np.pi) % (2 * np.pi) - np.pi, diff)
+        return self[int(np.argmin(np.einsum("ij,ij->i", diff, diff)))]
+
+
 class FlagBackend:
     """Anything that maps a list of configurations to raw flags uint8 [n, W] (bit0 rigid, bit1 exceeded)."""
 
@@ -86,8 +122,11 @@ class PlanLog:
 
 def extend_towards(tree: List[TreeNode], target: Conf, distance_fn, extend_fn, backend: FlagBackend, forward: bool,
                    swap: bool, log: Optional[PlanLog] = None) -> Tuple[TreeNode, bool]:
-    scores = [distance_fn(n.config, target) for n in tree]
-    last = tree[scores.index(min(scores))]
+    if isinstance(tree, ConfigTree):
+        last = tree.nearest(target)              # unit weights, 2-norm: the reference's default distance_fn
+    else:
+        scores = [distance_fn(n.config, target) for n in tree]
+        last = tree[scores.index(min(scores))]
     extend = list(asymmetric_extend(last.config, target, extend_fn, backward=swap))
     k = first_violation(backend.flags(extend), forward) if extend else 0
     if log is not None:
@@ -117,11 +156,16 @@ def check_forward_path(path2: List[TreeNode], backend: FlagBackend, nodes1: List
 
 
 def rrt_connect_multi_world(start: Conf, goal: Conf, distance_fn, sample_fn, extend_fn, backend: FlagBackend,
-                            max_iterations: int = 2000, log: Optional[PlanLog] = None):
-    """Returns (path of configurations, node path) or (None, None)."""
+                            max_iterations: int = 2000, log: Optional[PlanLog] = None, circular=None,
+                            vectorized_nearest: bool = True):
+    """Returns (path of configurations, node path) or (None, None).  `vectorized_nearest` assumes the default metric
+    (unit weights, 2-norm, wrap on `circular` joints); pass False to call `distance_fn` node by node."""
     if first_violation(backend.flags([start]), True) == 0:
         return None
-    nodes1, nodes2 = [TreeNode(start)], [TreeNode(goal)]
+    if vectorized_nearest:
+        nodes1, nodes2 = ConfigTree([TreeNode(start)], circular), ConfigTree([TreeNode(goal)], circular)
+    else:
+        nodes1, nodes2 = [TreeNode(start)], [TreeNode(goal)]
     swap = True
     for it in range(max_iterations):
         if log is not None:

@@ -44,3 +44,33 @@ def test_replay_gate_equals_first_violation():
             np.random.seed(5)
             b = birrt.first_violation(fl, fwd)
             assert a == b and ra == np.random.rand()
+
+
+def test_config_tree_nearest_equals_reference_argmin():
+    from plant_motion_planning_b200.robots import load_iiwa14
+    robot = load_iiwa14()
+    dist = PF.get_distance_fn(robot)
+    rng = np.random.RandomState(1)
+    tree = birrt.ConfigTree(circular=robot.circular)
+    plain = []
+    for _ in range(300):
+        n = birrt.TreeNode(tuple(rng.uniform(robot.lower, robot.upper)))
+        tree.append(n)
+        plain.append(n)
+    assert len(tree) == 300 and tree[137] is plain[137]
+    for _ in range(50):
+        t = tuple(rng.uniform(robot.lower, robot.upper))
+        scores = [dist(n.config, t) for n in plain]
+        assert tree.nearest(t) is plain[scores.index(min(scores))]
+    # circular joints wrap
+    class R:  # noqa: D401
+        lower = robot.lower; upper = robot.upper; dof = 7
+        circular = np.array([False, False, True, False, False, False, False])
+    d2 = PF.get_distance_fn(R)
+    tree2 = birrt.ConfigTree(circular=R.circular)
+    for n in plain:
+        tree2.append(n)
+    for _ in range(50):
+        t = tuple(rng.uniform(robot.lower, robot.upper))
+        scores = [d2(n.config, t) for n in plain]
+        assert tree2.nearest(t) is plain[scores.index(min(scores))]
