@@ -291,7 +291,7 @@ static int edge_steps(const pmp_robot_desc* rb, const pmp_params* prm, const flo
         ssum = ssum + v * v;
     }
     const double nd = floor(sqrt(ssum));
-    return (nd > 1.0e6 ? 1000000 : (int)nd) + 1;
+    return (nd >= 0.0 && nd <= 1.0e6) ? (int)nd + 1 : (nd > 1.0e6 ? 1000001 : 1);
 }
 
 typedef struct {

@@ -478,7 +478,8 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
         double ssum = 0.0;
         for (int j = 0; j < D; ++j) ssum = __dadd_rn(ssum, sm_sq[j]);
         const double nd = floor(__dsqrt_rn(ssum));
-        const int n = (nd > 1.0e6 ? 1000000 : (int)nd) + 1;
+        // NaN / inf inputs: one step, which the limit test of that configuration rejects
+        const int n = (nd >= 0.0 && nd <= 1.0e6) ? (int)nd + 1 : (nd > 1.0e6 ? 1000001 : 1);
         const int nc = min(n, args.max_steps);
         const int off = args.backward ? 0 : 1;
         const float inv_n = 1.0f / (float)n;

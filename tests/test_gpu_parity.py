@@ -187,6 +187,23 @@ def test_empty_batch_and_bad_shapes(ctx):
         chk.validate_edges(torch.zeros((4, 7)), torch.zeros((5, 7)))
 
 
+def test_non_finite_inputs_are_rejected_not_crashed(ctx):
+    torch, chk = ctx["torch"], ctx["chk"]
+    q0 = np.zeros((4, 7), np.float32)
+    q1 = np.full((4, 7), 0.2, np.float32)
+    q1[1, 2] = np.nan
+    q0[2, 0] = np.inf
+    q1[3, 5] = 1e30
+    out = chk.validate_edges(torch.from_numpy(q0), torch.from_numpy(q1), max_steps=64)
+    torch.cuda.synchronize()
+    fh, n = out.first_hit.cpu().numpy(), out.n_steps.cpu().numpy()
+    assert n[0] >= 1 and fh[0] == n[0]                 # the finite edge is untouched by its neighbours
+    assert n[1] == 1 and fh[1] == 0                   # NaN: one step, rejected
+    assert n[2] > 64 and fh[2] == 0                    # inf: infinitely long edge, every configuration rejected
+    assert n[3] > 64 and fh[3] < 64                    # absurdly long edge: truncated at max_steps and rejected (limits)
+    assert not bool(out.valid[1]) and not bool(out.valid[2]) and not bool(out.valid[3])
+
+
 def test_limits_violation_is_a_rigid_hit(ctx):
     torch, chk, model = ctx["torch"], ctx["chk"], ctx["model"]
     q = np.zeros((3, 7), np.float32)
