@@ -127,7 +127,7 @@ class MultiPlantWorld:
                  loadPath: Optional[str] = None, physicsClientId=None, avoid_all: bool = False, *,
                  robot: Optional[RobotModel] = None, worlds: Optional[Sequence[PlantWorld]] = None,
                  config: Optional[EdgeCheckConfig] = None, device: int = 0, stem_base_spacing: float = 0.0,
-                 checker=None):
+                 checker_factory=None):
         self.sample_robot = robot if robot is not None else load_iiwa14()
         self.joints = list(range(self.sample_robot.dof))
         self.deflection_limit = deflection_limit
@@ -150,10 +150,13 @@ class MultiPlantWorld:
         from dataclasses import replace
         self.config = replace(base, deflection_limit=float(deflection_limit),
                               mode="avoid_all" if avoid_all else "our_method")
-        # `checker`: dependency injection for tests (anything with check_configs_host / validate_edges*); the
-        # product always builds the CUDA EdgeChecker, which raises without a B200.
-        self.checker = checker if checker is not None else EdgeChecker(self.sample_robot, list(worlds), self.config,
-                                                                       device=device)
+        # `checker_factory(robot, worlds, config)`: dependency injection for tests (returns anything with
+        # check_configs_host / validate_edges*); the product always builds the CUDA EdgeChecker, which raises
+        # without a B200.
+        if checker_factory is not None:
+            self.checker = checker_factory(self.sample_robot, list(worlds), self.config)
+        else:
+            self.checker = EdgeChecker(self.sample_robot, list(worlds), self.config, device=device)
         self.plant_worlds = list(worlds)
         self._limits_fn = get_limits_fn(self.sample_robot)
         self.envs: Dict[Tuple[float, float], SinglePlantEnv] = {}

@@ -15,6 +15,9 @@ Everything that is *arithmetic of the reference* runs unmodified from /root/refe
                                observe_all_and_check (representation.py) on link poses served by the stub
   reference_gate.json          get_collision_fn_with_angle_constraints_v4 (pybullet_tools/utils.py:3827-3857):
                                result and number of np.random draws for scripted (rigid, exceeded) flags
+  reference_rrt.json           the reference's rrt_connect_multi_world run unchanged against this repository's
+                               MultiPlantWorld facade (oracle-backed here): returned paths + RNG state for the three
+                               multi_world_* script scenarios
   reference_fk.json            iiwa14 link frames composed with the reference's pybullet_tools/transformations.py
   seed1_plant.json             models/plant.urdf + models/plant_params.pkl (the one artefact of the reference that
                                carries sampler outputs) as plain numbers
@@ -465,6 +468,46 @@ def gen_fk(out):
                                 "links": [j.child for j in tree.joints], "cases": cases}
 
 
+def gen_rrt(out):
+    """Run the reference's rrt_connect_multi_world (rrt_connect_with_angle_constraints_v2.py:202-280) UNCHANGED against
+    the MultiPlantWorld facade of this repository.  No GPU exists in the build container, so the facade is given an
+    oracle-backed checker (tests/oracle_checker.py); what is pinned is the planner-facing behaviour: the facade drops
+    into the reference's RRT loop, and birrt.py (the restated driver) must return exactly these paths and leave the RNG
+    streams in exactly this state."""
+    import contextlib
+    import io
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_checker import OracleChecker
+    from plant_motion_planning.motion_planners.motion_planners.rrt_connect_with_angle_constraints_v2 import \
+        rrt_connect_multi_world
+    from plant_motion_planning_b200.env import MultiPlantWorld
+    from plant_motion_planning_b200.scenarios import GOAL, SCRIPTS, START
+    pb.saveState = lambda *a, **k: 1
+    pb.restoreState = lambda *a, **k: None
+    urdf = os.path.join(REF, "models/drake/iiwa_description/urdf/iiwa14_spheres_collision.urdf")
+    register_urdf_body(0, urdf)
+    joints = U.get_movable_joints(0)
+    res = {}
+    for script, cfg in SCRIPTS.items():
+        np.random.seed(cfg["seed"])
+        random.seed(cfg["seed"])
+        env = MultiPlantWorld(cfg["xs"], cfg["ys"], cfg["deflection_limit"], *cfg["args"], cfg["limits"],
+                              avoid_all=cfg["avoid_all"], checker_factory=OracleChecker)
+        plant_aware = script == "multi_world_our_method"
+        fwd = env.net_constraint_violation_checker_forward if plant_aware else env.net_constraint_violation_checker_benchmark
+        back = env.net_constraint_violation_checker_backward if plant_aware else env.net_constraint_violation_checker_benchmark
+        np.random.seed(1)
+        random.seed(1)
+        with contextlib.redirect_stdout(io.StringIO()):
+            r = rrt_connect_multi_world(START, 1, GOAL, U.get_distance_fn(0, joints), U.get_sample_fn(0, joints),
+                                        U.get_extend_fn(0, joints), [fwd, back], env)
+        path = r[0]
+        res[script] = {"planner_seed": 1, "plant_aware": plant_aware, "path_len": len(path),
+                       "path": [[float(v) for v in q] for q in path],
+                       "next_np_rand": float(np.random.rand()), "kernel_evaluations": int(env.kernel_evaluations)}
+    out["reference_rrt.json"] = res
+
+
 def gen_fixtures(out):
     def plant_numbers(urdf_path, pkl_path):
         tree = parse_urdf(urdf_path)
@@ -494,6 +537,7 @@ def main():
     gen_observers(out)
     gen_gate(out)
     gen_fk(out)
+    gen_rrt(out)
     gen_fixtures(out)
     for name, obj in out.items():
         path = os.path.join(HERE, name)

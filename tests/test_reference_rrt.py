@@ -1,0 +1,64 @@
+"""The reference's own RRT loop vs the restated driver.
+
+tests/golden/reference_rrt.json holds the paths returned by the reference's UNCHANGED rrt_connect_multi_world
+(motion_planners/.../rrt_connect_with_angle_constraints_v2.py:202-280) when it is given this repository's
+MultiPlantWorld facade and the reference's own sample/distance/extend callables, from the scripts' seeds.
+birrt.rrt_connect_multi_world must return the same paths and leave np.random in the same state:
+  * on oracle flags (CPU, runs everywhere)   -> pins the restated control flow against the reference's code
+  * on GPU flags (-m gpu)                    -> identical accept/reject decisions of the CUDA path along whole plans
+"""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle_checker import OracleChecker
+from plant_motion_planning_b200 import birrt
+from plant_motion_planning_b200 import planner_fns as F
+from plant_motion_planning_b200.robots import load_iiwa14
+from plant_motion_planning_b200.scenarios import GOAL, SCRIPTS, START, script_worlds
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+class _Backend(birrt.FlagBackend):
+    def __init__(self, checker, plant_aware):
+        self.checker, self.plant_aware = checker, plant_aware
+
+    def flags(self, configs):
+        fl = self.checker.check_configs_host(np.asarray(configs, np.float32), detail=False)["flags"]
+        return fl if self.plant_aware else (fl & 1)     # *_benchmark checkers: rigid obstacles only (env.py:249-255)
+
+
+def _plan(script, checker_cls):
+    from plant_motion_planning_b200.edgecheck import EdgeCheckConfig
+    with open(os.path.join(G, "reference_rrt.json")) as fp:
+        gold = json.load(fp)[script]
+    worlds, cfg = script_worlds(script)
+    robot = load_iiwa14()
+    mode = "avoid_all" if cfg["avoid_all"] else "our_method"
+    chk = checker_cls(robot, worlds, EdgeCheckConfig(mode=mode, deflection_limit=cfg["deflection_limit"]))
+    np.random.seed(gold["planner_seed"])
+    random.seed(gold["planner_seed"])
+    path, _ = birrt.rrt_connect_multi_world(START, GOAL, F.get_distance_fn(robot), F.get_sample_fn(robot),
+                                            F.get_extend_fn(robot), _Backend(chk, gold["plant_aware"]))
+    return path, float(np.random.rand()), gold
+
+
+@pytest.mark.parametrize("script", sorted(SCRIPTS))
+def test_restated_driver_equals_reference_rrt_on_oracle_flags(script):
+    path, nxt, gold = _plan(script, OracleChecker)
+    assert path is not None and len(path) == gold["path_len"]
+    assert [list(q) for q in path] == gold["path"]
+    assert nxt == gold["next_np_rand"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("script", sorted(SCRIPTS))
+def test_gpu_plans_equal_reference_rrt(script):
+    from plant_motion_planning_b200 import EdgeChecker
+    path, nxt, gold = _plan(script, EdgeChecker)
+    assert path is not None and [list(q) for q in path] == gold["path"]
+    assert nxt == gold["next_np_rand"]
