@@ -268,7 +268,7 @@ def smooth_path_multi_world(path: Sequence[Conf], extend_fn, distance_fn, backen
             log.edges.append(("shortcut", len(cfgs), k))
         if k == len(cfgs):
             way = new_way
-    out = [way[0]]
+    out: List[Conf] = []          # refine_waypoints (smoothing.py:49-52): the first waypoint itself is not emitted
     for a, b in zip(way[:-1], way[1:]):
         out.extend(extend_fn(a, b))
     return out

@@ -505,6 +505,16 @@ def gen_rrt(out):
         res[script] = {"planner_seed": 1, "plant_aware": plant_aware, "path_len": len(path),
                        "path": [[float(v) for v in q] for q in path],
                        "next_np_rand": float(np.random.rand()), "kernel_evaluations": int(env.kernel_evaluations)}
+        # the reference's shortcut smoother (smoothing.py:55-141), unchanged, on that path
+        from plant_motion_planning.motion_planners.motion_planners.smoothing import smooth_path_multi_world
+        np.random.seed(7)
+        random.seed(7)
+        with contextlib.redirect_stdout(io.StringIO()):
+            sm = smooth_path_multi_world(path, r[1], U.get_extend_fn(0, joints), fwd, env, max_iterations=20)
+        res[script]["smoothing_seed"] = 7
+        res[script]["smoothed"] = [[float(v) for v in q] for q in sm]
+        res[script]["smoothed_next_np_rand"] = float(np.random.rand())
+        res[script]["smoothed_next_py_random"] = float(random.random())
     out["reference_rrt.json"] = res
 
 

@@ -42,9 +42,15 @@ def _plan(script, checker_cls):
     chk = checker_cls(robot, worlds, EdgeCheckConfig(mode=mode, deflection_limit=cfg["deflection_limit"]))
     np.random.seed(gold["planner_seed"])
     random.seed(gold["planner_seed"])
+    backend = _Backend(chk, gold["plant_aware"])
     path, _ = birrt.rrt_connect_multi_world(START, GOAL, F.get_distance_fn(robot), F.get_sample_fn(robot),
-                                            F.get_extend_fn(robot), _Backend(chk, gold["plant_aware"]))
-    return path, float(np.random.rand()), gold
+                                            F.get_extend_fn(robot), backend)
+    nxt = float(np.random.rand())
+    np.random.seed(gold["smoothing_seed"])
+    random.seed(gold["smoothing_seed"])
+    sm = birrt.smooth_path_multi_world(path, F.get_extend_fn(robot), F.get_distance_fn(robot), backend, max_iterations=20)
+    gold["_smoothed"] = ([list(q) for q in sm], float(np.random.rand()), float(random.random()))
+    return path, nxt, gold
 
 
 @pytest.mark.parametrize("script", sorted(SCRIPTS))
@@ -53,6 +59,8 @@ def test_restated_driver_equals_reference_rrt_on_oracle_flags(script):
     assert path is not None and len(path) == gold["path_len"]
     assert [list(q) for q in path] == gold["path"]
     assert nxt == gold["next_np_rand"]
+    sm, np_next, py_next = gold["_smoothed"]
+    assert sm == gold["smoothed"] and np_next == gold["smoothed_next_np_rand"] and py_next == gold["smoothed_next_py_random"]
 
 
 @pytest.mark.gpu
@@ -62,3 +70,5 @@ def test_gpu_plans_equal_reference_rrt(script):
     path, nxt, gold = _plan(script, EdgeChecker)
     assert path is not None and [list(q) for q in path] == gold["path"]
     assert nxt == gold["next_np_rand"]
+    sm, np_next, py_next = gold["_smoothed"]
+    assert sm == gold["smoothed"] and np_next == gold["smoothed_next_np_rand"] and py_next == gold["smoothed_next_py_random"]
