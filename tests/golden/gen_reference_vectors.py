@@ -515,6 +515,35 @@ def gen_rrt(out):
         res[script]["smoothed"] = [[float(v) for v in q] for q in sm]
         res[script]["smoothed_next_np_rand"] = float(np.random.rand())
         res[script]["smoothed_next_py_random"] = float(random.random())
+        # the reference's cost report: Command.execute_multi_world (kuka_primitives.py:467-521), unchanged, on the
+        # smoothed path.  Its getLinkState(sample_robot, 9) is served by the stub from the oracle FK at the
+        # configuration the facade was last stepped to; the totals are parsed from what it prints.
+        from oracle import edgecheck_oracle as ORC
+        from plant_motion_planning.pybullet_tools.kuka_primitives import BodyPath, Command
+        robot_model = env.sample_robot
+
+        def ee_state(link, _env=env, _m=robot_model):
+            pos, quat, com = ORC.link_poses(_m, np.asarray(_env._action, dtype=np.float64)[None])
+            return (tuple(com[0, link]), tuple(quat[0, link]), (0, 0, 0), (0, 0, 0, 1), tuple(pos[0, link]), tuple(quat[0, link]))
+        pb.bodies[0]["link_state"] = ee_state
+
+        class _Proxy:
+            sample_robot = 0
+            def __init__(self, e):
+                self._e = e
+            def __getattr__(self, k):
+                return getattr(self._e, k)
+        env.checker.config = env.config
+        env.step(START)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            Command([BodyPath(0, sm, joints)]).execute_multi_world(START, _Proxy(env), num_worlds=len(env.envs))
+        txt = buf.getvalue()
+        import re
+        ee_len = float(re.search(r"total path cost:\s+([-0-9.e+]+)", txt).group(1))
+        over = [float(v) for v in re.search(r"total Deflection over limit:\s+\[([^\]]*)\]", txt).group(1).split()]
+        total = [float(v) for v in re.search(r"Total cost:\s+\[([^\]]*)\]", txt, flags=re.S).group(1).split()]
+        res[script]["execute"] = {"ee_len": ee_len, "over": over, "total": total, "alpha": 0.1}
     out["reference_rrt.json"] = res
 
 

@@ -72,3 +72,35 @@ def test_gpu_plans_equal_reference_rrt(script):
     assert nxt == gold["next_np_rand"]
     sm, np_next, py_next = gold["_smoothed"]
     assert sm == gold["smoothed"] and np_next == gold["smoothed_next_np_rand"] and py_next == gold["smoothed_next_py_random"]
+
+
+def _cost(script, factory):
+    from plant_motion_planning_b200.env import MultiPlantWorld
+    with open(os.path.join(G, "reference_rrt.json")) as fp:
+        gold = json.load(fp)[script]
+    cfg = SCRIPTS[script]
+    np.random.seed(cfg["seed"])
+    random.seed(cfg["seed"])
+    env = MultiPlantWorld(cfg["xs"], cfg["ys"], cfg["deflection_limit"], *cfg["args"], cfg["limits"],
+                          avoid_all=cfg["avoid_all"], checker_factory=factory)
+    ee_len, over, total = env.path_cost(START, [tuple(q) for q in gold["smoothed"]])
+    return ee_len, over, total, gold["execute"]
+
+
+@pytest.mark.parametrize("script", sorted(SCRIPTS))
+def test_path_cost_equals_reference_execute_report(script):
+    """env.path_cost vs the totals printed by the reference's unchanged Command.execute_multi_world
+    (pybullet_tools/kuka_primitives.py:467-521) on the same smoothed path (oracle-backed facade)."""
+    ee_len, over, total, ex = _cost(script, OracleChecker)
+    assert abs(ee_len - ex["ee_len"]) < 1e-5
+    assert np.allclose(over, ex["over"], atol=1e-4) and np.allclose(total, ex["total"], atol=1e-4)
+    if script == "multi_world_ignore_all":
+        assert max(ex["over"]) > 1.0          # the ignore-all plan really does bend plants past the limit
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("script", sorted(SCRIPTS))
+def test_gpu_path_cost_equals_reference_execute_report(script):
+    ee_len, over, total, ex = _cost(script, None)
+    assert abs(ee_len - ex["ee_len"]) < 1e-4
+    assert np.allclose(over, ex["over"], atol=5e-3, rtol=1e-3) and np.allclose(total, ex["total"], atol=1e-3, rtol=1e-3)
