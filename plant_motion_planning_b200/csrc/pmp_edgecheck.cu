@@ -32,6 +32,9 @@ struct pmp_ctx {
     cudaStream_t stream = nullptr;
     void* d_scratch = nullptr;
     size_t scratch_bytes = 0;
+    // pinned staging for small host calls (the per-step collision_fn adapter): one H2D, one kernel, one D2H
+    void* h_stage = nullptr;
+    size_t stage_bytes = 0;
 };
 
 static std::string g_create_err;
@@ -89,6 +92,7 @@ extern "C" int pmp_destroy(pmp_ctx* ctx) {
     cudaSetDevice(ctx->device);
     free_worlds(ctx);
     cudaFree(ctx->d_robot); cudaFree(ctx->d_links); cudaFree(ctx->d_scratch);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return PMP_OK;
@@ -253,7 +257,7 @@ static cudaError_t launch_edge(pmp_ctx* ctx, const PmpEdgeArgs& args, bool wsmem
 }
 
 template <int A, int NS>
-static cudaError_t launch_config(pmp_ctx* ctx, const PmpConfigArgs& args, int grid, int block, size_t smem,
+static cudaError_t launch_config(pmp_ctx* ctx, const PmpConfigArgs& args, dim3 grid, int block, size_t smem,
                                  cudaStream_t st) {
     pmp_config_kernel<A, NS><<<grid, block, smem, st>>>(args);
     cudaFuncAttributes fa;
@@ -356,12 +360,19 @@ extern "C" int pmp_check_configs(pmp_ctx* ctx, const float* q, int32_t B, uint8_
     pads(ctx, apad, nspad);
     // small batches (the scalar collision_fn adapter) spread over SMs: 32 threads per CTA
     const int block = B <= 32 * ctx->sm_count ? 32 : 128;
-    const int grid = (B + block - 1) / block;
+    const int gx = (B + block - 1) / block;
+    // spread the worlds over blockIdx.y until the grid holds about two CTAs per SM
+    int gy = (2 * ctx->sm_count + gx - 1) / gx;
+    if (gy > ctx->n_worlds) gy = ctx->n_worlds;
+    if (gy < 1) gy = 1;
+    a.worlds_per_cta = (ctx->n_worlds + gy - 1) / gy;
+    gy = (ctx->n_worlds + a.worlds_per_cta - 1) / a.worlds_per_cta;
+    const dim3 grid(gx, gy, 1);
     const size_t smem = sizeof(PmpRobotTab);
     cudaError_t err;
     PMP_DISPATCH(launch_config, ctx, a, grid, block, smem, (cudaStream_t)stream);
     if (err != cudaSuccess) return fail(ctx, PMP_E_CUDA, std::string("config kernel launch: ") + cudaGetErrorString(err));
-    ctx->info.grid = grid; ctx->info.block = block; ctx->info.smem_bytes = (int)smem; ctx->info.worlds_in_smem = 0;
+    ctx->info.grid = gx * gy; ctx->info.block = block; ctx->info.smem_bytes = (int)smem; ctx->info.worlds_in_smem = 0;
     ctx->info.n_sphere_pad = apad; ctx->info.n_slot_pad = nspad;
     ctx->info.kernel_launches++;
     return PMP_OK;
@@ -423,6 +434,15 @@ extern "C" int pmp_validate_edges_host(pmp_ctx* ctx, const float* q0, const floa
     return PMP_OK;
 }
 
+static int ensure_stage(pmp_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->stage_bytes) return PMP_OK;
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    ctx->h_stage = nullptr; ctx->stage_bytes = 0;
+    CK(cudaHostAlloc(&ctx->h_stage, bytes, cudaHostAllocDefault));
+    ctx->stage_bytes = bytes;
+    return PMP_OK;
+}
+
 extern "C" int pmp_check_configs_host(pmp_ctx* ctx, const float* q, int32_t B, uint8_t* flags, float* defl,
                                       float* theta, float* ee) {
     int rc = ready(ctx);
@@ -432,25 +452,47 @@ extern "C" int pmp_check_configs_host(pmp_ctx* ctx, const float* q, int32_t B, u
     if (!q || !flags) return fail(ctx, PMP_E_INVALID, "q and flags are required");
     CK(cudaSetDevice(ctx->device));
     const int D = ctx->h_robot.dof, W = ctx->n_worlds, P = ctx->max_stems;
-    const size_t bq = up256(sizeof(float) * (size_t)B * D), bf = up256((size_t)B * W),
-                 bd = up256(sizeof(float) * (size_t)B * W * P), be = up256(sizeof(float) * (size_t)B * 3);
-    rc = ensure_scratch(ctx, bq + bf + (defl ? bd : 0) + (theta ? 2 * bd : 0) + (ee ? be : 0));
+    const size_t nq = sizeof(float) * (size_t)B * D, nf = (size_t)B * W, nd = sizeof(float) * (size_t)B * W * P,
+                 ne = sizeof(float) * (size_t)B * 3;
+    const size_t bq = up256(nq), bf = up256(nf), bd = up256(nd), be = up256(ne);
+    // outputs are laid out back to back so that a small call needs a single device-to-host copy
+    const size_t out_bytes = bf + (defl ? bd : 0) + (theta ? 2 * bd : 0) + (ee ? be : 0);
+    rc = ensure_scratch(ctx, bq + out_bytes);
     if (rc) return rc;
     char* p = (char*)ctx->d_scratch;
     auto take = [&](size_t b) { char* r = p; p += b; return r; };
     float* dq = (float*)take(bq);
+    char* dout = p;
     uint8_t* dfl = (uint8_t*)take(bf);
     float* dd = defl ? (float*)take(bd) : nullptr;
     float* dt = theta ? (float*)take(2 * bd) : nullptr;
     float* de = ee ? (float*)take(be) : nullptr;
     cudaStream_t st = ctx->stream;
-    CK(cudaMemcpyAsync(dq, q, sizeof(float) * (size_t)B * D, cudaMemcpyHostToDevice, st));
+    const bool small = (bq + out_bytes) <= ((size_t)1 << 20);
+    if (small) {
+        rc = ensure_stage(ctx, bq + out_bytes);
+        if (rc) return rc;
+        char* hs = (char*)ctx->h_stage;
+        memcpy(hs, q, nq);
+        CK(cudaMemcpyAsync(dq, hs, nq, cudaMemcpyHostToDevice, st));
+        rc = pmp_check_configs(ctx, dq, B, dfl, dd, dt, de, st);
+        if (rc) return rc;
+        char* ho = hs + bq;
+        CK(cudaMemcpyAsync(ho, dout, out_bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        memcpy(flags, ho + ((char*)dfl - dout), nf);
+        if (defl) memcpy(defl, ho + ((char*)dd - dout), nd);
+        if (theta) memcpy(theta, ho + ((char*)dt - dout), 2 * nd);
+        if (ee) memcpy(ee, ho + ((char*)de - dout), ne);
+        return PMP_OK;
+    }
+    CK(cudaMemcpyAsync(dq, q, nq, cudaMemcpyHostToDevice, st));
     rc = pmp_check_configs(ctx, dq, B, dfl, dd, dt, de, st);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(flags, dfl, (size_t)B * W, cudaMemcpyDeviceToHost, st));
-    if (defl) CK(cudaMemcpyAsync(defl, dd, sizeof(float) * (size_t)B * W * P, cudaMemcpyDeviceToHost, st));
-    if (theta) CK(cudaMemcpyAsync(theta, dt, sizeof(float) * (size_t)B * W * P * 2, cudaMemcpyDeviceToHost, st));
-    if (ee) CK(cudaMemcpyAsync(ee, de, sizeof(float) * (size_t)B * 3, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(flags, dfl, nf, cudaMemcpyDeviceToHost, st));
+    if (defl) CK(cudaMemcpyAsync(defl, dd, nd, cudaMemcpyDeviceToHost, st));
+    if (theta) CK(cudaMemcpyAsync(theta, dt, 2 * nd, cudaMemcpyDeviceToHost, st));
+    if (ee) CK(cudaMemcpyAsync(ee, de, ne, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return PMP_OK;
 }

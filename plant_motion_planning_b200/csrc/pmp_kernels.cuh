@@ -591,9 +591,10 @@ struct PmpConfigArgs {
     float* defl;               // [B, W, max_stems] or null
     float* theta;              // [B, W, max_stems, 2] or null
     float* ee;                 // [B, 3] or null
+    int32_t worlds_per_cta;    // blockIdx.y handles worlds [y * worlds_per_cta, (y + 1) * worlds_per_cta)
 };
 
-// Explicit-configuration kernel: thread = configuration, all worlds.  Parity / scalar-adapter path.
+// Explicit-configuration kernel: thread = configuration, blockIdx.y = chunk of worlds.  Parity / scalar-adapter path.
 template <int A, int NSLOT>
 __global__ void __launch_bounds__(128, 2) pmp_config_kernel(const PmpConfigArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -612,8 +613,12 @@ __global__ void __launch_bounds__(128, 2) pmp_config_kernel(const PmpConfigArgs 
 #pragma unroll
         for (int a = 0; a < A; ++a) { c[a][0] = PMP_FAR; c[a][1] = PMP_FAR; c[a][2] = PMP_FAR; }
     }
-    if (live && args.ee) { args.ee[3 * b] = ee[0]; args.ee[3 * b + 1] = ee[1]; args.ee[3 * b + 2] = ee[2]; }
-    for (int w = 0; w < W; ++w) {
+    if (live && args.ee && blockIdx.y == 0) { args.ee[3 * b] = ee[0]; args.ee[3 * b + 1] = ee[1]; args.ee[3 * b + 2] = ee[2]; }
+    // worlds are spread over blockIdx.y so that small batches (the scalar collision_fn adapter: B = 1..50) use many
+    // SMs instead of one thread walking all W worlds; the arm FK above is simply recomputed per world chunk
+    const int w_lo = blockIdx.y * args.worlds_per_cta;
+    const int w_hi = min(W, w_lo + args.worlds_per_cta);
+    for (int w = w_lo; w < w_hi; ++w) {
         PmpUnitOut u;
         u.plant_hit = false; u.exceeded = false; u.max_defl = 0.f; u.over = 0.f;
         const size_t bw = (size_t)bb * W + w;
