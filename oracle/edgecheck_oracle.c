@@ -207,7 +207,9 @@ static void world_eval(const pmp_robot_desc* rb, const pmp_world_desc* wd, const
             if (!solve) { if (S > 0) out->plant_hit = 1; break; }
             if (!(S > 0)) { if (prm->dense) continue; else break; }
             const double lam = (double)prm->reg_eps * S, a11 = Hxx + lam, a22 = Hyy + lam;
-            const double det = a11 * a22 - Hxy * Hxy;
+            double det = a11 * a22 - Hxy * Hxy;
+            const double det_lo = lam * (lam + Hxx + Hyy);   /* = det when H is rank one; lower bound otherwise */
+            if (det < det_lo) det = det_lo;
             double dx = (a22 * gx - Hxy * gy) / det, dy = (a11 * gy - Hxy * gx) / det;
             dx = clampd(dx, -(double)prm->max_step, (double)prm->max_step);
             dy = clampd(dy, -(double)prm->max_step, (double)prm->max_step);

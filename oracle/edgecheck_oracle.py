@@ -28,8 +28,9 @@ Quasi-static plant model (replaces env.py:127-163 -- spring torques + 50 x stepS
      for every arm sphere a:  tau = clamp((c_a - o).u, z0, z1),  dv = c_a - o - tau u,  dist = |dv|,
          pen_a = max(r_a + r_s - dist, 0),
          J_a = d(pen_a)/d(th) = -(tau / dist) (dv . (ax x u),  dv . (ay x u))      (ax, ay = joint axes)
-     H = sum_a pen_a J_a J_a^T,  g = sum_a pen_a^2 J_a,  S = sum_a pen_a
-     dth = (H + eps S I)^-1 g   (skipped when S = 0), each component clamped to +-max_step,
+     H = sum_a pen_a J_a J_a^T,  g = sum_a pen_a^2 J_a,  S = sum_a pen_a,  lam = eps S
+     dth = adj(H + lam I) g / max(det(H + lam I), lam (lam + tr H))   (skipped when S = 0; the max is an identity in
+     exact arithmetic, it guards the float32 cancellation), each component clamped to +-max_step,
      th <- clamp(th + dth, +-limit)
   i.e. a least-squares removal of the penetrations weighted by their depth: for a single contact it is the
   minimum-norm joint motion that removes the penetration to first order (= the minimum-spring-energy response
@@ -332,7 +333,8 @@ def plant_equilibrium(world: PlantWorld, centers: np.ndarray, radii: np.ndarray,
             a11 = Hxx + lam
             a22 = Hyy + lam
             act = S > 0.0
-            det = np.where(act, a11 * a22 - Hxy * Hxy, 1.0)
+            # det(H + lam I) = lam^2 + lam tr(H) + det(H) >= lam (lam + tr H); the bound only matters in float32
+            det = np.where(act, np.maximum(a11 * a22 - Hxy * Hxy, lam * (lam + Hxx + Hyy)), 1.0)
             dx = np.where(act, (a22 * gx - Hxy * gy) / det, 0.0)
             dy = np.where(act, (a11 * gy - Hxy * gx) / det, 0.0)
             dx = np.clip(dx, -prm.max_step, prm.max_step)

@@ -273,7 +273,9 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
                 if (!dense && !__any_sync(PMP_FULL, act)) break;   // later steps would be no-ops for every lane
                 const float lam = prm.reg_eps * S;
                 const float a11 = Hxx + lam, a22 = Hyy + lam;
-                const float det = fmaf(a11, a22, -Hxy * Hxy);
+                // det(H + lam I) = lam^2 + lam tr(H) + det(H) >= lam (lam + tr H): the bound keeps float32 cancellation in
+                // a11 a22 - Hxy^2 (H is rank one for a single contact) from flipping or inflating the step
+                const float det = fmaxf(fmaf(a11, a22, -Hxy * Hxy), lam * (lam + Hxx + Hyy));
                 const float idet = act ? __frcp_rn(det) : 0.f;
                 float dtx = (a22 * gx - Hxy * gy) * idet;
                 float dty = (a11 * gy - Hxy * gx) * idet;
