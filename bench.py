@@ -272,6 +272,14 @@ def main() -> None:
                 traffic = json.load(fp).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    issue = None
+    ipath = os.path.join(ROOT, "profiles", "issue_utilization.json")
+    if os.path.exists(ipath):
+        try:
+            with open(ipath) as fp:
+                issue = json.load(fp)          # static ncu evidence, not measured in this run
+        except Exception:
+            issue = None
     roofline = {
         "bound": "fp32", "unit": "TFLOP/s", "peak": peak_tf,
         "peak_source": "measured on this GPU in this run: dependent-FMA probe kernel (pmp_measure_fp32_peak); "
@@ -298,6 +306,7 @@ def main() -> None:
                 "peak_gbs": 6534.1, "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / 6534.1,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs"},
         "traffic": traffic,
+        "issue_slots": issue,
         "launch": {k: info[k] for k in ("grid", "block", "smem_bytes", "regs_per_thread", "worlds_in_smem")},
     }
 
