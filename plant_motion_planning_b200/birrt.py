@@ -306,6 +306,50 @@ def smooth_path_batched(checker, path: Sequence[Conf], distance_fn, rounds: int 
     return [tuple(float(v) for v in w) for w in way]
 
 
+# ------------------------------------------------------------------------------------------------ restarts / Planner
+def random_restarts_multi_world(start: Conf, goal: Conf, distance_fn, sample_fn, extend_fn, backend: FlagBackend,
+                                max_solutions: int = 1, smooth_attempts: int = 10, smoothing_iterations: int = 20,
+                                rrt_iterations: int = 2000, circular=None, log: Optional[PlanLog] = None):
+    """motion_planners/motion_planners/meta.py:156-273: solve, then up to 10 rounds of (20-iteration shortcut smoothing +
+    forward re-check of the smoothed path); the smoothed path replaces the raw one only if its re-check passes.
+    With max_solutions = 1 (birrt_multi_world, rrt_connect_..._v2.py:291-292) the end-effector length the reference
+    accumulates for ranking never changes the answer, so it is not computed here."""
+    solutions: List[List[Conf]] = []
+    while len(solutions) < max_solutions:
+        res = rrt_connect_multi_world(start, goal, distance_fn, sample_fn, extend_fn, backend, rrt_iterations, log,
+                                      circular=circular)
+        if res is None or res[0] is None:
+            continue
+        path = res[0]
+        accepted = None
+        for _ in range(smooth_attempts):
+            sm = smooth_path_multi_world(path, extend_fn, distance_fn, backend, max_iterations=smoothing_iterations, log=log)
+            k = first_violation(backend.flags(sm), True) if sm else 0
+            if log is not None:
+                log.edges.append(("resmooth-check", len(sm), k))
+            if k == len(sm):
+                accepted = sm
+                break
+        solutions.append(accepted if accepted is not None else path)
+    return solutions[0]
+
+
+def move_arm_conf2conf_multi_world(start: Conf, goal: Conf, distance_fn, sample_fn, extend_fn, backend: FlagBackend,
+                                   num_attempts: int = 200, circular=None, log: Optional[PlanLog] = None):
+    """Planner.move_arm_conf2conf_multi_world (planner.py:18-51) -> get_free_motion_gen_with_angle_constraints_multi_world
+    (kuka_primitives.py:1069-1107) -> plan_joint_motion_with_angle_constraints_multi_world (pybullet_tools/utils.py:4506-4567):
+    per attempt the start and goal are re-checked (the reference exit()s if either is rejected; here ValueError), then
+    birrt_multi_world = random restarts with max_solutions 1.  Returns the path (list of configurations) or None."""
+    for _ in range(num_attempts):
+        for name, q in (("Initial", start), ("End", goal)):
+            if first_violation(backend.flags([q]), True) == 0:
+                raise ValueError(f"Error! {name} configuration is in collision")
+        path = random_restarts_multi_world(start, goal, distance_fn, sample_fn, extend_fn, backend, circular=circular, log=log)
+        if path is not None:
+            return path
+    return None
+
+
 # ------------------------------------------------------------------------------------------------ batched proposals
 def extend_many(checker, q_from: np.ndarray, q_to: np.ndarray, backward: bool = False, forward_checker: bool = True,
                 probability: float = GATE_PROBABILITY, rand: Optional[Callable[[], float]] = None):

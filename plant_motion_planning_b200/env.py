@@ -10,7 +10,8 @@ What the reference's RRT fork calls and what it gets here:
                                               np.random.rand() exactly where the reference does (utils.py:3836-3855)
   ..._backward(q) / ..._benchmark(q)          rigid obstacles only (env.py:96-120, 241-255)
   env.envs[(x, y)].plant_rep.observe_all() / .deflections / .observe_all_and_check(limit)
-  save_state() / restore_state(id)            no-ops returning ids: nothing to snapshot (pybullet_tools/utils.py:1517-1523)
+  save_state() / restore_state(id)            snapshot / restore of the one piece of state the model has: the arm
+                                              configuration last stepped to (pybullet_tools/utils.py:1517-1523)
 Additive: env.checker (EdgeChecker), env.validate_edges(...) for batched use.
 
 Like the reference's collision closures, the checkers test the state left by the last ``step`` and use their
@@ -29,18 +30,24 @@ from .model.robot import RobotModel
 from .planner_fns import GATE_PROBABILITY, get_limits_fn
 from .robots import load_iiwa14
 
-_STATE_COUNTER = [0]
+_STATES: Dict[int, Tuple[object, Optional[Tuple[float, ...]]]] = {}
+_ACTIVE: List[Optional["MultiPlantWorld"]] = [None]
 
 
 def save_state() -> int:
-    """pybullet_tools/utils.py:1517-1519 -- the quasi-static model has no state; ids only keep callers happy."""
-    _STATE_COUNTER[0] += 1
-    return _STATE_COUNTER[0]
+    """pybullet_tools/utils.py:1517-1519 (p.saveState).  The quasi-static world has one piece of state -- the arm
+    configuration it was last stepped to -- so a snapshot is that configuration of the active MultiPlantWorld."""
+    sid = len(_STATES) + 1
+    env = _ACTIVE[0]
+    _STATES[sid] = (env, None if env is None else env._action)
+    return sid
 
 
 def restore_state(state_id: int) -> None:
-    """pybullet_tools/utils.py:1521-1523."""
-    return None
+    """pybullet_tools/utils.py:1521-1523 (p.restoreState)."""
+    env, action = _STATES.get(state_id, (None, None))
+    if env is not None:
+        env._action = action
 
 
 class PlantRepresentation:
@@ -164,6 +171,7 @@ class MultiPlantWorld:
             self.envs[xy] = SinglePlantEnv(self, i, w, xy, avoid_all)
         self.fixed = self.envs[offsets[0]].fixed
         self._action: Optional[Tuple[float, ...]] = None
+        _ACTIVE[0] = self
         self._cache_q: Optional[Tuple[float, ...]] = None
         self._cache = None
         self.kernel_evaluations = 0

@@ -18,6 +18,8 @@ Everything that is *arithmetic of the reference* runs unmodified from /root/refe
   reference_rrt.json           the reference's rrt_connect_multi_world run unchanged against this repository's
                                MultiPlantWorld facade (oracle-backed here): returned paths + RNG state for the three
                                multi_world_* script scenarios
+  reference_planner.json       the reference's Planner.move_arm_conf2conf_multi_world + execute_path_multi_world run
+                               unchanged (whole call chain down to the RRT loop) on a robot with Val's joint layout
   reference_fk.json            iiwa14 link frames composed with the reference's pybullet_tools/transformations.py
   seed1_plant.json             models/plant.urdf + models/plant_params.pkl (the one artefact of the reference that
                                carries sampler outputs) as plain numbers
@@ -547,6 +549,88 @@ def gen_rrt(out):
     out["reference_rrt.json"] = res
 
 
+def gen_planner(out):
+    """The reference's whole planning entry point, UNCHANGED: Planner.move_arm_conf2conf_multi_world (planner.py:18-51) ->
+    get_free_motion_gen_with_angle_constraints_multi_world -> plan_joint_motion_with_angle_constraints_multi_world ->
+    birrt_multi_world -> random_restarts_multi_world -> rrt_connect_multi_world / smooth_path_multi_world, followed by
+    Planner.execute_path_multi_world, run against this repository's MultiPlantWorld facade (oracle-backed here).
+    BodyConf hard-codes Val's joint layout (val_utils.py:12-23: the arm is movable joints 6..14), so the robot is a
+    synthetic URDF with that layout (tests/synthetic_robot.py: 4 wheels, 2 torso joints, a 9-joint arm)."""
+    import contextlib
+    import io
+    import re
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle import edgecheck_oracle as ORC
+    from oracle_checker import OracleChecker
+    from plant_motion_planning.planner import Planner
+    from plant_motion_planning.pybullet_tools.val_utils import get_arm_joints
+    from plant_motion_planning_b200.env import MultiPlantWorld
+    from synthetic_robot import val_like_robot, val_like_urdf_text
+    pb.saveState = lambda *a, **k: 1
+    pb.restoreState = lambda *a, **k: None
+    pb.resetJointState = lambda *a, **k: None
+    model, tree = val_like_robot()
+    with tempfile.NamedTemporaryFile("w", suffix=".urdf", delete=False) as fp:
+        fp.write(val_like_urdf_text())
+        path_urdf = fp.name
+    register_urdf_body(0, path_urdf)
+    os.unlink(path_urdf)
+    joints = get_arm_joints(0, is_left=True, include_torso=False)
+    assert list(joints) == [6, 7, 8, 9, 10, 11, 12, 13, 14]
+    np.random.seed(19)
+    random.seed(19)
+    env = MultiPlantWorld((0, 5), (0, 5), 0.30, 1, 2, 1, ((0.2, 0.35), (-0.5, 0.0)), robot=model,
+                          checker_factory=OracleChecker)
+    # goal: the accepted configuration (no flag in any world) that bends the plants most -- so the gate is exercised
+    rng = np.random.RandomState(2)
+    cands = rng.uniform(model.lower, model.upper, size=(6000, 9))
+    r = env.checker.check_configs_host(cands.astype(np.float32), detail=True)
+    ok = (r["flags"] == 0).all(axis=1)
+    score = np.where(ok, r["deflection"].sum(axis=(1, 2)), -1.0)
+    goal = tuple(float(v) for v in cands[int(np.argmax(score))])
+    start = tuple([0.0] * 9)
+
+    def ee_state(link, _env=env, _m=model):
+        pos, quat, com = ORC.link_poses(_m, np.asarray(_env._action, dtype=np.float64)[None])
+        return (tuple(com[0, link]), tuple(quat[0, link]), (0, 0, 0), (0, 0, 0, 1), tuple(pos[0, link]), tuple(quat[0, link]))
+    pb.bodies[0]["link_state"] = ee_state
+
+    class _Proxy:
+        sample_robot = 0
+        def __init__(self, e):
+            self._e = e
+            self.joints = list(joints)
+        def __getattr__(self, k):
+            return getattr(self._e, k)
+    penv = _Proxy(env)
+    from plant_motion_planning_b200 import env as facade
+    pb.saveState = lambda *a, **k: facade.save_state()
+    pb.restoreState = lambda sid=None, *a, **k: facade.restore_state(sid if sid is not None else k.get("stateId"))
+    env.step(start)
+    saved_world = pb.saveState()                       # scripts/multi_world_our_method.py:111
+    np.random.seed(1)
+    random.seed(1)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        planner = Planner()
+        cmd = planner.move_arm_conf2conf_multi_world(start, goal, penv)
+        nxt_np, nxt_py = float(np.random.rand()), float(random.random())
+        pb.restoreState(saved_world)                   # scripts/multi_world_our_method.py:118
+        planner.execute_path_multi_world(penv)
+    txt = buf.getvalue()
+    path = [[float(v) for v in q] for q in cmd.body_paths[0].path]
+    ee_len = float(re.findall(r"total path cost:\s+([-0-9.e+]+)", txt)[-1])
+    over = [float(v) for v in re.findall(r"total Deflection over limit:\s+\[([^\]]*)\]", txt)[-1].split()]
+    out["reference_planner.json"] = {
+        "robot": "tests/synthetic_robot.py:val_like_robot()", "world_seed": 19, "planner_seed": 1,
+        "start": list(start), "goal": list(goal), "goal_deflection_sum": float(score.max()),
+        "path": path, "next_np_rand": nxt_np, "next_py_random": nxt_py,
+        "kernel_evaluations": int(env.kernel_evaluations),
+        "execute": {"ee_len": ee_len, "over": over},
+    }
+
+
 def gen_fixtures(out):
     def plant_numbers(urdf_path, pkl_path):
         tree = parse_urdf(urdf_path)
@@ -577,6 +661,7 @@ def main():
     gen_gate(out)
     gen_fk(out)
     gen_rrt(out)
+    gen_planner(out)
     gen_fixtures(out)
     for name, obj in out.items():
         path = os.path.join(HERE, name)

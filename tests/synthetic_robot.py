@@ -50,3 +50,49 @@ def synthetic_robot(n_joints: int = 9, spheres_per_link: int = 2, seed: int = 0,
     if prune:
         prune_always_colliding(model, samples=512)
     return model
+
+
+def val_like_urdf_text(seed: int = 0) -> str:
+    """A robot with Val's joint layout (pybullet_tools/val_utils.py:5-23): movable joints 0-3 wheels, 4-5 torso,
+    6-14 the nine left-arm joints -- so that the reference's BodyConf / get_arm_joints pick the arm unchanged."""
+    rng = np.random.RandomState(seed)
+    out = ['<?xml version="1.0"?>', '<robot name="val_like">',
+           '<link name="base"><collision><origin xyz="0 0 0.1"/><geometry><box size="0.5 0.4 0.2"/></geometry></collision></link>']
+    for k, (x, y) in enumerate([(0.2, 0.2), (0.2, -0.2), (-0.2, 0.2), (-0.2, -0.2)]):
+        out.append(f'<joint name="wheel{k}" type="continuous"><parent link="base"/><child link="w{k}"/>'
+                   f'<origin xyz="{x} {y} 0.05"/><axis xyz="0 1 0"/></joint><link name="w{k}"/>')
+    out.append('<joint name="torso0" type="revolute"><parent link="base"/><child link="t0"/><origin xyz="0 0 0.25"/>'
+               '<axis xyz="0 0 1"/><limit lower="-1" upper="1" effort="1" velocity="1"/></joint>'
+               '<link name="t0"><collision><origin xyz="0 0 0.1"/><geometry><sphere radius="0.09"/></geometry></collision></link>')
+    out.append('<joint name="torso1" type="revolute"><parent link="t0"/><child link="t1"/><origin xyz="0 0 0.2"/>'
+               '<axis xyz="0 1 0"/><limit lower="-1" upper="1" effort="1" velocity="1"/></joint>'
+               '<link name="t1"><collision><origin xyz="0 0 0.1"/><geometry><sphere radius="0.08"/></geometry></collision></link>')
+    parent = "t1"
+    for j in range(9):
+        link = f"a{j}"
+        xyz = [0.0, 0.12, 0.15] if j == 0 else [0.0, 0.0, 0.11]
+        rpy = rng.uniform(-0.5, 0.5, 3) * (j % 2)
+        out.append(f'<joint name="arm{j}" type="revolute"><parent link="{parent}"/><child link="{link}"/>'
+                   f'<origin xyz="{xyz[0]} {xyz[1]} {xyz[2]}" rpy="{rpy[0]:.6f} {rpy[1]:.6f} {rpy[2]:.6f}"/>'
+                   f'<axis xyz="{AXES[j]}"/><limit lower="{-2.2 - 0.05 * j:.3f}" upper="{2.2 + 0.05 * j:.3f}" effort="10" velocity="1"/></joint>')
+        r = 0.04 - 0.002 * j
+        out.append(f'<link name="{link}"><inertial><origin xyz="0 0 0.05"/><mass value="1"/></inertial>'
+                   f'<collision><origin xyz="0 0 0.055"/><geometry><sphere radius="{r:.4f}"/></geometry></collision></link>')
+        parent = link
+    out.append('</robot>')
+    return "\n".join(out)
+
+
+def val_like_robot(seed: int = 0, torso=(0.2, -0.3), ee_link_index: int = 9):
+    """Compiled with the arm as the active chain, wheels/torso frozen; the cost end-effector is PyBullet link 9, the
+    link the reference hard-codes (kuka_primitives.py:478)."""
+    from plant_motion_planning_b200.model.robot import compile_robot, prune_always_colliding
+    from plant_motion_planning_b200.model.transforms import Frame
+    from plant_motion_planning_b200.model.urdf import parse_urdf
+    tree = parse_urdf(val_like_urdf_text(seed), is_text=True)
+    model = compile_robot(tree, active_joints=[f"arm{j}" for j in range(9)],
+                          frozen_positions={"torso0": torso[0], "torso1": torso[1]},
+                          base=Frame(np.eye(3), np.array([-0.35, 0.25, 0.0])),
+                          ee_link=tree.joints[ee_link_index].child, name="val_like")
+    prune_always_colliding(model, samples=512)
+    return model, tree

@@ -104,3 +104,40 @@ def test_gpu_path_cost_equals_reference_execute_report(script):
     ee_len, over, total, ex = _cost(script, None)
     assert abs(ee_len - ex["ee_len"]) < 1e-4
     assert np.allclose(over, ex["over"], atol=5e-3, rtol=1e-3) and np.allclose(total, ex["total"], atol=1e-3, rtol=1e-3)
+
+
+def _planner_case(factory):
+    from plant_motion_planning_b200.env import MultiPlantWorld
+    from synthetic_robot import val_like_robot
+    with open(os.path.join(G, "reference_planner.json")) as fp:
+        gold = json.load(fp)
+    model, _ = val_like_robot()
+    np.random.seed(gold["world_seed"])
+    random.seed(gold["world_seed"])
+    env = MultiPlantWorld((0, 5), (0, 5), 0.30, 1, 2, 1, ((0.2, 0.35), (-0.5, 0.0)), robot=model, checker_factory=factory)
+    backend = _Backend(env.checker, True)
+    np.random.seed(gold["planner_seed"])
+    random.seed(gold["planner_seed"])
+    path = birrt.move_arm_conf2conf_multi_world(tuple(gold["start"]), tuple(gold["goal"]), F.get_distance_fn(model),
+                                                F.get_sample_fn(model), F.get_extend_fn(model), backend)
+    nxt = (float(np.random.rand()), float(random.random()))
+    ee_len, over, _ = env.path_cost(tuple(gold["start"]), path)
+    return path, nxt, ee_len, over, gold
+
+
+def test_restated_planner_equals_reference_planner_on_oracle_flags():
+    """The reference's unchanged Planner.move_arm_conf2conf_multi_world (whole chain: free-motion generator, start/goal
+    checks, random restarts, RRT-connect, 10 x 20 smoothing, forward re-checks; 32 018 checker calls) on a robot with
+    Val's joint layout, vs birrt.move_arm_conf2conf_multi_world: same path, same RNG state, same cost report."""
+    path, nxt, ee_len, over, gold = _planner_case(OracleChecker)
+    assert [list(q) for q in path] == gold["path"]
+    assert nxt == (gold["next_np_rand"], gold["next_py_random"])
+    assert abs(ee_len - gold["execute"]["ee_len"]) < 1e-5 and np.allclose(over, gold["execute"]["over"], atol=1e-4)
+
+
+@pytest.mark.gpu
+def test_gpu_planner_equals_reference_planner():
+    path, nxt, ee_len, over, gold = _planner_case(None)
+    assert [list(q) for q in path] == gold["path"]
+    assert nxt == (gold["next_np_rand"], gold["next_py_random"])
+    assert abs(ee_len - gold["execute"]["ee_len"]) < 1e-4 and np.allclose(over, gold["execute"]["over"], atol=5e-3)
