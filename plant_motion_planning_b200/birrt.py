@@ -241,6 +241,11 @@ def smooth_path_multi_world(path: Sequence[Conf], extend_fn, distance_fn, backen
     segments are drawn with probability proportional to their length (np.random.choice), a point is drawn on each
     (random.random), and the shortcut between them is kept if it shortens the path and passes the forward checker.
     One kernel launch per tried shortcut."""
+    return _smooth(path, extend_fn, distance_fn, backend, max_iterations, True, log)
+
+
+def _smooth(path: Sequence[Conf], extend_fn, distance_fn, backend: FlagBackend, max_iterations: int, forward: bool,
+            log: Optional[PlanLog]) -> List[Conf]:
     import random as _random
     way = waypoints_from_path(path)
     for _ in range(max_iterations):
@@ -263,7 +268,7 @@ def smooth_path_multi_world(path: Sequence[Conf], extend_fn, distance_fn, backen
         if _path_length(new_way, distance_fn) >= total:
             continue
         cfgs = list(extend_fn(p1, p2))
-        k = first_violation(backend.flags(cfgs), True) if cfgs else 0
+        k = first_violation(backend.flags(cfgs), forward) if cfgs else 0
         if log is not None:
             log.edges.append(("shortcut", len(cfgs), k))
         if k == len(cfgs):
@@ -345,6 +350,67 @@ def move_arm_conf2conf_multi_world(start: Conf, goal: Conf, distance_fn, sample_
             if first_violation(backend.flags([q]), True) == 0:
                 raise ValueError(f"Error! {name} configuration is in collision")
         path = random_restarts_multi_world(start, goal, distance_fn, sample_fn, extend_fn, backend, circular=circular, log=log)
+        if path is not None:
+            return path
+    return None
+
+
+# ------------------------------------------------------------------------------------------------ benchmark chain
+def rrt_connect_benchmark(start: Conf, goal: Conf, distance_fn, sample_fn, extend_fn, backend: FlagBackend,
+                          max_iterations: int = 20, log: Optional[PlanLog] = None, circular=None):
+    """rrt_connect_multiworld_benchmark (motion_planners/motion_planners/rrt_connect.py:62-91): classic RRT-connect --
+    the smaller tree is extended first, both extensions use the rigid-obstacle checker
+    (net_constraint_violation_checker_benchmark), RRT_ITERATIONS = 20 iterations per call."""
+    nodes1, nodes2 = ConfigTree([TreeNode(start)], circular), ConfigTree([TreeNode(goal)], circular)
+    for it in range(max_iterations):
+        if log is not None:
+            log.iterations += 1
+        swap = len(nodes1) > len(nodes2)
+        tree1, tree2 = (nodes2, nodes1) if swap else (nodes1, nodes2)
+        target = sample_fn()
+        last1, _ = extend_towards(tree1, target, distance_fn, extend_fn, backend, False, swap, log)
+        last2, success = extend_towards(tree2, last1.config, distance_fn, extend_fn, backend, False, not swap, log)
+        if success:
+            path1, path2 = last1.retrace(), last2.retrace()
+            if swap:
+                path1, path2 = path2, path1
+            return [n.config for n in path1[:-1] + path2[::-1]]
+    return None
+
+
+def smooth_path_benchmark(path: Sequence[Conf], extend_fn, backend: FlagBackend, max_iterations: int = 5,
+                          log: Optional[PlanLog] = None) -> List[Conf]:
+    """smooth_path_multiworld_benchmark (smoothing.py:651-707): as smooth_path_multi_world but with the Euclidean
+    metric, the rigid checker (no gate, so the bisect visiting order of the reference does not matter) and
+    RRT_SMOOTHING = 5 iterations."""
+    euclid = lambda a, b: float(np.linalg.norm(np.asarray(b) - np.asarray(a)))
+    return _smooth(path, extend_fn, euclid, backend, max_iterations, False, log)
+
+
+def random_restarts_benchmark(start: Conf, goal: Conf, distance_fn, sample_fn, extend_fn, backend: FlagBackend,
+                              restarts: int = 2, smooth: int = 5, rrt_iterations: int = 20, circular=None,
+                              log: Optional[PlanLog] = None):
+    """random_restarts_multiworld_benchmark (meta.py:89-118) with max_solutions = 1: up to restarts + 1 solves, the first
+    solution is smoothed and returned."""
+    for _ in range(restarts + 1):
+        path = rrt_connect_benchmark(start, goal, distance_fn, sample_fn, extend_fn, backend, rrt_iterations, log, circular)
+        if path is None:
+            continue
+        return smooth_path_benchmark(path, extend_fn, backend, smooth, log)
+    return None
+
+
+def move_arm_conf2conf_multi_world_benchmark(start: Conf, goal: Conf, distance_fn, sample_fn, extend_fn,
+                                             backend: FlagBackend, num_attempts: int = 200, circular=None,
+                                             log: Optional[PlanLog] = None):
+    """Planner.move_arm_conf2conf_multi_world_benchmark (planner.py:53-78) -> get_free_motion_gen_multiworld_benchmark
+    (kuka_primitives.py:1019-1039) -> plan_joint_motion_multiworld_benchmark (pybullet_tools/utils.py:4483-4503): what
+    the avoid_all / ignore_all scripts run.  Rigid checker everywhere; start/goal are re-checked every attempt."""
+    for _ in range(num_attempts):
+        for name, q in (("Initial", start), ("End", goal)):
+            if first_violation(backend.flags([q]), False) == 0:
+                raise ValueError(f"Error! {name} configuration is in collision")
+        path = random_restarts_benchmark(start, goal, distance_fn, sample_fn, extend_fn, backend, circular=circular, log=log)
         if path is not None:
             return path
     return None

@@ -622,13 +622,41 @@ def gen_planner(out):
     path = [[float(v) for v in q] for q in cmd.body_paths[0].path]
     ee_len = float(re.findall(r"total path cost:\s+([-0-9.e+]+)", txt)[-1])
     over = [float(v) for v in re.findall(r"total Deflection over limit:\s+\[([^\]]*)\]", txt)[-1].split()]
-    out["reference_planner.json"] = {
+    result = {
         "robot": "tests/synthetic_robot.py:val_like_robot()", "world_seed": 19, "planner_seed": 1,
         "start": list(start), "goal": list(goal), "goal_deflection_sum": float(score.max()),
         "path": path, "next_np_rand": nxt_np, "next_py_random": nxt_py,
         "kernel_evaluations": int(env.kernel_evaluations),
         "execute": {"ee_len": ee_len, "over": over},
     }
+    # ---- the benchmark entry the avoid_all / ignore_all scripts use (planner.py:53-78), same worlds with avoid_all ----
+    np.random.seed(19)
+    random.seed(19)
+    env2 = MultiPlantWorld((0, 5), (0, 5), 0.30, 1, 2, 1, ((0.2, 0.35), (-0.5, 0.0)), robot=model, avoid_all=True,
+                           checker_factory=OracleChecker)
+    r2 = env2.checker.check_configs_host(cands.astype(np.float32), detail=False)
+    ok2 = (r2["flags"] & 1 == 0).all(axis=1)
+    ee_c = ORC.ee_positions(model, cands)
+    score2 = np.where(ok2, -np.linalg.norm(ee_c - np.array([0.27, -0.25, 0.45]), axis=1), -1e9)
+    goal2 = tuple(float(v) for v in cands[int(np.argmax(score2))])
+    pb.bodies[0]["link_state"] = lambda link, _env=env2, _m=model: ee_state(link, _env, _m)
+    pb.getJointState = lambda body, joint, *a, **k: (float(env2._action[list(joints).index(joint)]), 0.0, (0.0,) * 6, 0.0)
+    penv2 = _Proxy(env2)
+    env2.step(start)
+    saved2 = pb.saveState()
+    np.random.seed(1)
+    random.seed(1)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        planner2 = Planner()
+        cmd2 = planner2.move_arm_conf2conf_multi_world_benchmark(start, goal2, penv2, saved2)
+        nxt2 = (float(np.random.rand()), float(random.random()))
+    result["benchmark"] = {
+        "avoid_all": True, "goal": list(goal2),
+        "path": [[float(v) for v in q] for q in cmd2.body_paths[0].path],
+        "next_np_rand": nxt2[0], "next_py_random": nxt2[1], "kernel_evaluations": int(env2.kernel_evaluations),
+    }
+    out["reference_planner.json"] = result
 
 
 def gen_fixtures(out):

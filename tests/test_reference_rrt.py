@@ -141,3 +141,37 @@ def test_gpu_planner_equals_reference_planner():
     assert [list(q) for q in path] == gold["path"]
     assert nxt == (gold["next_np_rand"], gold["next_py_random"])
     assert abs(ee_len - gold["execute"]["ee_len"]) < 1e-4 and np.allclose(over, gold["execute"]["over"], atol=5e-3)
+
+
+def _benchmark_case(factory):
+    from plant_motion_planning_b200.env import MultiPlantWorld
+    from synthetic_robot import val_like_robot
+    with open(os.path.join(G, "reference_planner.json")) as fp:
+        gold = json.load(fp)
+    model, _ = val_like_robot()
+    np.random.seed(gold["world_seed"])
+    random.seed(gold["world_seed"])
+    env = MultiPlantWorld((0, 5), (0, 5), 0.30, 1, 2, 1, ((0.2, 0.35), (-0.5, 0.0)), robot=model, avoid_all=True,
+                          checker_factory=factory)
+    np.random.seed(gold["planner_seed"])
+    random.seed(gold["planner_seed"])
+    b = gold["benchmark"]
+    path = birrt.move_arm_conf2conf_multi_world_benchmark(tuple(gold["start"]), tuple(b["goal"]), F.get_distance_fn(model),
+                                                          F.get_sample_fn(model), F.get_extend_fn(model),
+                                                          _Backend(env.checker, True))
+    return path, (float(np.random.rand()), float(random.random())), b
+
+
+def test_restated_benchmark_planner_equals_reference_on_oracle_flags():
+    """Planner.move_arm_conf2conf_multi_world_benchmark (planner.py:53-78; what multi_world_avoid_all / ignore_all run),
+    unchanged reference code vs birrt.move_arm_conf2conf_multi_world_benchmark, avoid_all worlds."""
+    path, nxt, b = _benchmark_case(OracleChecker)
+    assert [list(q) for q in path] == b["path"]
+    assert nxt == (b["next_np_rand"], b["next_py_random"])
+
+
+@pytest.mark.gpu
+def test_gpu_benchmark_planner_equals_reference():
+    path, nxt, b = _benchmark_case(None)
+    assert [list(q) for q in path] == b["path"]
+    assert nxt == (b["next_np_rand"], b["next_py_random"])
