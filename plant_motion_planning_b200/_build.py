@@ -16,10 +16,11 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libpmp_edgecheck.so")
 STAMP = os.path.join(LIB_DIR, "libpmp_edgecheck.stamp")
-SOURCES = ["pmp_edgecheck.cu"]
-HEADERS = ["pmp_kernels.cuh", "pmp_tables.h", os.path.join("..", "..", "include", "pmp_edgecheck.h")]
+SOURCES = ["pmp_edgecheck.cu", "pmp_inst_a12.cu", "pmp_inst_a16.cu", "pmp_inst_a32.cu"]
+HEADERS = ["pmp_kernels.cuh", "pmp_tables.h", "pmp_launch.h", "pmp_launch_impl.cuh",
+           os.path.join("..", "..", "include", "pmp_edgecheck.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "--shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
 
 def _nvcc() -> str:
@@ -50,16 +51,37 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and is_current():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
+    obj_dir = os.path.join(LIB_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    nvcc = _nvcc()
     log = os.path.join(LIB_DIR, "build.log")
+
+    def compile_one(src: str):
+        obj = os.path.join(obj_dir, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        return src, obj, cmd, proc
+
+    # one translation unit per sphere-count padding: the template instantiations compile in parallel
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    text = ""
+    for src, obj, cmd, proc in results:
+        text += " ".join(cmd) + "\n" + proc.stdout + proc.stderr + "\n"
+    link = [nvcc, "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + [r[1] for r in results]
+    failed = [r for r in results if r[3].returncode != 0]
+    lproc = None
+    if not failed:
+        lproc = subprocess.run(link, capture_output=True, text=True)
+        text += " ".join(link) + "\n" + lproc.stdout + lproc.stderr
     with open(log, "w") as fp:
-        fp.write(" ".join(cmd) + "\n" + proc.stdout + proc.stderr)
-    if proc.returncode != 0:
-        sys.stderr.write(proc.stdout + proc.stderr)
+        fp.write(text)
+    if failed or lproc.returncode != 0:
+        sys.stderr.write(text[-4000:])
         raise RuntimeError(f"nvcc failed (see {log})")
     if verbose:
-        sys.stderr.write(proc.stderr)
+        sys.stderr.write(text)
     with open(STAMP, "w") as fp:
         fp.write(source_digest())
     return LIB_PATH

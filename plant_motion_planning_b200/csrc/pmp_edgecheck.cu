@@ -9,7 +9,7 @@
 #include <string>
 #include <vector>
 
-#include "pmp_kernels.cuh"
+#include "pmp_launch.h"
 
 struct pmp_ctx {
     int device = 0;
@@ -235,59 +235,7 @@ extern "C" int pmp_fk(pmp_ctx* ctx, const float* q_dev, int32_t B, float* pos, f
     return PMP_OK;
 }
 
-// ---- kernel selection ---------------------------------------------------------------------------
-template <int A, int NS>
-static cudaError_t launch_edge(pmp_ctx* ctx, const PmpEdgeArgs& args, bool wsmem, int grid, int block, size_t smem,
-                               cudaStream_t st) {
-    cudaError_t e;
-    cudaFuncAttributes fa;
-    if (wsmem) {
-        e = cudaFuncSetAttribute(pmp_edge_kernel<A, NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        pmp_edge_kernel<A, NS, true><<<grid, block, smem, st>>>(args);
-        cudaFuncGetAttributes(&fa, pmp_edge_kernel<A, NS, true>);
-    } else {
-        e = cudaFuncSetAttribute(pmp_edge_kernel<A, NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        pmp_edge_kernel<A, NS, false><<<grid, block, smem, st>>>(args);
-        cudaFuncGetAttributes(&fa, pmp_edge_kernel<A, NS, false>);
-    }
-    ctx->info.regs_per_thread = fa.numRegs;
-    return cudaGetLastError();
-}
-
-template <int A, int NS>
-static cudaError_t launch_config(pmp_ctx* ctx, const PmpConfigArgs& args, dim3 grid, int block, size_t smem,
-                                 cudaStream_t st) {
-    pmp_config_kernel<A, NS><<<grid, block, smem, st>>>(args);
-    cudaFuncAttributes fa;
-    cudaFuncGetAttributes(&fa, pmp_config_kernel<A, NS>);
-    ctx->info.regs_per_thread = fa.numRegs;
-    return cudaGetLastError();
-}
-
-#ifdef PMP_FAST_BUILD   /* development builds: only the iiwa14 / (1,2,1)-plant instantiation */
-#define PMP_DISPATCH(FN, ...)                                                              \
-    do {                                                                                   \
-        if (apad == 12 && nspad == 2) err = FN<12, 2>(__VA_ARGS__);                        \
-        else err = cudaErrorNotSupported;                                                  \
-    } while (0)
-#else
-#define PMP_DISPATCH(FN, ...)                                                              \
-    do {                                                                                   \
-        const int ap_ = apad, ns_ = nspad;                                                 \
-        if (ap_ == 12 && ns_ == 1) err = FN<12, 1>(__VA_ARGS__);                           \
-        else if (ap_ == 12 && ns_ == 2) err = FN<12, 2>(__VA_ARGS__);                      \
-        else if (ap_ == 12 && ns_ == 4) err = FN<12, 4>(__VA_ARGS__);                      \
-        else if (ap_ == 16 && ns_ == 1) err = FN<16, 1>(__VA_ARGS__);                      \
-        else if (ap_ == 16 && ns_ == 2) err = FN<16, 2>(__VA_ARGS__);                      \
-        else if (ap_ == 16 && ns_ == 4) err = FN<16, 4>(__VA_ARGS__);                      \
-        else if (ap_ == 32 && ns_ == 1) err = FN<32, 1>(__VA_ARGS__);                      \
-        else if (ap_ == 32 && ns_ == 2) err = FN<32, 2>(__VA_ARGS__);                      \
-        else err = FN<32, 4>(__VA_ARGS__);                                                 \
-    } while (0)
-#endif
-
+// ---- kernel selection (instantiations live in pmp_inst_a*.cu) ---------------------------------------
 static void pads(pmp_ctx* ctx, int& apad, int& nspad) {
     const int A = ctx->h_robot.n_spheres;
     apad = A <= 12 ? 12 : (A <= 16 ? 16 : 32);
@@ -337,7 +285,11 @@ extern "C" int pmp_validate_edges(pmp_ctx* ctx, const float* q0, const float* q1
     const int cap = ctx->sm_count * per_sm;
     if (grid > cap) grid = cap;
     cudaError_t err;
-    PMP_DISPATCH(launch_edge, ctx, a, wsmem, grid, block, smem, (cudaStream_t)stream);
+    int regs = 0;
+    if (apad == 12) err = pmp_launch_edge_a12(nspad, a, wsmem, grid, block, smem, (cudaStream_t)stream, &regs);
+    else if (apad == 16) err = pmp_launch_edge_a16(nspad, a, wsmem, grid, block, smem, (cudaStream_t)stream, &regs);
+    else err = pmp_launch_edge_a32(nspad, a, wsmem, grid, block, smem, (cudaStream_t)stream, &regs);
+    ctx->info.regs_per_thread = regs;
     if (err != cudaSuccess) return fail(ctx, PMP_E_CUDA, std::string("edge kernel launch: ") + cudaGetErrorString(err));
     ctx->info.grid = grid; ctx->info.block = block; ctx->info.smem_bytes = (int)smem;
     ctx->info.worlds_in_smem = wsmem ? 1 : 0; ctx->info.n_sphere_pad = apad; ctx->info.n_slot_pad = nspad;
@@ -370,7 +322,11 @@ extern "C" int pmp_check_configs(pmp_ctx* ctx, const float* q, int32_t B, uint8_
     const dim3 grid(gx, gy, 1);
     const size_t smem = sizeof(PmpRobotTab);
     cudaError_t err;
-    PMP_DISPATCH(launch_config, ctx, a, grid, block, smem, (cudaStream_t)stream);
+    int regs = 0;
+    if (apad == 12) err = pmp_launch_config_a12(nspad, a, grid, block, smem, (cudaStream_t)stream, &regs);
+    else if (apad == 16) err = pmp_launch_config_a16(nspad, a, grid, block, smem, (cudaStream_t)stream, &regs);
+    else err = pmp_launch_config_a32(nspad, a, grid, block, smem, (cudaStream_t)stream, &regs);
+    ctx->info.regs_per_thread = regs;
     if (err != cudaSuccess) return fail(ctx, PMP_E_CUDA, std::string("config kernel launch: ") + cudaGetErrorString(err));
     ctx->info.grid = gx * gy; ctx->info.block = block; ctx->info.smem_bytes = (int)smem; ctx->info.worlds_in_smem = 0;
     ctx->info.n_sphere_pad = apad; ctx->info.n_slot_pad = nspad;

@@ -685,7 +685,7 @@ __device__ __forceinline__ void pmp_emit_link(const PmpLinkTab& lt, int l, const
     }
 }
 
-__global__ void __launch_bounds__(128) pmp_fk_kernel(const PmpRobotTab* __restrict__ robot,
+static __global__ void __launch_bounds__(128) pmp_fk_kernel(const PmpRobotTab* __restrict__ robot,
                                                       const PmpLinkTab* __restrict__ links,
                                                       const float* __restrict__ q, int B, float* pos, float* quat,
                                                       float* com) {
@@ -725,7 +725,7 @@ __global__ void __launch_bounds__(128) pmp_fk_kernel(const PmpRobotTab* __restri
 }
 
 // FP32 FMA-pipe probe: 8 independent dependent-FMA chains per thread.
-__global__ void __launch_bounds__(256) pmp_fma_probe_kernel(float* out, int iters, float a, float b) {
+static __global__ void __launch_bounds__(256) pmp_fma_probe_kernel(float* out, int iters, float a, float b) {
     float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f,
           x6 = x0 + 6.f, x7 = x0 + 7.f;
     for (int i = 0; i < iters; ++i) {
