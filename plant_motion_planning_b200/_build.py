@@ -82,6 +82,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError(f"nvcc failed (see {log})")
     if verbose:
         sys.stderr.write(text)
+    shutil.rmtree(obj_dir, ignore_errors=True)      # 18 MB of objects that need not travel with the snapshot
     with open(STAMP, "w") as fp:
         fp.write(source_digest())
     return LIB_PATH

@@ -42,6 +42,13 @@ __device__ __forceinline__ void pmp_mat_mul(const float* __restrict__ X, const f
     }
 }
 __device__ __forceinline__ float pmp_clamp(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+// One MUFU.RSQ: the argument is clamped to >= 1e-24 by the caller, so the denormal pre/post-scaling that rsqrtf()
+// emits without -ftz (FSETP + FMUL + FSEL + FMUL per call) is dead weight in the innermost loop.
+__device__ __forceinline__ float pmp_rsqrt_ftz(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 // Sphere (centre c, radius r) against a static primitive: oracle _prim_hit.
 __device__ __forceinline__ bool pmp_prim_hit(int kind, const float* __restrict__ R, const float* __restrict__ t,
@@ -254,8 +261,8 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
                     const float wx = c[a][0] - tv[0], wy = c[a][1] - tv[1], wz = c[a][2] - tv[2];
                     const float tau = pmp_clamp(fmaf(wx, ux, fmaf(wy, uy, wz * uz)), z0, z1);
                     const float dx = fmaf(-tau, ux, wx), dy = fmaf(-tau, uy, wy), dz = fmaf(-tau, uz, wz);
-                    const float d2 = fmaxf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)), 1e-24f);
-                    const float inv = rsqrtf(d2);
+                    const float d2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, 1e-24f)));   // > 0: rsqrt stays finite
+                    const float inv = pmp_rsqrt_ftz(d2);
                     const float pen = fmaxf((rt.sph_radius[a] + rad) - d2 * inv, 0.f);
                     const float sc = -tau * inv;
                     const float Jx = sc * fmaf(dx, bxx, fmaf(dy, bxy, dz * bxz));
