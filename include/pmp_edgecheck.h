@@ -108,8 +108,27 @@ typedef struct pmp_params {
     int32_t mode;            /* PMP_MODE_* */
     int32_t dense;           /* 1 = disable data-dependent early exits (every unit runs all K iterations
                                 on every stem: results identical, used to measure the FP32 roofline) */
+    uint32_t gate_seed;      /* seed of the on-device gate (below) */
+    float gate_probability;  /* 0 = off.  Otherwise first_hit treats "deflection exceeded" at (edge e, step s,
+                                world w) as a violation only if hash32(gate_seed, e, s, w) < gate_probability * 2^32:
+                                the reference's 5 % random pass-through (pybullet_tools/utils.py:3843, probability 0.95)
+                                with a counter-based generator, so that it can run inside the kernel.  The raw step
+                                masks are never gated; replay them on the host to reproduce the reference's
+                                np.random stream exactly. */
     int32_t reserved;
 } pmp_params;
+
+/* The counter-based hash of the on-device gate (murmur3 finaliser over the mixed coordinates). */
+#ifdef __CUDACC__
+#define PMP_HOST_DEVICE __host__ __device__
+#else
+#define PMP_HOST_DEVICE
+#endif
+static inline PMP_HOST_DEVICE uint32_t pmp_gate_hash(uint32_t seed, uint32_t e, uint32_t s, uint32_t w) {
+    uint32_t h = seed ^ (e * 0x9E3779B1u) ^ (s * 0x85EBCA77u) ^ (w * 0xC2B2AE3Du);
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
 
 int pmp_create(pmp_ctx** out, int device);
 int pmp_destroy(pmp_ctx* ctx);

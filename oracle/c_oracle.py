@@ -98,7 +98,7 @@ class COracle:
         w.n_boxes, w.boxes = _capi.iptr(self.wt.n_boxes), _capi.fptr(self._boxes)
         self.wd = w
         self.prm = _capi.Params(float(resolution), deflection_limit, alpha, max_step, reg_eps, iterations, MODES[mode],
-                                1 if dense else 0, 0)
+                                1 if dense else 0, 0, 0.0, 0)
 
     @property
     def max_threads(self) -> int:

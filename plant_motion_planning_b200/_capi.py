@@ -44,7 +44,7 @@ class Params(C.Structure):
     _fields_ = [
         ("resolution", C.c_double), ("deflection_limit", C.c_float), ("alpha", C.c_float),
         ("max_step", C.c_float), ("reg_eps", C.c_float), ("iterations", C.c_int32), ("mode", C.c_int32),
-        ("dense", C.c_int32), ("reserved", C.c_int32),
+        ("dense", C.c_int32), ("gate_seed", C.c_uint32), ("gate_probability", C.c_float), ("reserved", C.c_int32),
     ]
 
 

@@ -204,6 +204,9 @@ extern "C" int pmp_set_params(pmp_ctx* ctx, const pmp_params* p) {
     ctx->prm.iterations = p->iterations;
     ctx->prm.mode = p->mode;
     ctx->prm.dense = p->dense;
+    if (!(p->gate_probability >= 0.f && p->gate_probability <= 1.f)) return fail(ctx, PMP_E_INVALID, "gate_probability outside [0, 1]");
+    ctx->prm.gate_seed = p->gate_seed;
+    ctx->prm.gate_threshold = p->gate_probability >= 1.f ? 0xFFFFFFFFu : (uint32_t)((double)p->gate_probability * 4294967296.0);
     ctx->has_params = true;
     return PMP_OK;
 }

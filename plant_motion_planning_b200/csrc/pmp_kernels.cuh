@@ -548,7 +548,14 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
                 }
                 const uint32_t rm = rigid0_mask | __ballot_sync(PMP_FULL, live && u.plant_hit);
                 const uint32_t xm = __ballot_sync(PMP_FULL, live && u.exceeded);
-                viol |= rm | xm;
+                uint32_t xg = xm;   // exceeded flags that count as violations
+                if (prm.gate_threshold != 0u && xm != 0u) {
+                    // on-device stand-in for `rand() < 0.95` (pybullet_tools/utils.py:3843): counter-based, so the
+                    // decision of (edge, step, world) does not depend on evaluation order
+                    const bool pass = pmp_gate_hash(prm.gate_seed, (uint32_t)e, (uint32_t)i, (uint32_t)w) < prm.gate_threshold;
+                    xg = __ballot_sync(PMP_FULL, live && u.exceeded && pass);
+                }
+                viol |= rm | xg;
                 const float md = __uint_as_float(__reduce_max_sync(PMP_FULL, __float_as_uint(live ? u.max_defl : 0.f)));
                 float ov = live ? u.over : 0.f;
 #pragma unroll

@@ -85,6 +85,8 @@ struct PmpKernelParams {
     int32_t iterations;
     int32_t mode;
     int32_t dense;
+    uint32_t gate_seed;
+    uint32_t gate_threshold;   // gate_probability * 2^32 (0 = gate off)
     int32_t n_worlds;
     int32_t max_stems;
     int32_t max_boxes;

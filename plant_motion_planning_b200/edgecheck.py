@@ -42,6 +42,8 @@ class EdgeCheckConfig:
     gate_probability: float = 0.95        # pybullet_tools/utils.py:3843 (applied by the host adapters only)
     max_steps: int = 320                  # per-edge step capacity of validate_edges
     dense: bool = False                   # disable data-dependent early exits (roofline measurements)
+    device_gate_seed: Optional[int] = None   # not None: validate_edges applies the gate on the device (counter-based
+                                             # hash instead of np.random; first_hit / valid then include the 5 % pass-through)
 
 
 @dataclass
@@ -141,7 +143,9 @@ class EdgeChecker:
         if c.mode not in MODES:
             raise ValueError(f"mode must be one of {sorted(MODES)}")
         p = _capi.Params(c.resolution, c.deflection_limit, c.alpha, c.max_step, c.reg_eps, c.iterations,
-                         MODES[c.mode], 1 if c.dense else 0, 0)
+                         MODES[c.mode], 1 if c.dense else 0,
+                         0 if c.device_gate_seed is None else int(c.device_gate_seed) & 0xFFFFFFFF,
+                         0.0 if c.device_gate_seed is None else float(c.gate_probability), 0)
         self._check(self._lib.pmp_set_params(self._ctx, C.byref(p)), "pmp_set_params")
 
     def set_config(self, **changes) -> None:

@@ -143,3 +143,35 @@ def replay_gate(n_steps: int, rigid_mask: np.ndarray, exceed_mask: np.ndarray, p
             if forward and (exceed_mask[w, word] & bit) and rand() < probability:
                 return s
     return n_steps
+
+
+def gate_hash(seed: int, e, s, w):
+    """include/pmp_edgecheck.h:pmp_gate_hash -- the counter-based generator of the on-device gate (numpy, vectorised)."""
+    u = np.uint32
+    with np.errstate(over="ignore"):
+        h = u(seed) ^ (np.asarray(e, dtype=np.uint32) * u(0x9E3779B1)) ^ (np.asarray(s, dtype=np.uint32) * u(0x85EBCA77)) \
+            ^ (np.asarray(w, dtype=np.uint32) * u(0xC2B2AE3D))
+        h = h ^ (h >> u(16))
+        h = h * u(0x85EBCA6B)
+        h = h ^ (h >> u(13))
+        h = h * u(0xC2B2AE35)
+        h = h ^ (h >> u(16))
+    return h
+
+
+def device_gate_first_hit(n_steps: np.ndarray, rigid_mask: np.ndarray, exceed_mask: np.ndarray, seed: int,
+                          probability: float = GATE_PROBABILITY, max_steps: Optional[int] = None) -> np.ndarray:
+    """What validate_edges(device_gate_seed=seed) reports as first_hit, recomputed on the host from the raw masks."""
+    E, W, C = rigid_mask.shape
+    cap = C * 32 if max_steps is None else max_steps
+    thr = 0xFFFFFFFF if probability >= 1.0 else int(probability * 4294967296.0)
+    steps = np.arange(C * 32, dtype=np.uint32)
+    bit = lambda m: ((m[..., steps >> 5] >> (steps & 31).astype(np.uint32)) & np.uint32(1)).astype(bool)   # [E, W, S]
+    r, x = bit(rigid_mask.astype(np.uint32)), bit(exceed_mask.astype(np.uint32))
+    h = gate_hash(seed, np.arange(E, dtype=np.uint32)[:, None, None], steps[None, None, :],
+                  np.arange(W, dtype=np.uint32)[None, :, None])
+    viol = (r | (x & (h < np.uint32(thr)))).any(axis=1)                                                   # [E, S]
+    out = np.minimum(n_steps, cap).astype(np.int32)
+    has = viol.any(axis=1)
+    out[has] = np.argmax(viol[has], axis=1)
+    return out

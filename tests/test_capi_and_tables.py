@@ -19,7 +19,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_header_symbols_are_exported():
     with open(os.path.join(ROOT, "include", "pmp_edgecheck.h")) as fp:
         text = fp.read()
-    declared = set(re.findall(r"\b(pmp_[a-z0-9_]+)\s*\(", text))
+    # exported prototypes only (`int pmp_x(` / `const char* pmp_x(`); `static inline` helpers live in the header
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(pmp_[a-z0-9_]+)\s*\(", text, flags=re.M))
     assert declared == set(_capi.EXPORTS), declared ^ set(_capi.EXPORTS)
     if not os.path.exists(_build.LIB_PATH):
         _build.build()

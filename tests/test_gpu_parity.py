@@ -187,6 +187,33 @@ def test_empty_batch_and_bad_shapes(ctx):
         chk.validate_edges(torch.zeros((4, 7)), torch.zeros((5, 7)))
 
 
+def test_device_gate_matches_host_recomputation(ctx):
+    """validate_edges with the on-device 5 % pass-through (counter-based hash) vs the same rule applied on the host to
+    the raw masks; the raw masks themselves must not change."""
+    from plant_motion_planning_b200 import EdgeCheckConfig, EdgeChecker, planner_fns as F
+    from plant_motion_planning_b200.workloads import random_edges
+    torch, model, worlds = ctx["torch"], ctx["model"], ctx["worlds"]
+    q0, q1 = random_edges(model, 2048, seed=17)
+    raw = ctx["chk"].validate_edges(torch.from_numpy(q0), torch.from_numpy(q1), want_masks=True)
+    rm = raw.rigid_mask.cpu().numpy().view(np.uint32)
+    xm = raw.exceed_mask.cpu().numpy().view(np.uint32)
+    n = raw.n_steps.cpu().numpy()
+    for seed, prob in ((5, 0.95), (6, 0.5), (7, 1.0)):
+        chk = EdgeChecker(model, worlds, EdgeCheckConfig(device_gate_seed=seed, gate_probability=prob))
+        g = chk.validate_edges(torch.from_numpy(q0), torch.from_numpy(q1), want_masks=True)
+        assert torch.equal(g.rigid_mask, raw.rigid_mask) and torch.equal(g.exceed_mask, raw.exceed_mask)
+        want = F.device_gate_first_hit(n, rm, xm, seed, prob)
+        got = g.first_hit.cpu().numpy()
+        assert np.array_equal(got, want)
+        if prob < 1.0:
+            assert (got != raw.first_hit.cpu().numpy()).any(), "the gate must let some exceeded steps through"
+        else:
+            assert np.array_equal(got, raw.first_hit.cpu().numpy())
+    # the gate passes ~5 % of the exceeded (edge, step, world) triples
+    h = F.gate_hash(5, np.arange(200000, dtype=np.uint32), 3, 1)
+    assert abs((h < np.uint32(int(0.95 * 2 ** 32))).mean() - 0.95) < 0.005
+
+
 def test_non_finite_inputs_are_rejected_not_crashed(ctx):
     torch, chk = ctx["torch"], ctx["chk"]
     q0 = np.zeros((4, 7), np.float32)
