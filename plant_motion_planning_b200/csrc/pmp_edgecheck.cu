@@ -270,18 +270,24 @@ extern "C" int pmp_validate_edges(pmp_ctx* ctx, const float* q0, const float* q1
     auto smem_for = [&](int blk, bool ws) {
         const int warps = blk / 32;
         return sizeof(PmpRobotTab) + (ws ? world_bytes : 0) + sizeof(int32_t) * ((W + 3) & ~3) +
-               (size_t)warps * PMP_MAX_DOF * (sizeof(double) + 3 * sizeof(float));
+               (size_t)warps * PMP_MAX_DOF * (sizeof(double) + 3 * sizeof(float)) +
+               (size_t)warps * 3 * apad * 33 * sizeof(float);          // swept-bound staging tile per warp
     };
     int wpc = (E + ctx->sm_count - 1) / ctx->sm_count;      // warps (= edges in flight) per CTA
     if (wpc > 16) wpc = 16;
     if (wpc < 1) wpc = 1;
+    // shared memory: robot table + per-warp staging always; world tables when they fit next to them.  A CTA of fewer
+    // than 4 warps would spend longer staging the tables than using them.  If even the per-warp staging of `wpc`
+    // warps does not fit (32-sphere arms: 12.7 KB of swept-bound tile per warp), use fewer warps.
+    const size_t lim = (size_t)ctx->max_smem_optin;
+    while (wpc > 1 && smem_for(32 * wpc, false) > lim) wpc >>= 1;
     int block = 32 * wpc, per_sm = 1;
-    // a CTA of fewer than 4 warps would spend longer staging the tables than using them
-    bool wsmem = wpc >= 4 && smem_for(block, true) <= (size_t)ctx->max_smem_optin;
+    bool wsmem = wpc >= 4 && smem_for(block, true) <= lim;
     // tuning knobs (profiling only): PMP_EDGE_BLOCK = threads per CTA, PMP_EDGE_PER_SM = resident CTAs per SM
     if (const char* eb = getenv("PMP_EDGE_BLOCK")) { int v = atoi(eb); if (v >= 32 && v <= PMP_EDGE_MAXT && v % 32 == 0) block = v; }
     if (const char* ep = getenv("PMP_EDGE_PER_SM")) { int v = atoi(ep); if (v >= 1 && v <= 16) per_sm = v; }
-    if (smem_for(block, wsmem) > (size_t)ctx->max_smem_optin) wsmem = false;
+    if (smem_for(block, wsmem) > lim) wsmem = false;
+    if (smem_for(block, false) > lim) return fail(ctx, PMP_E_INVALID, "shared memory budget exceeded for this block size");
     const size_t smem = smem_for(block, wsmem);
     const int warps = block / 32;
     int grid = (E + warps - 1) / warps;

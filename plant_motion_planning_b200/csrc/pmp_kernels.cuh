@@ -44,6 +44,11 @@ __device__ __forceinline__ void pmp_mat_mul(const float* __restrict__ X, const f
 __device__ __forceinline__ float pmp_clamp(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 // One MUFU.RSQ: the argument is clamped to >= 1e-24 by the caller, so the denormal pre/post-scaling that rsqrtf()
 // emits without -ftz (FSETP + FMUL + FSEL + FMUL per call) is dead weight in the innermost loop.
+__device__ __forceinline__ float pmp_rcp_ftz(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float pmp_rsqrt_ftz(float x) {
     float y;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -162,12 +167,20 @@ struct PmpUnitOut {
     float over;
 };
 
-template <int A, int NSLOT, bool DETAIL>
+// Swept bound of one arm sphere over a group of lanes (= consecutive interpolation steps of the warp's edge): a ball
+// that contains the sphere at every step of the group.  Each lane carries ONE such ball (lane -> (group, sphere)), so
+// that "can anything touch this stem at rest?" costs one sphere-capsule test per lane instead of A per lane.
+struct PmpSweptBound {
+    float x, y, z, r;    // r < 0: this lane carries no bound
+};
+
+template <int A, int NSLOT, bool DETAIL, bool CULL>
 __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ wt, int n_stems,
                                                       const float* __restrict__ boxes, int n_boxes,
                                                       const PmpRobotTab& rt, const PmpKernelParams& prm,
                                                       const float (&c)[A][3], float* __restrict__ defl_out,
-                                                      float* __restrict__ theta_out) {
+                                                      float* __restrict__ theta_out,
+                                                      const PmpSweptBound bound = PmpSweptBound{0.f, 0.f, 0.f, -1.f}) {
     PmpUnitOut out;
     out.plant_hit = false; out.exceeded = false; out.max_defl = 0.f; out.over = 0.f;
     float FR[NSLOT][9], FT[NSLOT][3];
@@ -194,12 +207,14 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
         for (int i = 0; i < 9; ++i) Rv[i] = rec[PMP_S_RW0 + i];
         tv[0] = rec[PMP_S_TW0]; tv[1] = rec[PMP_S_TW0 + 1]; tv[2] = rec[PMP_S_TW0 + 2];
         bool moved = false;
+        bool chain_at_rest = true;     // warp-uniform: no lane has a deflected ancestor, so Rv/tv are the table values
         if (pslot >= 0) {
             moved = FM[0];
 #pragma unroll
             for (int k = 1; k < NSLOT; ++k)
                 if (pslot == k) moved = FM[k];   // warp-uniform
-            if (dense || __any_sync(PMP_FULL, moved)) {
+            chain_at_rest = !__any_sync(PMP_FULL, moved);
+            if (dense || !chain_at_rest) {
                 float Rp[9], tp[3];
 #pragma unroll
                 for (int i = 0; i < 9; ++i) Rp[i] = FR[0][i];
@@ -226,6 +241,27 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
             }
         }
         const float z0 = rec[PMP_S_Z0], z1 = rec[PMP_S_Z1], rad = rec[PMP_S_RAD], lim = rec[PMP_S_LIM];
+        // ---- phase 0: can ANY step of this warp touch the stem at rest?  One swept-bound test per lane. ----
+        bool maybe = true;
+        if (CULL && !dense && chain_at_rest) {
+            const float ux = Rv[2], uy = Rv[5], uz = Rv[8];
+            const float wx = bound.x - tv[0], wy = bound.y - tv[1], wz = bound.z - tv[2];
+            const float tau = pmp_clamp(fmaf(wx, ux, fmaf(wy, uy, wz * uz)), z0, z1);
+            const float dx = fmaf(-tau, ux, wx), dy = fmaf(-tau, uy, wy), dz = fmaf(-tau, uz, wz);
+            const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+            const float rr = bound.r + rad;
+            maybe = __any_sync(PMP_FULL, bound.r >= 0.f && d2 < rr * rr);
+        }
+        if (CULL && !maybe && prm.deflection_limit >= 0.f) {
+            // nothing can touch this stem at any step of the warp: it stays at rest with zero deflection.  Only the
+            // chain-rule state and the "moved" bit of its frame slot need updating (children of an unmoved stem take
+            // their frames from the table, and the observer rebuilds an unmoved parent's rotation from the record).
+            if (flags & (PMP_SF_PLANT_START | PMP_SF_IS_MAIN)) last = 0.f;
+#pragma unroll
+            for (int k = 0; k < NSLOT; ++k)
+                if (oslot == k) FM[k] = false;
+            continue;
+        }
         // ---- phase 1: does any arm sphere touch the stem in its initial pose?  (exact, no rsqrt / Jacobian) ----
         bool touch = false;
         {
@@ -283,7 +319,7 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
                 // det(H + lam I) = lam^2 + lam tr(H) + det(H) >= lam (lam + tr H): the bound keeps float32 cancellation in
                 // a11 a22 - Hxy^2 (H is rank one for a single contact) from flipping or inflating the step
                 const float det = fmaxf(fmaf(a11, a22, -Hxy * Hxy), lam * (lam + Hxx + Hyy));
-                const float idet = act ? __frcp_rn(det) : 0.f;
+                const float idet = act ? pmp_rcp_ftz(det) : 0.f;      // det >= lam^2 > 0 whenever act
                 float dtx = (a22 * gx - Hxy * gy) * idet;
                 float dty = (a11 * gy - Hxy * gx) * idet;
                 dtx = pmp_clamp(dtx, -prm.max_step, prm.max_step);
@@ -334,15 +370,30 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
                 if (flags & PMP_SF_OBS_ROOT) {
                     pmp_mat_vec(Rs, ox, oy, oz, vx, vy, vz);
                 } else {
-                    float Rp[9];
+                    // parent rotation: from its frame slot if the parent moved, else its rest value rebuilt from this
+                    // stem's record, R_p0 = Rw0 Ro^T (an unmoved parent may have skipped the slot store altogether)
+                    float Rp[9], Rw0[9], RoT[9], Rp0[9];
+                    bool pm = FM[0];
 #pragma unroll
                     for (int i = 0; i < 9; ++i) Rp[i] = FR[0][i];
 #pragma unroll
                     for (int k = 1; k < NSLOT; ++k) {
                         if (pslot == k) {
+                            pm = FM[k];
 #pragma unroll
                             for (int i = 0; i < 9; ++i) Rp[i] = FR[k][i];
                         }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) Rw0[i] = rec[PMP_S_RW0 + i];
+#pragma unroll
+                    for (int r_ = 0; r_ < 3; ++r_)
+#pragma unroll
+                        for (int c_ = 0; c_ < 3; ++c_) RoT[3 * r_ + c_] = rec[PMP_S_RO + 3 * c_ + r_];
+                    pmp_mat_mul(Rw0, RoT, Rp0);
+                    if (!pm) {
+#pragma unroll
+                        for (int i = 0; i < 9; ++i) Rp[i] = Rp0[i];
                     }
                     float lx, ly, lz;
                     pmp_matT_vec(Rs, ox, oy, oz, lx, ly, lz);
@@ -452,6 +503,7 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* sm_sq_all = reinterpret_cast<double*>(sm_nstems + nstem_words);
     float* sm_q_all = reinterpret_cast<float*>(sm_sq_all + warps * PMP_MAX_DOF);
+    float* sm_tile = sm_q_all + warps * (3 * PMP_MAX_DOF) + wid * (3 * A * 33);   // swept-bound staging, per warp
     double* sm_sq = sm_sq_all + wid * PMP_MAX_DOF;
     float* sm_q0 = sm_q_all + wid * (3 * PMP_MAX_DOF);
     float* sm_q1 = sm_q0 + PMP_MAX_DOF;
@@ -520,6 +572,40 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
 #pragma unroll
                 for (int a = 0; a < A; ++a) { c[a][0] = PMP_FAR; c[a][1] = PMP_FAR; c[a][2] = PMP_FAR; }
             }
+            // swept bounds: G = 32 / L lane groups, lane g*L + a carries the ball around sphere a over the steps of
+            // group g.  The per-lane centres go through a per-warp shared-memory tile ([3A][33], padded: conflict-free)
+            // so that this once-per-chunk step costs no registers in the world loop below.
+            PmpSweptBound bound{0.f, 0.f, 0.f, -1.f};
+            {
+                constexpr int L = (A <= 16) ? 16 : 32;           // lanes per group (>= A)
+                __syncwarp();
+#pragma unroll
+                for (int a = 0; a < A; ++a) {
+                    sm_tile[(3 * a + 0) * 33 + lane] = c[a][0];
+                    sm_tile[(3 * a + 1) * 33 + lane] = c[a][1];
+                    sm_tile[(3 * a + 2) * 33 + lane] = c[a][2];
+                }
+                __syncwarp();
+                const int la = lane & (L - 1), g0 = lane & ~(L - 1);
+                const int n_live = nc - base;                      // live lanes are the prefix [0, n_live)
+                if (la < rt.n_spheres && g0 < n_live) {
+                    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+                    const int jn = min(L, n_live - g0);
+                    for (int j = 0; j < jn; ++j) {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const float v = sm_tile[(3 * la + k) * 33 + g0 + j];
+                            lo[k] = fminf(lo[k], v); hi[k] = fmaxf(hi[k], v);
+                        }
+                    }
+                    const float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+                    bound.x = 0.5f * (lo[0] + hi[0]); bound.y = 0.5f * (lo[1] + hi[1]); bound.z = 0.5f * (lo[2] + hi[2]);
+                    // half diagonal of the box + sphere radius, rounded up (1e-5 m + 1e-6 relative slack keeps the cull
+                    // conservative against float32 rounding in this bound and in the capsule test)
+                    bound.r = fmaf(0.5f * 1.000001f, sqrtf(fmaf(ex, ex, fmaf(ey, ey, ez * ez))), rt.sph_radius[la] + 1e-5f);
+                }
+                __syncwarp();
+            }
             // end-effector path length (kuka_primitives.py:504-508)
             {
                 float px = __shfl_up_sync(PMP_FULL, ee[0], 1), py = __shfl_up_sync(PMP_FULL, ee[1], 1),
@@ -541,10 +627,10 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
                 PmpUnitOut u;
                 u.plant_hit = false; u.exceeded = false; u.max_defl = 0.f; u.over = 0.f;
                 if (prm.mode != PMP_MODE_IGNORE_ALL) {
-                    u = pmp_world_eval<A, NSLOT, false>(
+                    u = pmp_world_eval<A, NSLOT, false, true>(
                         stems_base + (size_t)w * prm.max_stems * PMP_STEM_STRIDE, sm_nstems[w],
                         args.boxes + (size_t)w * prm.max_boxes * PMP_BOX_STRIDE,
-                        prm.mode == PMP_MODE_AVOID_ALL ? args.n_boxes[w] : 0, rt, prm, c, nullptr, nullptr);
+                        prm.mode == PMP_MODE_AVOID_ALL ? args.n_boxes[w] : 0, rt, prm, c, nullptr, nullptr, bound);
                 }
                 const uint32_t rm = rigid0_mask | __ballot_sync(PMP_FULL, live && u.plant_hit);
                 const uint32_t xm = __ballot_sync(PMP_FULL, live && u.exceeded);
@@ -642,7 +728,7 @@ __global__ void __launch_bounds__(128, 2) pmp_config_kernel(const PmpConfigArgs 
         float* tptr = (live && args.theta) ? args.theta + bw * P * 2 : nullptr;
         const int ns = args.n_stems[w];
         if (prm.mode != PMP_MODE_IGNORE_ALL) {
-            u = pmp_world_eval<A, NSLOT, true>(args.stems + (size_t)w * P * PMP_STEM_STRIDE, ns,
+            u = pmp_world_eval<A, NSLOT, true, false>(args.stems + (size_t)w * P * PMP_STEM_STRIDE, ns,
                                                args.boxes + (size_t)w * prm.max_boxes * PMP_BOX_STRIDE,
                                                prm.mode == PMP_MODE_AVOID_ALL ? args.n_boxes[w] : 0, rt, prm, c, dptr, tptr);
         } else {
