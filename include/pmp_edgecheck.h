@@ -197,6 +197,50 @@ int pmp_get_launch_info(pmp_ctx* ctx, pmp_launch_info* out);
  * measured roofline denominator: returns achieved TFLOP/s in *tflops and the kernel time in *ms. */
 int pmp_measure_fp32_peak(pmp_ctx* ctx, int32_t repeats, double* tflops, double* ms);
 
+/* ---- batched tree extension: the caller of the edge path (motion_planners/motion_planners/primitives.py:196-255,
+ * rrt_connect_with_angle_constraints_v2.py:240-290), many proposals per launch ------------------------------- */
+
+/* Nearest tree node of each target: argmin over nodes of distance_fn(node, target) (weights 1, 2-norm of
+ * difference_fn, continuous joints wrapped), first minimum wins -- motion_planners/motion_planners/utils.py:47-53
+ * as called from primitives.py:207; pybullet_tools/utils.py:3604-3627.
+ *   nodes_dev [T*D], targets_dev [B*D]; size_dev (NULL ok): device int holding the live node count (<= T)
+ *   index_dev [B]; dist_dev [B] float64 distance (NULL ok); q_from_dev [B*D] the chosen nodes (NULL ok)
+ * float64 arithmetic on the float32 data in joint order: indices are bit-identical to the oracle. A target with a
+ * NaN coordinate gets node 0. */
+int pmp_nearest(pmp_ctx* ctx, const float* nodes_dev, int32_t T, const int32_t* size_dev, const float* targets_dev,
+                int32_t B, int32_t* index_dev, double* dist_dev, float* q_from_dev, void* stream);
+
+/* Configuration number step_dev[e] of edge e (0-based, the numbering of pmp_validate_edges), out_dev [E*D].
+ * The arithmetic is the edge kernel's, so these are exactly the configurations that were validated
+ * (get_refine_fn / get_extend_fn, pybullet_tools/utils.py:3641-3676). */
+int pmp_edge_points(pmp_ctx* ctx, const float* q0_dev, const float* q1_dev, int32_t E, const int32_t* step_dev,
+                    int32_t backward, float* out_dev, void* stream);
+
+/* A search tree in caller-owned device memory. Node i lies on the edge parent[i] -> via[i] (its step via_steps[i]-1,
+ * all earlier steps of that edge validated). */
+typedef struct pmp_tree {
+    float* nodes;        /* [capacity*D] */
+    int32_t* parent;     /* [capacity], -1 for the root */
+    float* via;          /* [capacity*D] */
+    int32_t* via_steps;  /* [capacity] */
+    int32_t* size;       /* [1] live node count */
+    int32_t capacity;
+    int32_t reserved;
+} pmp_tree;
+
+/* One batched extension: for each target, the nearest node is extended towards it with the full multi-world check
+ * (forward sequence, q_near excluded, target included) and the last safe configuration -- if any step was safe --
+ * is appended to the tree in batch order.  Three kernels on `stream`, no host synchronisation.
+ *   size_bound     host upper bound of *tree->size (for grid sizing), 1 <= size_bound <= capacity
+ *   new_index_dev  [B] slot of the appended node, -1 if none
+ *   reached_dev    [B] 1 if the target itself was reached (first_hit >= n_steps)
+ *   new_cfg_dev    [B*D] appended configuration, NaN where none (NULL ok) -- the targets of the connect step
+ *   stats_dev      [4] nodes appended, targets reached, first reached batch index (B if none), capacity overflow
+ * Replaces extend_towards_with_angle_constraint_multi_world (primitives.py:196-255) for B proposals at once. */
+int pmp_tree_extend(pmp_ctx* ctx, const pmp_tree* tree, int32_t size_bound, const float* targets_dev, int32_t B,
+                    int32_t max_steps, int32_t* new_index_dev, int32_t* reached_dev, float* new_cfg_dev,
+                    int32_t* stats_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

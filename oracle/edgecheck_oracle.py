@@ -546,3 +546,74 @@ def validate_edge(model: RobotModel, worlds: Sequence[PlantWorld], q1, q2, prm: 
     mx = np.max(res.deflection, axis=(0, 2))
     return EdgeResult(n, first, res.rigid, res.exceeded, mx, over, ee_len,
                       ee_len + prm.alpha * float(np.mean(over)))
+
+
+# ----------------------------------------------------------------------------- batched tree extension
+def nearest(model: RobotModel, nodes: np.ndarray, targets: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """argmin over tree nodes of distance_fn(node, target), first minimum wins
+    (motion_planners/motion_planners/utils.py:47-53 called from primitives.py:207; metric
+    pybullet_tools/utils.py:3604-3627).  Returns (index [B], distance [B]).  The per-joint terms are summed in
+    joint order (the CUDA kernel reproduces the float64 arithmetic bit for bit).  A NaN distance is never selected;
+    if every distance is NaN the answer is node 0."""
+    nodes = np.asarray(nodes, dtype=np.float64)
+    targets = np.asarray(targets, dtype=np.float64)
+    idx = np.zeros(targets.shape[0], dtype=np.int32)
+    dist = np.full(targets.shape[0], np.inf)
+    circ = np.asarray(model.circular, dtype=bool)
+    for b in range(targets.shape[0]):
+        d = targets[b][None, :] - nodes
+        if circ.any():
+            d = np.where(circ[None, :], wrap_pi(d), d)
+        s = np.zeros(nodes.shape[0])
+        for j in range(nodes.shape[1]):
+            s = s + d[:, j] * d[:, j]
+        r = np.sqrt(s)
+        r = np.where(np.isnan(r), np.inf, r)
+        k = int(np.argmin(r))
+        if np.isfinite(r[k]):
+            idx[b], dist[b] = k, r[k]
+    return idx, dist
+
+
+def edge_point(model: RobotModel, q1, q2, resolution: float, step: int, backward: bool = False) -> np.ndarray:
+    """Configuration number `step` of the edge (0-based): edge_configs(...)[step] without building the sequence."""
+    n = num_steps(model, q1, q2, resolution)
+    d = difference(model, q2, q1)
+    num = step + (0 if backward else 1)
+    return np.asarray(q1, dtype=np.float64) + d * (num / n)
+
+
+def tree_append(model: RobotModel, tree: dict, from_index: np.ndarray, targets: np.ndarray, first_hit: np.ndarray,
+                n_steps: np.ndarray, resolution: float, max_steps: int) -> dict:
+    """The bookkeeping of one batched extension given the per-edge results (first_hit, n_steps) of the edges
+    tree.nodes[from_index[e]] -> targets[e]: every extension with at least one safe step appends its last safe
+    configuration, in batch order (the batched form of primitives.py:243-254: `safe = steps[:first_hit]`, last
+    node parented on the nearest node).  ``tree``: dict(nodes [n, D], parent [n], via [n, D], via_steps [n]) plus
+    'capacity'; returns the outputs of pmp_tree_extend and mutates ``tree``."""
+    B = targets.shape[0]
+    new_index = np.full(B, -1, dtype=np.int32)
+    reached = np.zeros(B, dtype=np.int32)
+    new_cfg = np.full(targets.shape, np.nan, dtype=np.float64)
+    appended = overflow = 0
+    for e in range(B):
+        if first_hit[e] < 1:
+            continue
+        slot = tree["nodes"].shape[0]
+        if slot >= tree["capacity"]:
+            overflow = 1
+            continue
+        q0 = tree["nodes"][from_index[e]]
+        cfg = edge_point(model, q0, targets[e], resolution, int(first_hit[e]) - 1)
+        if n_steps[e] <= max_steps and first_hit[e] >= n_steps[e]:
+            reached[e] = 1
+            cfg = np.where(model.circular, cfg, np.asarray(targets[e], dtype=np.float64))
+        tree["nodes"] = np.concatenate([tree["nodes"], cfg[None]], axis=0)
+        tree["parent"] = np.append(tree["parent"], np.int32(from_index[e]))
+        tree["via"] = np.concatenate([tree["via"], np.asarray(targets[e], dtype=np.float64)[None]], axis=0)
+        tree["via_steps"] = np.append(tree["via_steps"], np.int32(first_hit[e]))
+        new_index[e] = slot
+        new_cfg[e] = cfg
+        appended += 1
+    hits = np.nonzero(reached)[0]
+    stats = np.array([appended, len(hits), hits[0] if len(hits) else B, overflow], dtype=np.int32)
+    return {"new_index": new_index, "reached": reached, "new_config": new_cfg, "stats": stats}

@@ -60,7 +60,14 @@ EXPORTS = [
     "pmp_create", "pmp_destroy", "pmp_last_error", "pmp_set_robot", "pmp_set_worlds", "pmp_set_params",
     "pmp_num_worlds", "pmp_max_stems", "pmp_fk", "pmp_check_configs", "pmp_validate_edges",
     "pmp_validate_edges_host", "pmp_check_configs_host", "pmp_get_launch_info", "pmp_measure_fp32_peak",
+    "pmp_nearest", "pmp_edge_points", "pmp_tree_extend",
 ]
+
+
+class Tree(C.Structure):
+    """pmp_tree: caller-owned device buffers of one search tree."""
+    _fields_ = [("nodes", C.c_void_p), ("parent", C.c_void_p), ("via", C.c_void_p), ("via_steps", C.c_void_p),
+                ("size", C.c_void_p), ("capacity", C.c_int32), ("reserved", C.c_int32)]
 
 _lib: Optional[C.CDLL] = None
 
@@ -98,6 +105,9 @@ def load() -> C.CDLL:
     lib.pmp_check_configs_host.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp]
     lib.pmp_get_launch_info.argtypes = [vp, C.POINTER(LaunchInfo)]
     lib.pmp_measure_fp32_peak.argtypes = [vp, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.pmp_nearest.argtypes = [vp, vp, C.c_int32, vp, vp, C.c_int32, vp, vp, vp, vp]
+    lib.pmp_edge_points.argtypes = [vp, vp, vp, C.c_int32, vp, C.c_int32, vp, vp]
+    lib.pmp_tree_extend.argtypes = [vp, C.POINTER(Tree), C.c_int32, vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         if name != "pmp_last_error":
             getattr(lib, name).restype = C.c_int

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "pmp_launch.h"
+#include "pmp_tree.cuh"
 
 struct pmp_ctx {
     int device = 0;
@@ -35,6 +36,9 @@ struct pmp_ctx {
     // pinned staging for small host calls (the per-step collision_fn adapter): one H2D, one kernel, one D2H
     void* h_stage = nullptr;
     size_t stage_bytes = 0;
+    // scratch of the tree entry points (nearest-node partials, gathered nodes, per-extension edge results)
+    void* d_tree_scratch = nullptr;
+    size_t tree_scratch_bytes = 0;
 };
 
 static std::string g_create_err;
@@ -91,7 +95,7 @@ extern "C" int pmp_destroy(pmp_ctx* ctx) {
     if (!ctx) return PMP_OK;
     cudaSetDevice(ctx->device);
     free_worlds(ctx);
-    cudaFree(ctx->d_robot); cudaFree(ctx->d_links); cudaFree(ctx->d_scratch);
+    cudaFree(ctx->d_robot); cudaFree(ctx->d_links); cudaFree(ctx->d_scratch); cudaFree(ctx->d_tree_scratch);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -496,5 +500,128 @@ extern "C" int pmp_measure_fp32_peak(pmp_ctx* ctx, int32_t repeats, double* tflo
     const double flops = 2.0 * 8.0 * 16.0 * (double)iters * (double)grid * block;
     *ms = best;
     *tflops = flops / (best * 1e-3) / 1e12;
+    return PMP_OK;
+}
+
+// ---- batched tree extension -------------------------------------------------------
+static int ensure_tree_scratch(pmp_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->tree_scratch_bytes) return PMP_OK;
+    cudaFree(ctx->d_tree_scratch);
+    ctx->d_tree_scratch = nullptr; ctx->tree_scratch_bytes = 0;
+    size_t want = bytes + bytes / 2;
+    CK(cudaMalloc(&ctx->d_tree_scratch, want));
+    ctx->tree_scratch_bytes = want;
+    return PMP_OK;
+}
+
+static int nearest_tile(pmp_ctx* ctx) { return ctx->h_robot.dof <= 8 ? 8 : 4; }
+
+static int nearest_splits(pmp_ctx* ctx, int T, int B) {
+    const int tgt = nearest_tile(ctx);
+    const int tiles = (B + tgt - 1) / tgt;
+    int splits = (2 * ctx->sm_count + tiles - 1) / tiles;            // about two CTAs per SM
+    const int max_splits = (T + 4 * PMP_NN_BLOCK - 1) / (4 * PMP_NN_BLOCK);   // at least 4 nodes per thread
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    return splits;
+}
+
+// launches the two nearest-node kernels; part_* must hold B * splits entries
+static int launch_nearest(pmp_ctx* ctx, const float* nodes, int T, const int32_t* size_dev, const float* targets, int B,
+                          int splits, double* part_r, int32_t* part_i, int32_t* index, double* dist, float* q_from,
+                          cudaStream_t st) {
+    PmpNearestArgs a;
+    a.nodes = nodes; a.size_dev = size_dev; a.T = T; a.targets = targets; a.B = B; a.D = ctx->h_robot.dof;
+    a.circular_mask = ctx->h_robot.circular_mask; a.splits = splits; a.part_r = part_r; a.part_i = part_i;
+    a.index = index; a.dist = dist; a.q_from = q_from;
+    const int tgt = nearest_tile(ctx);
+    const dim3 grid((B + tgt - 1) / tgt, splits, 1);
+    if (a.D <= 8) pmp_nearest_kernel<8, 8><<<grid, PMP_NN_BLOCK, 0, st>>>(a);
+    else pmp_nearest_kernel<16, 4><<<grid, PMP_NN_BLOCK, 0, st>>>(a);
+    pmp_nearest_finish_kernel<<<(B + 127) / 128, 128, 0, st>>>(a);
+    CK(cudaGetLastError());
+    ctx->info.kernel_launches += 2;
+    return PMP_OK;
+}
+
+extern "C" int pmp_nearest(pmp_ctx* ctx, const float* nodes_dev, int32_t T, const int32_t* size_dev,
+                           const float* targets_dev, int32_t B, int32_t* index_dev, double* dist_dev,
+                           float* q_from_dev, void* stream) {
+    if (!ctx) return PMP_E_INVALID;
+    if (!ctx->has_robot) return fail(ctx, PMP_E_STATE, "robot must be set first");
+    if (T < 1 || B < 0) return fail(ctx, PMP_E_INVALID, "bad T / B");
+    if (B == 0) return PMP_OK;
+    if (!nodes_dev || !targets_dev || !index_dev) return fail(ctx, PMP_E_INVALID, "nodes, targets and index are required");
+    CK(cudaSetDevice(ctx->device));
+    const int splits = nearest_splits(ctx, T, B);
+    const size_t br = up256(sizeof(double) * (size_t)B * splits), bi = up256(sizeof(int32_t) * (size_t)B * splits);
+    int rc = ensure_tree_scratch(ctx, br + bi);
+    if (rc) return rc;
+    char* p = (char*)ctx->d_tree_scratch;
+    return launch_nearest(ctx, nodes_dev, T, size_dev, targets_dev, B, splits, (double*)p, (int32_t*)(p + br), index_dev,
+                          dist_dev, q_from_dev, (cudaStream_t)stream);
+}
+
+extern "C" int pmp_edge_points(pmp_ctx* ctx, const float* q0_dev, const float* q1_dev, int32_t E,
+                               const int32_t* step_dev, int32_t backward, float* out_dev, void* stream) {
+    if (!ctx) return PMP_E_INVALID;
+    if (!ctx->has_robot || !ctx->has_params) return fail(ctx, PMP_E_STATE, "robot and params must be set first");
+    if (E < 0) return fail(ctx, PMP_E_INVALID, "bad E");
+    if (E == 0) return PMP_OK;
+    if (!q0_dev || !q1_dev || !step_dev || !out_dev) return fail(ctx, PMP_E_INVALID, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    pmp_edge_points_kernel<<<(E + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        q0_dev, q1_dev, E, ctx->h_robot.dof, ctx->h_robot.circular_mask, ctx->prm.resolution, step_dev, backward ? 1 : 0,
+        out_dev);
+    CK(cudaGetLastError());
+    ctx->info.kernel_launches++;
+    return PMP_OK;
+}
+
+extern "C" int pmp_tree_extend(pmp_ctx* ctx, const pmp_tree* tree, int32_t size_bound, const float* targets_dev,
+                               int32_t B, int32_t max_steps, int32_t* new_index_dev, int32_t* reached_dev,
+                               float* new_cfg_dev, int32_t* stats_dev, void* stream) {
+    int rc = ready(ctx);
+    if (rc) return rc;
+    if (!tree || !tree->nodes || !tree->parent || !tree->via || !tree->via_steps || !tree->size)
+        return fail(ctx, PMP_E_INVALID, "incomplete pmp_tree");
+    if (B < 0 || max_steps < 1 || size_bound < 1 || size_bound > tree->capacity)
+        return fail(ctx, PMP_E_INVALID, "bad B / max_steps / size_bound");
+    if (B == 0) return PMP_OK;
+    if (!targets_dev || !new_index_dev || !reached_dev || !stats_dev)
+        return fail(ctx, PMP_E_INVALID, "targets, new_index, reached and stats are required");
+    CK(cudaSetDevice(ctx->device));
+    const int D = ctx->h_robot.dof;
+    const int splits = nearest_splits(ctx, size_bound, B);
+    const size_t br = up256(sizeof(double) * (size_t)B * splits), bp = up256(sizeof(int32_t) * (size_t)B * splits),
+                 bi = up256(sizeof(int32_t) * (size_t)B), bq = up256(sizeof(float) * (size_t)B * D);
+    rc = ensure_tree_scratch(ctx, br + bp + 3 * bi + bq);
+    if (rc) return rc;
+    char* p = (char*)ctx->d_tree_scratch;
+    auto take = [&](size_t b) { char* r = p; p += b; return r; };
+    double* part_r = (double*)take(br);
+    int32_t* part_i = (int32_t*)take(bp);
+    int32_t* from_index = (int32_t*)take(bi);
+    int32_t* first_hit = (int32_t*)take(bi);
+    int32_t* n_steps = (int32_t*)take(bi);
+    float* q_from = (float*)take(bq);
+    cudaStream_t st = (cudaStream_t)stream;
+    // 1. nearest node of every target (+ gather), 2. the edge kernel on (nearest node -> target),
+    // 3. append the last safe configuration of every extension that made progress
+    rc = launch_nearest(ctx, tree->nodes, size_bound, tree->size, targets_dev, B, splits, part_r, part_i, from_index,
+                        nullptr, q_from, st);
+    if (rc) return rc;
+    rc = pmp_validate_edges(ctx, q_from, targets_dev, B, max_steps, 0, first_hit, n_steps, nullptr, nullptr, nullptr,
+                            nullptr, nullptr, nullptr, stream);
+    if (rc) return rc;
+    PmpTreeAppendArgs a;
+    a.nodes = tree->nodes; a.parent = tree->parent; a.via = tree->via; a.via_steps = tree->via_steps; a.size = tree->size;
+    a.capacity = tree->capacity; a.q_from = q_from; a.targets = targets_dev; a.from_index = from_index;
+    a.first_hit = first_hit; a.n_steps = n_steps; a.B = B; a.D = D; a.max_steps = max_steps;
+    a.circular_mask = ctx->h_robot.circular_mask; a.resolution = ctx->prm.resolution; a.new_index = new_index_dev;
+    a.reached = reached_dev; a.new_cfg = new_cfg_dev; a.stats = stats_dev;
+    pmp_tree_append_kernel<<<1, B >= 1024 ? 1024 : ((B + 31) / 32) * 32, 0, st>>>(a);
+    CK(cudaGetLastError());
+    ctx->info.kernel_launches++;
     return PMP_OK;
 }

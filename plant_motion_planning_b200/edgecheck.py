@@ -261,6 +261,59 @@ class EdgeChecker:
                 "pmp_validate_edges")
         return out
 
+    # ------------------------------------------------------------------ batched tree extension (device)
+    def nearest(self, nodes, targets, size=None, want_nodes: bool = False):
+        """Nearest tree node of each target (pmp_nearest): (index int32 [B], distance float64 [B][, q_near [B, D]]).
+        ``nodes`` [T, D] / ``targets`` [B, D] torch CUDA tensors; ``size``: optional device int32 [1] live count."""
+        torch = self._torch()
+        nodes = self._prep(nodes, "nodes")
+        targets = self._prep(targets, "targets")
+        T, B = nodes.shape[0], targets.shape[0]
+        with torch.cuda.device(self._dev()):
+            index = torch.empty((B,), device=nodes.device, dtype=torch.int32)
+            dist = torch.empty((B,), device=nodes.device, dtype=torch.float64)
+            q_near = torch.empty((B, self.dof), device=nodes.device, dtype=torch.float32) if want_nodes else None
+            self._check(self._lib.pmp_nearest(self._ctx, self._p(nodes), T, self._p(size), self._p(targets), B,
+                                              self._p(index), self._p(dist), self._p(q_near), self._stream()),
+                        "pmp_nearest")
+        return (index, dist, q_near) if want_nodes else (index, dist)
+
+    def edge_points(self, q_from, q_to, steps, backward: bool = False):
+        """Configuration number steps[e] of every edge, with the arithmetic of the edge kernel (pmp_edge_points)."""
+        torch = self._torch()
+        q0 = self._prep(q_from, "q_from")
+        q1 = self._prep(q_to, "q_to")
+        st = torch.as_tensor(steps).to(device=q0.device, dtype=torch.int32).contiguous()
+        if q0.shape != q1.shape or st.shape != (q0.shape[0],):
+            raise ValueError("q_from, q_to [E, D] and steps [E] must agree")
+        with torch.cuda.device(self._dev()):
+            out = torch.empty_like(q0)
+            self._check(self._lib.pmp_edge_points(self._ctx, self._p(q0), self._p(q1), q0.shape[0], self._p(st),
+                                                  1 if backward else 0, self._p(out), self._stream()),
+                        "pmp_edge_points")
+        return out
+
+    def new_tree(self, root, capacity: int = 1 << 16) -> "DeviceTree":
+        return DeviceTree(self, root, capacity)
+
+    def tree_extend(self, tree: "DeviceTree", targets, max_steps: Optional[int] = None) -> "TreeExtension":
+        """One batched extension of ``tree`` towards ``targets`` [B, D] (pmp_tree_extend): nearest node, multi-world
+        edge check, append of the last safe configuration -- three kernels, no host synchronisation."""
+        torch = self._torch()
+        targets = self._prep(targets, "targets")
+        B = targets.shape[0]
+        ms = int(max_steps or self.config.max_steps)
+        with torch.cuda.device(self._dev()):
+            mk = lambda shape, dt: torch.empty(shape, device=targets.device, dtype=dt)
+            ext = TreeExtension(mk((B,), torch.int32), mk((B,), torch.int32), mk((B, self.dof), torch.float32),
+                                mk((4,), torch.int32), targets)
+            self._check(self._lib.pmp_tree_extend(
+                self._ctx, C.byref(tree._desc), min(tree.size_bound, tree.capacity), self._p(targets), B, ms,
+                self._p(ext.new_index), self._p(ext.reached), self._p(ext.new_config), self._p(ext.stats),
+                self._stream()), "pmp_tree_extend")
+        tree.size_bound = min(tree.size_bound + B, tree.capacity)
+        return ext
+
     # ------------------------------------------------------------------ host API (numpy; the C-ABI *_host calls)
     def validate_edges_host(self, q_from: np.ndarray, q_to: np.ndarray, backward: bool = False,
                             want_masks: bool = False, max_steps: Optional[int] = None, out: Optional[dict] = None) -> dict:
@@ -298,3 +351,42 @@ class EdgeChecker:
         self._check(self._lib.pmp_check_configs_host(self._ctx, vp(q), B, vp(out["flags"]), vp(out.get("deflection")),
                                                      vp(out.get("theta")), vp(out["ee"])), "pmp_check_configs_host")
         return out
+
+
+@dataclass
+class TreeExtension:
+    """Device outputs of one pmp_tree_extend call."""
+    new_index: object      # int32 [B] slot of the appended node, -1 if the extension made no progress
+    reached: object        # int32 [B] 1 if the target itself was reached
+    new_config: object     # float32 [B, D] appended configuration, NaN where none
+    stats: object          # int32 [4] appended, reached, first reached batch index (B if none), capacity overflow
+    targets: object        # float32 [B, D] the targets of the call
+
+
+class DeviceTree:
+    """A search tree resident in HBM (pmp_tree): configurations, parent links and, per node, the edge it lies on."""
+
+    def __init__(self, checker: EdgeChecker, root, capacity: int):
+        import torch
+        self.checker = checker
+        self.capacity = int(capacity)
+        dev = checker._dev()
+        D = checker.dof
+        self.nodes = torch.zeros((self.capacity, D), device=dev, dtype=torch.float32)
+        self.parent = torch.full((self.capacity,), -1, device=dev, dtype=torch.int32)
+        self.via = torch.zeros((self.capacity, D), device=dev, dtype=torch.float32)
+        self.via_steps = torch.zeros((self.capacity,), device=dev, dtype=torch.int32)
+        self.size = torch.ones((1,), device=dev, dtype=torch.int32)
+        root_t = torch.as_tensor(np.asarray(root, dtype=np.float32)).to(dev)
+        self.nodes[0] = root_t
+        self.via[0] = root_t
+        self.size_bound = 1            # host upper bound of the live node count (no synchronisation needed)
+        self._desc = _capi.Tree(self.nodes.data_ptr(), self.parent.data_ptr(), self.via.data_ptr(),
+                                self.via_steps.data_ptr(), self.size.data_ptr(), self.capacity, 0)
+
+    def download(self) -> dict:
+        """Host copy of the live part of the tree (synchronises)."""
+        n = int(self.size.item())
+        self.size_bound = n
+        return {"nodes": self.nodes[:n].cpu().numpy(), "parent": self.parent[:n].cpu().numpy(),
+                "via": self.via[:n].cpu().numpy(), "via_steps": self.via_steps[:n].cpu().numpy()}

@@ -1,0 +1,103 @@
+#!/usr/bin/env python
+"""Planner-level timing on a B200: the reference-order sequential BiRRT driver (birrt.plan, one
+kernel launch per extension) against the batched device-resident planner (batched_rrt.batched_rrt_connect) on the
+reference scripts' scenarios and on a crowded many-world scene, plus the nearest-node kernel alone.
+
+    python tools/planner_bench.py > gpurun_out/planner_bench.json
+"""
+import json
+import os
+import random
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import torch  # noqa: E402
+
+from plant_motion_planning_b200 import EdgeCheckConfig, EdgeChecker, birrt, load_iiwa14, planner_fns as F  # noqa: E402
+from plant_motion_planning_b200.batched_rrt import batched_rrt_connect  # noqa: E402
+from plant_motion_planning_b200.env import MultiPlantWorld  # noqa: E402
+from plant_motion_planning_b200.scenarios import GOAL, SCRIPTS, START, script_worlds  # noqa: E402
+from plant_motion_planning_b200.workloads import synthetic_worlds  # noqa: E402
+
+
+def timed(fn, repeats=3):
+    best, out = 1e30, None
+    for _ in range(repeats):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = fn()
+        torch.cuda.synchronize()
+        best = min(best, time.perf_counter() - t0)
+    return best, out
+
+
+def main():
+    robot = load_iiwa14()
+    report = {"scenarios": [], "nearest": []}
+    # 64 sampled worlds in which the scripts' start and goal are valid (drawn from 128 candidates)
+    cand = synthetic_worlds(128)
+    probe = EdgeChecker(robot, cand, EdgeCheckConfig(deflection_limit=0.30))
+    ok = ~probe.check_configs_host(np.asarray([START, GOAL], dtype=np.float32), detail=False)["flags"].any(axis=0)
+    probe.close()
+    crowd = [w for w, k in zip(cand, ok) if k]
+    scenes = [(name, None) for name in SCRIPTS] + [(f"synthetic_{n}_worlds_limit_0.30", crowd[:n]) for n in (8, 16, 32)]
+    for name, worlds in scenes:
+        if worlds is None:
+            worlds, cfg = script_worlds(name)
+            limit, mode, avoid = cfg["deflection_limit"], cfg["mode"], cfg["avoid_all"]
+        else:
+            limit, mode, avoid = 0.30, "our_method", False
+        ec = EdgeCheckConfig(deflection_limit=limit, mode=mode)
+        chk = EdgeChecker(robot, worlds, ec)
+        row = {"scenario": name, "worlds": len(worlds), "mode": mode}
+        for batch in (64, 256, 1024):
+            t, plan = timed(lambda: batched_rrt_connect(chk, START, GOAL, batch=batch, max_iterations=300, seed=0))
+            row[f"batched_{batch}"] = {"seconds": t, "iterations": plan.iterations if plan else None,
+                                       "edges_validated": plan.edges_validated if plan else None,
+                                       "path_configs": len(plan.path) if plan else None,
+                                       "waypoints": len(plan.waypoints) if plan else None}
+        # the reference-order driver on the same checker (sequential, one launch per extension; gate replayed on the host)
+        xs = list(range(len(worlds)))
+        env = MultiPlantWorld(xs, [0], limit, worlds=worlds, avoid_all=avoid, checker_factory=lambda r, w, c: chk,
+                              robot=robot)
+        dist, samp, ext = F.get_distance_fn(robot), F.get_sample_fn(robot), F.get_extend_fn(robot)
+        backend = birrt.GpuBackend(chk)
+
+        def sequential():
+            np.random.seed(1); random.seed(1)
+            for _ in range(5):
+                res = birrt.plan(env, START, GOAL, dist, samp, ext, backend, max_iterations=2000)
+                if res is not None:
+                    return res
+            return None
+        l0 = backend.launches
+        t, res = timed(sequential, repeats=1)
+        row["sequential_reference_order"] = {"seconds": t, "kernel_launches": backend.launches - l0,
+                                             "path_configs": len(res[0]) if res else None}
+        report["scenarios"].append(row)
+        chk.close()
+    # nearest-node kernel alone
+    chk = EdgeChecker(robot, synthetic_worlds(1), EdgeCheckConfig())
+    rng = np.random.RandomState(0)
+    for T, B in ((1 << 10, 256), (1 << 14, 1024), (1 << 17, 1024), (1 << 20, 1024), (1 << 20, 8192)):
+        nodes = torch.from_numpy(rng.uniform(robot.lower, robot.upper, size=(T, 7)).astype(np.float32)).cuda()
+        targets = torch.from_numpy(rng.uniform(robot.lower, robot.upper, size=(B, 7)).astype(np.float32)).cuda()
+        for _ in range(3):
+            chk.nearest(nodes, targets)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            chk.nearest(nodes, targets)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        report["nearest"].append({"T": T, "B": B, "ms": ms, "pairs_per_s": T * B / (ms * 1e-3),
+                                  "node_bytes_per_s": T * 28 * ((B + 7) // 8) / (ms * 1e-3)})
+    print(json.dumps(report, indent=1))
+
+
+if __name__ == "__main__":
+    main()
