@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--deflection_limit", type=float, default=None)
     ap.add_argument("--iterations", type=int, default=2000)
     ap.add_argument("--smooth", action="store_true")
+    ap.add_argument("--batched", action="store_true", help="batched RRT-Connect on device-resident trees (pmp_tree_extend)")
+    ap.add_argument("--batch", type=int, default=256)
     args = ap.parse_args()
     cfg = SCRIPTS[args.script]
     limit = cfg["deflection_limit"] if args.deflection_limit is None else args.deflection_limit
@@ -44,7 +46,22 @@ def main():
     log = birrt.PlanLog()
     t0 = time.time()
     res = None
-    for attempt in range(200):                      # planner.py:36-48
+    if args.batched:
+        from plant_motion_planning_b200.batched_rrt import batched_rrt_connect
+        plan = batched_rrt_connect(env.checker, START, GOAL, batch=args.batch, max_iterations=args.iterations, seed=cfg["seed"])
+        if plan is None:
+            print("Unable to find a plan!")
+            return 1
+        print(f"batched plan: {len(plan.path)} configurations through {len(plan.waypoints)} tree nodes, "
+              f"{plan.iterations} iterations x {2 * args.batch} extensions, trees {plan.tree_sizes}, {time.time() - t0:.3f} s")
+        path = plan.path[1:]
+        if args.smooth:
+            path = birrt.smooth_path_batched(env.checker, [START] + list(path), dist, rounds=10, proposals=256)[1:]
+            print(f"smoothed: {len(path)} waypoints")
+        ee_len, over, _ = env.path_cost(START, path)
+        res = (path, ee_len, over)
+        args.smooth = False
+    for attempt in range(0 if args.batched else 200):                      # planner.py:36-48
         res = birrt.plan(env, START, GOAL, dist, samp, ext, backend, max_iterations=args.iterations, log=log)
         if res is not None:
             break

@@ -230,7 +230,7 @@ typedef struct pmp_tree {
 
 /* One batched extension: for each target, the nearest node is extended towards it with the full multi-world check
  * (forward sequence, q_near excluded, target included) and the last safe configuration -- if any step was safe --
- * is appended to the tree in batch order.  Three kernels on `stream`, no host synchronisation.
+ * is appended to the tree in batch order.  Five kernels on `stream`, no host synchronisation.
  *   size_bound     host upper bound of *tree->size (for grid sizing), 1 <= size_bound <= capacity
  *   new_index_dev  [B] slot of the appended node, -1 if none
  *   reached_dev    [B] 1 if the target itself was reached (first_hit >= n_steps)

@@ -519,7 +519,7 @@ static int nearest_tile(pmp_ctx* ctx) { return ctx->h_robot.dof <= 8 ? 8 : 4; }
 static int nearest_splits(pmp_ctx* ctx, int T, int B) {
     const int tgt = nearest_tile(ctx);
     const int tiles = (B + tgt - 1) / tgt;
-    int splits = (2 * ctx->sm_count + tiles - 1) / tiles;            // about two CTAs per SM
+    int splits = (16 * ctx->sm_count + tiles - 1) / tiles;           // about eight waves of two CTAs per SM: short tail
     const int max_splits = (T + 4 * PMP_NN_BLOCK - 1) / (4 * PMP_NN_BLOCK);   // at least 4 nodes per thread
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
@@ -528,19 +528,28 @@ static int nearest_splits(pmp_ctx* ctx, int T, int B) {
 
 // launches the two nearest-node kernels; part_* must hold B * splits entries
 static int launch_nearest(pmp_ctx* ctx, const float* nodes, int T, const int32_t* size_dev, const float* targets, int B,
-                          int splits, double* part_r, int32_t* part_i, int32_t* index, double* dist, float* q_from,
-                          cudaStream_t st) {
+                          int splits, uint32_t* min32, double* part_r, int32_t* part_i, int32_t* index, double* dist,
+                          float* q_from, cudaStream_t st) {
     PmpNearestArgs a;
+    a.min32 = min32;
     a.nodes = nodes; a.size_dev = size_dev; a.T = T; a.targets = targets; a.B = B; a.D = ctx->h_robot.dof;
     a.circular_mask = ctx->h_robot.circular_mask; a.splits = splits; a.part_r = part_r; a.part_i = part_i;
     a.index = index; a.dist = dist; a.q_from = q_from;
     const int tgt = nearest_tile(ctx);
     const dim3 grid((B + tgt - 1) / tgt, splits, 1);
-    if (a.D <= 8) pmp_nearest_kernel<8, 8><<<grid, PMP_NN_BLOCK, 0, st>>>(a);
-    else pmp_nearest_kernel<16, 4><<<grid, PMP_NN_BLOCK, 0, st>>>(a);
+    CK(cudaMemsetAsync(min32, 0x7f, sizeof(uint32_t) * (size_t)B, st));      // 0x7f7f7f7f = 3.39e38f
+    const bool circ = a.circular_mask != 0;
+#define PMP_NN_LAUNCH(DP, TG, CI)                                                \
+    do {                                                                         \
+        pmp_nearest_min_kernel<DP, TG, CI><<<grid, PMP_NN_BLOCK, 0, st>>>(a);    \
+        pmp_nearest_kernel<DP, TG, CI><<<grid, PMP_NN_BLOCK, 0, st>>>(a);        \
+    } while (0)
+    if (a.D <= 8) { if (circ) PMP_NN_LAUNCH(8, 8, true); else PMP_NN_LAUNCH(8, 8, false); }
+    else { if (circ) PMP_NN_LAUNCH(16, 4, true); else PMP_NN_LAUNCH(16, 4, false); }
+#undef PMP_NN_LAUNCH
     pmp_nearest_finish_kernel<<<(B + 127) / 128, 128, 0, st>>>(a);
     CK(cudaGetLastError());
-    ctx->info.kernel_launches += 2;
+    ctx->info.kernel_launches += 3;
     return PMP_OK;
 }
 
@@ -554,12 +563,13 @@ extern "C" int pmp_nearest(pmp_ctx* ctx, const float* nodes_dev, int32_t T, cons
     if (!nodes_dev || !targets_dev || !index_dev) return fail(ctx, PMP_E_INVALID, "nodes, targets and index are required");
     CK(cudaSetDevice(ctx->device));
     const int splits = nearest_splits(ctx, T, B);
-    const size_t br = up256(sizeof(double) * (size_t)B * splits), bi = up256(sizeof(int32_t) * (size_t)B * splits);
-    int rc = ensure_tree_scratch(ctx, br + bi);
+    const size_t br = up256(sizeof(double) * (size_t)B * splits), bi = up256(sizeof(int32_t) * (size_t)B * splits),
+                 bm = up256(sizeof(uint32_t) * (size_t)B);
+    int rc = ensure_tree_scratch(ctx, br + bi + bm);
     if (rc) return rc;
     char* p = (char*)ctx->d_tree_scratch;
-    return launch_nearest(ctx, nodes_dev, T, size_dev, targets_dev, B, splits, (double*)p, (int32_t*)(p + br), index_dev,
-                          dist_dev, q_from_dev, (cudaStream_t)stream);
+    return launch_nearest(ctx, nodes_dev, T, size_dev, targets_dev, B, splits, (uint32_t*)(p + br + bi), (double*)p,
+                          (int32_t*)(p + br), index_dev, dist_dev, q_from_dev, (cudaStream_t)stream);
 }
 
 extern "C" int pmp_edge_points(pmp_ctx* ctx, const float* q0_dev, const float* q1_dev, int32_t E,
@@ -595,7 +605,7 @@ extern "C" int pmp_tree_extend(pmp_ctx* ctx, const pmp_tree* tree, int32_t size_
     const int splits = nearest_splits(ctx, size_bound, B);
     const size_t br = up256(sizeof(double) * (size_t)B * splits), bp = up256(sizeof(int32_t) * (size_t)B * splits),
                  bi = up256(sizeof(int32_t) * (size_t)B), bq = up256(sizeof(float) * (size_t)B * D);
-    rc = ensure_tree_scratch(ctx, br + bp + 3 * bi + bq);
+    rc = ensure_tree_scratch(ctx, br + bp + 4 * bi + bq);
     if (rc) return rc;
     char* p = (char*)ctx->d_tree_scratch;
     auto take = [&](size_t b) { char* r = p; p += b; return r; };
@@ -604,12 +614,13 @@ extern "C" int pmp_tree_extend(pmp_ctx* ctx, const pmp_tree* tree, int32_t size_
     int32_t* from_index = (int32_t*)take(bi);
     int32_t* first_hit = (int32_t*)take(bi);
     int32_t* n_steps = (int32_t*)take(bi);
+    uint32_t* min32 = (uint32_t*)take(bi);
     float* q_from = (float*)take(bq);
     cudaStream_t st = (cudaStream_t)stream;
     // 1. nearest node of every target (+ gather), 2. the edge kernel on (nearest node -> target),
     // 3. append the last safe configuration of every extension that made progress
-    rc = launch_nearest(ctx, tree->nodes, size_bound, tree->size, targets_dev, B, splits, part_r, part_i, from_index,
-                        nullptr, q_from, st);
+    rc = launch_nearest(ctx, tree->nodes, size_bound, tree->size, targets_dev, B, splits, min32, part_r, part_i,
+                        from_index, nullptr, q_from, st);
     if (rc) return rc;
     rc = pmp_validate_edges(ctx, q_from, targets_dev, B, max_steps, 0, first_hit, n_steps, nullptr, nullptr, nullptr,
                             nullptr, nullptr, nullptr, stream);

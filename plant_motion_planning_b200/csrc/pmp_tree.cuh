@@ -4,8 +4,9 @@
 //   pmp_nearest_kernel / pmp_nearest_finish_kernel
 //        nearest tree node of every target under the reference metric -- argmin over the tree of
 //        distance_fn(node, target) with the first minimum winning (motion_planners/motion_planners/utils.py:47-53,
-//        primitives.py:207; pybullet_tools/utils.py:3604-3627).  float64 arithmetic on the float32 node/target
-//        data in a fixed summation order, so the chosen INDEX is bit-identical to the float64 oracle.
+//        primitives.py:207; pybullet_tools/utils.py:3604-3627).  A float32 pass finds the minimum up to its rounding
+//        error; every node inside that error band is then evaluated in float64 on the float32 node/target data in
+//        a fixed summation order, so the chosen INDEX (and distance) is bit-identical to the float64 oracle.
 //   pmp_edge_points_kernel
 //        configuration number step[e] of edge e, the same arithmetic as the edge kernel's interpolation.
 //   pmp_tree_append_kernel
@@ -27,6 +28,7 @@ struct PmpNearestArgs {
     int32_t B, D;
     uint32_t circular_mask;
     int32_t splits;            // CTAs along the tree axis
+    uint32_t* min32;           // [B] float32 bits of the smallest float32 squared distance (pass 1)
     double* part_r;            // [B, splits] partial minimum distance
     int32_t* part_i;           // [B, splits] its node index
     int32_t* index;            // [B]
@@ -39,74 +41,126 @@ __device__ __forceinline__ bool pmp_nn_better(double ra, int ia, double rb, int 
     return ra < rb || (ra == rb && ia < ib);
 }
 
-// Python's float modulo form of wrap_interval: (d + pi) % 2pi - pi (pybullet_tools/utils.py:1666-1686); fmod is exact.
-// Not inlined: continuous joints are rare and the fmod expansion is long.
-__device__ __noinline__ double pmp_wrap_pi_f64(double d) {
-    const double two_pi = 6.283185307179586, pi = 3.141592653589793;
-    double m = fmod(__dadd_rn(d, pi), two_pi);
-    if (m < 0.0) m = __dadd_rn(m, two_pi);
-    return __dsub_rn(m, pi);
+// Exact float64 distance of one (node, target) pair: sqrt of the per-joint squares summed in joint order, the
+// difference wrapped on continuous joints with Python's float modulo ((d + pi) % 2pi - pi,
+// pybullet_tools/utils.py:1666-1686, 3604-3627; fmod is exact).  Only near-minimal pairs get here.
+__device__ __noinline__ double pmp_nn_exact(const float* __restrict__ node, const float* __restrict__ target, int D,
+                                            uint32_t circ) {
+    double s = 0.0;
+    for (int j = 0; j < D; ++j) {
+        double d = __dsub_rn((double)target[j], (double)node[j]);
+        if ((circ >> j) & 1u) {
+            const double two_pi = 6.283185307179586, pi = 3.141592653589793;
+            double m = fmod(__dadd_rn(d, pi), two_pi);
+            if (m < 0.0) m = __dadd_rn(m, two_pi);
+            d = __dsub_rn(m, pi);
+        }
+        s = __dadd_rn(s, __dmul_rn(d, d));
+    }
+    return __dsqrt_rn(s);
 }
 
-// DP = DOF padding (8 or 16): the per-joint loops are fully unrolled over DP slots; PMP_NN_TGT targets per CTA.
-template <int DP, int PMP_NN_TGT>
-__global__ void __launch_bounds__(PMP_NN_BLOCK) pmp_nearest_kernel(const PmpNearestArgs a) {
-    __shared__ double sm_t[PMP_NN_TGT][PMP_MAX_DOF];
-    __shared__ double sm_r[PMP_NN_BLOCK / 32][PMP_NN_TGT];
-    __shared__ int sm_i[PMP_NN_BLOCK / 32][PMP_NN_TGT];
-    const int D = a.D;
-    const int t0 = blockIdx.x * PMP_NN_TGT;
-    for (int k = threadIdx.x; k < PMP_NN_TGT * PMP_MAX_DOF; k += blockDim.x) {
-        const int t = k / PMP_MAX_DOF, j = k % PMP_MAX_DOF;
-        sm_t[t][j] = (t0 + t < a.B && j < D) ? (double)a.targets[(size_t)(t0 + t) * D + j] : 0.0;
+// float32 squared distance used as the filter (relative error <= (D + 2) * 2^-24, plus 1.3e-5 per continuous joint)
+template <int DP, bool CIRC>
+__device__ __forceinline__ float pmp_nn_s32(const float (&t)[DP], const float (&q)[DP], uint32_t circ) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < DP; ++j) {
+        float d = t[j] - q[j];
+        if (CIRC && ((circ >> j) & 1u)) d = fmaf(-6.2831853071795865f, rintf(d * 0.15915494309189535f), d);
+        s = fmaf(d, d, s);
     }
-    __syncthreads();
+    return s;
+}
+
+__device__ __forceinline__ void pmp_nn_range(const PmpNearestArgs& a, int& lo, int& hi) {
     int T = a.T;
     if (a.size_dev) T = min(T, *a.size_dev);
     // contiguous slice of the tree per blockIdx.y, a multiple of the block size
     int per = (T + a.splits - 1) / a.splits;
     per = (per + PMP_NN_BLOCK - 1) / PMP_NN_BLOCK * PMP_NN_BLOCK;
-    const int lo = blockIdx.y * per, hi = min(T, lo + per);
+    lo = blockIdx.y * per;
+    hi = min(T, lo + per);
+}
 
-    const double inf = __longlong_as_double(0x7ff0000000000000LL);
-    double best_s[PMP_NN_TGT];
-    int best_i[PMP_NN_TGT];
+// Pass 1: smallest float32 squared distance of each target over the whole tree (atomicMin on the float bits: the
+// values are non-negative).  DP = DOF padding (8 or 16), TGT targets per CTA, all in registers; CIRC = the robot has
+// continuous joints (their wrap costs three instructions per term, so arms without one get a kernel without it).
+// Padding joints have target = node = 0 and contribute nothing.
+template <int DP, int TGT, bool CIRC>
+__global__ void __launch_bounds__(PMP_NN_BLOCK) pmp_nearest_min_kernel(const PmpNearestArgs a) {
+    const int D = a.D;
+    const int t0 = blockIdx.x * TGT;
+    float tg[TGT][DP];
 #pragma unroll
-    for (int t = 0; t < PMP_NN_TGT; ++t) { best_s[t] = inf; best_i[t] = 0x7fffffff; }
-
+    for (int t = 0; t < TGT; ++t)
+#pragma unroll
+        for (int j = 0; j < DP; ++j)
+            tg[t][j] = (t0 + t < a.B && j < D) ? a.targets[(size_t)(t0 + t) * D + j] : 0.f;
+    int lo, hi;
+    pmp_nn_range(a, lo, hi);
+    float best[TGT];
+#pragma unroll
+    for (int t = 0; t < TGT; ++t) best[t] = 3.0e38f;
     for (int n = lo + threadIdx.x; n < hi; n += PMP_NN_BLOCK) {
-        double q[DP];
+        float q[DP];
 #pragma unroll
-        for (int j = 0; j < DP; ++j) q[j] = j < D ? (double)a.nodes[(size_t)n * D + j] : 0.0;
+        for (int j = 0; j < DP; ++j) q[j] = j < D ? a.nodes[(size_t)n * D + j] : 0.f;
 #pragma unroll
-        for (int t = 0; t < PMP_NN_TGT; ++t) {
-            double s = 0.0;
+        for (int t = 0; t < TGT; ++t) best[t] = fminf(best[t], pmp_nn_s32<DP, CIRC>(tg[t], q, a.circular_mask));
+    }
 #pragma unroll
-            for (int j = 0; j < DP; ++j) {
-                if (j < D) {
-                    // difference_fn(target, node): target - node, wrapped on continuous joints
-                    double d = __dsub_rn(sm_t[t][j], q[j]);
-                    if ((a.circular_mask >> j) & 1u) d = pmp_wrap_pi_f64(d);
-                    s = __dadd_rn(s, __dmul_rn(d, d));
-                }
-            }
-            // The reference compares sqrt(s).  sqrt is monotone, so away from a 1e-15 relative band around the
-            // running best the comparison of the sums decides; inside the band (near ties) compare the rounded
-            // square roots exactly as the reference does, lower index first.
-            const double b = best_s[t];
-            if (s < b * (1.0 - 1e-15)) {
-                best_s[t] = s; best_i[t] = n;
-            } else if (!(s > b * (1.0 + 1e-15))) {
-                const double rn = __dsqrt_rn(s), rb = __dsqrt_rn(b);
-                if (pmp_nn_better(rn, n, rb, best_i[t])) { best_s[t] = s; best_i[t] = n; }
+    for (int t = 0; t < TGT; ++t) {
+        float v = best[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if ((threadIdx.x & 31) == 0 && t0 + t < a.B) atomicMin(&a.min32[t0 + t], __float_as_uint(v));
+    }
+}
+
+// Pass 2: every node whose float32 distance is within the filter's error band of the pass-1 minimum is evaluated
+// exactly in float64; the lexicographic minimum of (distance, index) over those is the reference's argmin.
+template <int DP, int TGT, bool CIRC>
+__global__ void __launch_bounds__(PMP_NN_BLOCK) pmp_nearest_kernel(const PmpNearestArgs a) {
+    __shared__ double sm_r[PMP_NN_BLOCK / 32][TGT];
+    __shared__ int sm_i[PMP_NN_BLOCK / 32][TGT];
+    const int D = a.D;
+    const int t0 = blockIdx.x * TGT;
+    float tg[TGT][DP], thr[TGT];
+    const float band = 3.0e-5f * (float)__popc(a.circular_mask);     // absolute error of the wrapped terms
+#pragma unroll
+    for (int t = 0; t < TGT; ++t) {
+#pragma unroll
+        for (int j = 0; j < DP; ++j)
+            tg[t][j] = (t0 + t < a.B && j < D) ? a.targets[(size_t)(t0 + t) * D + j] : 0.f;
+        const float m = t0 + t < a.B ? __uint_as_float(a.min32[t0 + t]) : 0.f;
+        thr[t] = (m + 2.f * band) * 1.00001f + 1e-30f;    // + underflow range of the float32 squares
+    }
+    int lo, hi;
+    pmp_nn_range(a, lo, hi);
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    double best_r[TGT];
+    int best_i[TGT];
+#pragma unroll
+    for (int t = 0; t < TGT; ++t) { best_r[t] = inf; best_i[t] = 0x7fffffff; }
+    for (int n = lo + threadIdx.x; n < hi; n += PMP_NN_BLOCK) {
+        float q[DP];
+#pragma unroll
+        for (int j = 0; j < DP; ++j) q[j] = j < D ? a.nodes[(size_t)n * D + j] : 0.f;
+#pragma unroll
+        for (int t = 0; t < TGT; ++t) {
+            if (pmp_nn_s32<DP, CIRC>(tg[t], q, a.circular_mask) <= thr[t] && t0 + t < a.B) {
+                const double r = pmp_nn_exact(a.nodes + (size_t)n * D, a.targets + (size_t)(t0 + t) * D, D,
+                                              a.circular_mask);
+                if (pmp_nn_better(r, n, best_r[t], best_i[t])) { best_r[t] = r; best_i[t] = n; }
             }
         }
     }
-    // block reduction of (sqrt(s), index)
+    // block reduction of (distance, index)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
-    for (int t = 0; t < PMP_NN_TGT; ++t) {
-        double r = __dsqrt_rn(best_s[t]);
+    for (int t = 0; t < TGT; ++t) {
+        double r = best_r[t];
         int i = best_i[t];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -117,7 +171,7 @@ __global__ void __launch_bounds__(PMP_NN_BLOCK) pmp_nearest_kernel(const PmpNear
         if (lane == 0) { sm_r[wid][t] = r; sm_i[wid][t] = i; }
     }
     __syncthreads();
-    if (threadIdx.x < PMP_NN_TGT && t0 + threadIdx.x < a.B) {
+    if (threadIdx.x < TGT && t0 + threadIdx.x < a.B) {
         const int t = threadIdx.x;
         double r = sm_r[0][t];
         int i = sm_i[0][t];

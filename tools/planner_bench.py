@@ -37,19 +37,23 @@ def timed(fn, repeats=3):
 def main():
     robot = load_iiwa14()
     report = {"scenarios": [], "nearest": []}
-    # 64 sampled worlds in which the scripts' start and goal are valid (drawn from 128 candidates)
-    cand = synthetic_worlds(128)
-    probe = EdgeChecker(robot, cand, EdgeCheckConfig(deflection_limit=0.30))
-    ok = ~probe.check_configs_host(np.asarray([START, GOAL], dtype=np.float32), detail=False)["flags"].any(axis=0)
-    probe.close()
-    crowd = [w for w, k in zip(cand, ok) if k]
-    scenes = [(name, None) for name in SCRIPTS] + [(f"synthetic_{n}_worlds_limit_0.30", crowd[:n]) for n in (8, 16, 32)]
-    for name, worlds in scenes:
+    # crowded scenes: sampled worlds in which the scripts' start and goal are valid at the given deflection limit
+    cand = synthetic_worlds(64)
+    scenes = [(name, None, None) for name in SCRIPTS]
+    for limit, n in ((0.6, 4), (1.0, 16), (1.0, 48)):
+        probe = EdgeChecker(robot, cand, EdgeCheckConfig(deflection_limit=limit))
+        ok = ~probe.check_configs_host(np.asarray([START, GOAL], dtype=np.float32), detail=False)["flags"].any(axis=0)
+        probe.close()
+        crowd = [w for w, k in zip(cand, ok) if k][:n]
+        scenes.append((f"synthetic_{len(crowd)}_worlds_limit_{limit}", crowd, limit))
+    if "--nearest-only" in sys.argv:
+        scenes = []
+    for name, worlds, limit in scenes:
         if worlds is None:
             worlds, cfg = script_worlds(name)
             limit, mode, avoid = cfg["deflection_limit"], cfg["mode"], cfg["avoid_all"]
         else:
-            limit, mode, avoid = 0.30, "our_method", False
+            mode, avoid = "our_method", False
         ec = EdgeCheckConfig(deflection_limit=limit, mode=mode)
         chk = EdgeChecker(robot, worlds, ec)
         row = {"scenario": name, "worlds": len(worlds), "mode": mode}
