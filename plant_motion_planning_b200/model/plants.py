@@ -362,3 +362,73 @@ def _load_env_sets() -> None:
 
 
 _load_env_sets()
+
+
+# --------------------------------------------------------------------------- writers
+def _rpy_from_matrix(R: np.ndarray) -> Tuple[float, float, float]:
+    """Inverse of rpy_to_matrix (Rz(yaw) Ry(pitch) Rx(roll)), pitch in [-pi/2, pi/2]."""
+    sp = -float(R[2, 0])
+    if abs(sp) < 1.0 - 1e-12:
+        return (float(np.arctan2(R[2, 1], R[2, 2])), float(np.arcsin(sp)), float(np.arctan2(R[1, 0], R[0, 0])))
+    return (float(np.arctan2(-R[1, 2], R[1, 1])), float(np.copysign(np.pi / 2, sp)), 0.0)
+
+
+def plant_urdf_text(world: PlantWorld, decimals: int = 5) -> str:
+    """The plant of ``world`` as URDF text in the layout of the saved fixtures (environments/multi_branch/envK/
+    plant.urdf, written by urdfEditor.saveUrdf from generate_random_plant, plant_motion_planning/utils.py:270-272):
+    link0 = base box, then per stem a massless link (joint about x) and the stem link (joint about y, box of
+    0.05 x 0.05 x 2h centred z_offset + h, mass 10, COM at com_z), `continuous` joints with damping 1.0.
+    Numbers are printed with ``decimals`` places like urdfEditor does (5)."""
+    if len(world.base_boxes) != 1:
+        raise ValueError("one plant (one base box) per URDF")
+    if any(s.y_first for s in world.stems):
+        raise ValueError("only x-then-y stems have a generated-plant URDF form")
+    base, half = world.base_boxes[0]
+    base_inv = Frame(base.R.T, -base.R.T @ base.t)
+    f = lambda v: f"{float(v) + 0.0:.{decimals}f}"
+    vec = lambda a: " ".join(f(v) for v in a)
+
+    def link(name, mass, com, box_xyz, box_size, inertia):
+        o = f'<origin rpy="{vec((0, 0, 0))}" xyz="{vec(box_xyz)}"/>'
+        return (f'\t<link name="{name}">\n\t\t<inertial>\n\t\t\t<origin rpy="{vec((0, 0, 0))}" xyz="{vec(com)}"/>\n'
+                f'\t\t\t<mass value="{f(mass)}"/>\n\t\t\t<inertia ixx="{f(inertia[0])}" ixy="0" ixz="0" iyy="{f(inertia[1])}" '
+                f'iyz="0" izz="{f(inertia[2])}"/>\n\t\t</inertial>\n\t\t<visual>\n\t\t\t{o}\n\t\t\t<geometry>\n'
+                f'\t\t\t\t<box size="{vec(box_size)}"/>\n\t\t\t</geometry>\n\t\t</visual>\n\t\t<collision>\n\t\t\t{o}\n'
+                f'\t\t\t<geometry>\n\t\t\t\t<box size="{vec(box_size)}"/>\n\t\t\t</geometry>\n\t\t</collision>\n\t</link>\n')
+
+    def joint(k, parent, child, origin: Frame, axis):
+        return (f'\t<joint name="joint{k}" type="continuous">\n\t\t<parent link="link{parent}"/>\n\t\t<child link="link{child}"/>\n'
+                f'\t\t<dynamics damping="1.0" friction="0.0001"/>\n'
+                f'\t\t<origin rpy="{vec(_rpy_from_matrix(origin.R))}" xyz="{vec(origin.t)}"/>\n'
+                f'\t\t<axis xyz="{vec(axis)}"/>\n\t</joint>\n')
+
+    def box_inertia(m, sx, sy, sz):
+        return (m * (sy * sy + sz * sz) / 12.0, m * (sx * sx + sz * sz) / 12.0, m * (sx * sx + sy * sy) / 12.0)
+
+    size0 = 2.0 * np.asarray(half)
+    links = [link("link0", 1e9, (0, 0, 0), (0, 0, 0), size0, box_inertia(1e9, *size0))]
+    joints = []
+    for k, s in enumerate(world.stems):
+        size = (2 * s.half_width, 2 * s.half_width, 2 * s.half_height)
+        links.append(link(f"link{2 * k + 1}", 0.0, (0, 0, 0), (0, 0, 0), (0, 0, 0), (0, 0, 0)))
+        links.append(link(f"link{2 * k + 2}", 10.0, (0, 0, s.com_z), (0, 0, s.z_offset + s.half_height), size,
+                          box_inertia(10.0, *size)))
+        origin = (base_inv @ s.origin) if s.parent < 0 else s.origin
+        parent_link = 0 if s.parent < 0 else 2 * s.parent + 2
+        joints.append(joint(2 * k + 1, parent_link, 2 * k + 1, origin, (1, 0, 0)))
+        joints.append(joint(2 * k + 2, 2 * k + 1, 2 * k + 2, Frame(np.eye(3), np.zeros(3)), (0, 1, 0)))
+    return '<?xml version="0.0" ?>\n<robot name="">\n' + "".join(links) + "".join(joints) + "</robot>\n"
+
+
+def save_plant(world: PlantWorld, urdf_path: str, params_path: str) -> None:
+    """Write ``plant.urdf`` + ``plant_params.pkl`` = [joint_list, main_stem_indices, base_points, base_pos], the pair
+    generate_random_plant(save_plant=True) leaves behind (plant_motion_planning/utils.py:270-279) and
+    load_plant_from_urdf / load_plant read back."""
+    if not world.base_pos or not world.base_points:
+        raise ValueError("world carries no plant_params bookkeeping (base_pos / base_points)")
+    with open(urdf_path, "w") as fp:
+        fp.write(plant_urdf_text(world))
+    params = [list(world.joint_list), list(world.main_stem_indices),
+              {int(k): [float(c) for c in v] for k, v in world.base_points.items()}, [float(c) for c in world.base_pos]]
+    with open(params_path, "wb") as fp:
+        pickle.dump(params, fp)
