@@ -242,3 +242,49 @@ class MultiPlantWorld:
         d = out["deflection"][1:].astype(np.float64)
         over = np.sum(np.maximum(d - self.deflection_limit, 0.0), axis=(0, 2))
         return ee_len, over, ee_len + self.config.alpha * over
+
+    def execute_multi_world(self, init_conf, path: Sequence[Sequence[float]], verbose: bool = True, out=None) -> dict:
+        """Command.execute_multi_world (pybullet_tools/kuka_primitives.py:467-521) as ONE batched evaluation: the
+        whole path is checked in every world by a single launch and the report the reference prints step by step
+        is produced from the returned traces.  Returns dict(ee_path_cost, deflection_over_limit [W], total_cost [W],
+        alpha, deflection [steps, W, P] (per-world deflection traces), flags [steps, W])."""
+        import sys
+        out = sys.stdout if out is None else out
+        Q = np.asarray([tuple(init_conf)] + [tuple(p) for p in path], dtype=np.float32)
+        res = self.checker.check_configs_host(Q, detail=True)
+        ee = res["ee"].astype(np.float64)
+        defl = res["deflection"][1:].astype(np.float64)
+        limit, alpha = float(self.deflection_limit), float(self.config.alpha)
+        over = np.zeros(len(self.envs))
+        ee_cost = 0.0
+        if verbose:
+            print("Executing path...", file=out)
+        for i in range(defl.shape[0]):
+            for w, env in enumerate(self.envs.values()):
+                n = env.plant_rep._n
+                if verbose:
+                    print("Environment: ", w, file=out)
+                for e in range(n):
+                    d = float(defl[i, w, e])
+                    if verbose:
+                        print("\tDeflection of plant %d: %f" % (e, d), file=out)
+                    if d > limit:
+                        if verbose:
+                            print("Error! Deflection limit exceeded!", file=out)
+                        over[w] += d - limit
+                if verbose:
+                    print("========================================", file=out)
+            ee_cost += float(np.linalg.norm(ee[i + 1] - ee[i]))
+        total = ee_cost + alpha * over
+        if verbose:
+            bar = "===================================================="
+            print(bar, file=out)
+            print("total path cost: ", ee_cost, file=out)
+            print("total Deflection over limit: ", over, file=out)
+            print("alpha: ", alpha, file=out)
+            print(bar, file=out)
+            print("Total cost: ", total, file=out)
+            print(bar, file=out)
+        self._set_action(Q[-1])
+        return {"ee_path_cost": ee_cost, "deflection_over_limit": over, "total_cost": total, "alpha": alpha,
+                "deflection": defl, "flags": res["flags"][1:]}

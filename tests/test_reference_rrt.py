@@ -84,6 +84,16 @@ def _cost(script, factory):
     env = MultiPlantWorld(cfg["xs"], cfg["ys"], cfg["deflection_limit"], *cfg["args"], cfg["limits"],
                           avoid_all=cfg["avoid_all"], checker_factory=factory)
     ee_len, over, total = env.path_cost(START, [tuple(q) for q in gold["smoothed"]])
+    # the batched execute report carries the same totals plus the per-world deflection traces
+    import io
+    buf = io.StringIO()
+    rep = env.execute_multi_world(START, [tuple(q) for q in gold["smoothed"]], out=buf)
+    assert abs(rep["ee_path_cost"] - ee_len) < 1e-9 and np.allclose(rep["deflection_over_limit"], over, atol=1e-9)
+    assert rep["deflection"].shape[:2] == (len(gold["smoothed"]), len(env.envs))
+    text = buf.getvalue()
+    assert text.startswith("Executing path...") and "total Deflection over limit: " in text
+    assert text.count("Environment: ") == len(gold["smoothed"]) * len(env.envs)
+    assert (text.count("Error! Deflection limit exceeded!") > 0) == bool(np.any(over > 0))
     return ee_len, over, total, gold["execute"]
 
 
