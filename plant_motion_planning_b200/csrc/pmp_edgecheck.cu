@@ -37,6 +37,8 @@ struct pmp_ctx {
     void* h_stage = nullptr;
     size_t stage_bytes = 0;
     // scratch of the tree entry points (nearest-node partials, gathered nodes, per-extension edge results)
+    int32_t* d_work_counter = nullptr;     // edge kernel: ring of 64 'next unclaimed edge' counters, one per launch
+    unsigned work_slot = 0;
     void* d_tree_scratch = nullptr;
     size_t tree_scratch_bytes = 0;
 };
@@ -95,7 +97,7 @@ extern "C" int pmp_destroy(pmp_ctx* ctx) {
     if (!ctx) return PMP_OK;
     cudaSetDevice(ctx->device);
     free_worlds(ctx);
-    cudaFree(ctx->d_robot); cudaFree(ctx->d_links); cudaFree(ctx->d_scratch); cudaFree(ctx->d_tree_scratch);
+    cudaFree(ctx->d_robot); cudaFree(ctx->d_links); cudaFree(ctx->d_scratch); cudaFree(ctx->d_tree_scratch); cudaFree(ctx->d_work_counter);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -263,6 +265,9 @@ extern "C" int pmp_validate_edges(pmp_ctx* ctx, const float* q0, const float* q1
     a.n_boxes = ctx->d_nboxes; a.prm = ctx->prm; a.q0 = q0; a.q1 = q1; a.E = E; a.max_steps = max_steps;
     a.backward = backward ? 1 : 0; a.first_hit = first_hit; a.n_steps = n_steps; a.max_defl = max_defl; a.over = over;
     a.ee_len = ee_len; a.cost = cost; a.rigid_mask = rigid_mask; a.exceed_mask = exceed_mask;
+    if (!ctx->d_work_counter) CK(cudaMalloc(&ctx->d_work_counter, 64 * sizeof(int32_t)));
+    a.work_counter = ctx->d_work_counter + (ctx->work_slot++ & 63u);   // launches in flight on other streams keep theirs
+    CK(cudaMemsetAsync(a.work_counter, 0, sizeof(int32_t), (cudaStream_t)stream));
 
     int apad, nspad;
     pads(ctx, apad, nspad);

@@ -479,6 +479,7 @@ struct PmpEdgeArgs {
     float* cost;               // [E] or null
     uint32_t* rigid_mask;      // [E, W, C] or null
     uint32_t* exceed_mask;     // [E, W, C] or null
+    int32_t* work_counter;     // [1] next unclaimed edge (zeroed before the launch)
 };
 
 // Edge-batch kernel.  Persistent CTAs; warp = edge, lane = step.
@@ -516,10 +517,15 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
 
     const int D = rt.dof;
     const int C = (args.max_steps + 31) >> 5;
-    const int total_warps = gridDim.x * warps;
     const float* stems_base = WSMEM ? sm_stems : args.stems;
 
-    for (int e = blockIdx.x * warps + wid; e < args.E; e += total_warps) {
+    // Edges are claimed one at a time from a global counter: their cost varies by an order of magnitude (free space
+    // vs. a sweep through a plant), and with a static stride the last warps of every SM would run alone.
+    for (;;) {
+        int e = 0;
+        if (lane == 0) e = atomicAdd(args.work_counter, 1);
+        e = __shfl_sync(PMP_FULL, e, 0);
+        if (e >= args.E) break;
         // ---- interpolation set-up: oracle num_steps / edge_configs (pybullet_tools/utils.py:3604-3676) ----
         __syncwarp();
         if (lane < D) {
