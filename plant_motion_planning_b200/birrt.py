@@ -425,8 +425,18 @@ def extend_many(checker, q_from: np.ndarray, q_to: np.ndarray, backward: bool = 
     out = checker.validate_edges_host(q_from, q_to, backward=backward, want_masks=True)
     E = out["n_steps"].shape[0]
     cap = out["rigid_mask"].shape[2] * 32
-    first = np.empty(E, np.int32)
-    for e in range(E):
-        n = min(int(out["n_steps"][e]), cap)
-        first[e] = replay_gate(n, out["rigid_mask"][e], out["exceed_mask"][e], probability, rand, forward_checker)
+    n_all = np.minimum(out["n_steps"], cap).astype(np.int32)
+    # edges without any "deflection exceeded" bit draw no random number: their first violation is the lowest set bit
+    # of the rigid masks OR-ed over the worlds (vectorised); only the others need the sequential gate replay
+    rig = np.bitwise_or.reduce(out["rigid_mask"].astype(np.uint32), axis=1)                  # [E, C]
+    exc_any = out["exceed_mask"].any(axis=(1, 2)) if forward_checker else np.zeros(E, dtype=bool)
+    word_has = rig != 0
+    first_word = np.argmax(word_has, axis=1)
+    w = rig[np.arange(E), first_word]
+    low = (w & (~w + np.uint32(1))).astype(np.float64)                                       # isolated lowest set bit
+    bit = np.where(w != 0, np.log2(np.maximum(low, 1.0)), 0).astype(np.int32)
+    first = np.where(word_has.any(axis=1), np.minimum(first_word * 32 + bit, n_all), n_all).astype(np.int32)
+    for e in np.nonzero(exc_any)[0]:
+        first[e] = replay_gate(int(n_all[e]), out["rigid_mask"][e], out["exceed_mask"][e], probability, rand,
+                               forward_checker)
     return first, out["n_steps"], out

@@ -260,3 +260,24 @@ def test_batched_planner_on_gpu_is_valid_under_the_oracle(gpu, name):
     assert not chk.check_configs_host(P.astype(np.float32), detail=False)["flags"].any()
     again = batched_rrt_connect(chk, S.START, S.GOAL, batch=256, max_iterations=50, seed=0)
     assert again.path == plan.path
+
+
+def test_extend_many_equals_per_edge_gate_replay():
+    """birrt.extend_many's vectorised first-violation (lowest rigid bit when no gate draw is needed) == replay_gate
+    edge by edge, including the number of random draws consumed."""
+    from plant_motion_planning_b200 import birrt
+    from plant_motion_planning_b200.workloads import random_edges, synthetic_worlds
+    robot = load_iiwa14()
+    ck = OracleChecker(robot, synthetic_worlds(3), EdgeCheckConfig(deflection_limit=0.05))
+    q0, q1 = random_edges(robot, 96, seed=4, max_len=2.5)
+    for forward in (True, False):
+        np.random.seed(8)
+        first, n, out = birrt.extend_many(ck, q0, q1, forward_checker=forward)
+        after = np.random.rand()
+        np.random.seed(8)
+        cap = out["rigid_mask"].shape[2] * 32
+        want = [F.replay_gate(min(int(out["n_steps"][e]), cap), out["rigid_mask"][e], out["exceed_mask"][e],
+                              F.GATE_PROBABILITY, None, forward) for e in range(len(q0))]
+        assert first.tolist() == want
+        assert np.random.rand() == after
+        assert out["exceed_mask"].any() and (np.asarray(want) < np.minimum(n, cap)).any() and (np.asarray(want) >= n).any()
