@@ -304,9 +304,18 @@ extern "C" int pmp_validate_edges(pmp_ctx* ctx, const float* q0, const float* q1
     if (grid > cap) grid = cap;
     cudaError_t err;
     int regs = 0;
-    if (apad == 12) err = pmp_launch_edge_a12(nspad, a, wsmem, grid, block, smem, (cudaStream_t)stream, &regs);
-    else if (apad == 16) err = pmp_launch_edge_a16(nspad, a, wsmem, grid, block, smem, (cudaStream_t)stream, &regs);
-    else err = pmp_launch_edge_a32(nspad, a, wsmem, grid, block, smem, (cudaStream_t)stream, &regs);
+    // a call that asks for nothing but first_hit / n_steps gets the early-stopping instantiation
+    const bool first_only = !max_defl && !over && !ee_len && !cost && !rigid_mask && !exceed_mask;
+    cudaStream_t st_ = (cudaStream_t)stream;
+    if (first_only) {
+        if (apad == 12) err = pmp_launch_edge_first_a12(nspad, a, wsmem, grid, block, smem, st_, &regs);
+        else if (apad == 16) err = pmp_launch_edge_first_a16(nspad, a, wsmem, grid, block, smem, st_, &regs);
+        else err = pmp_launch_edge_first_a32(nspad, a, wsmem, grid, block, smem, st_, &regs);
+    } else {
+        if (apad == 12) err = pmp_launch_edge_a12(nspad, a, wsmem, grid, block, smem, st_, &regs);
+        else if (apad == 16) err = pmp_launch_edge_a16(nspad, a, wsmem, grid, block, smem, st_, &regs);
+        else err = pmp_launch_edge_a32(nspad, a, wsmem, grid, block, smem, st_, &regs);
+    }
     ctx->info.regs_per_thread = regs;
     if (err != cudaSuccess) return fail(ctx, PMP_E_CUDA, std::string("edge kernel launch: ") + cudaGetErrorString(err));
     ctx->info.grid = grid; ctx->info.block = block; ctx->info.smem_bytes = (int)smem;

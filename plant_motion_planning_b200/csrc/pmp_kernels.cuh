@@ -489,7 +489,8 @@ struct PmpEdgeArgs {
 #ifndef PMP_EDGE_MINB
 #define PMP_EDGE_MINB 1
 #endif
-template <int A, int NSLOT, bool WSMEM>
+// FIRST: first-violation-only instantiation (no optional output requested), which stops like the reference's loops.
+template <int A, int NSLOT, bool WSMEM, bool FIRST>
 __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(const PmpEdgeArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PmpRobotTab& rt = *reinterpret_cast<PmpRobotTab*>(smem_raw);
@@ -517,6 +518,7 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
 
     const int D = rt.dof;
     const int C = (args.max_steps + 31) >> 5;
+    constexpr bool first_only = FIRST;
     const float* stems_base = WSMEM ? sm_stems : args.stems;
 
     // Edges are claimed one at a time from a global counter: their cost varies by an order of magnitude (free space
@@ -561,7 +563,7 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
         }
         for (int base = 0, chunk = 0; base < nc; base += 32, ++chunk) {
             const int i = base + lane;
-            const bool live = i < nc;
+            bool live = i < nc;
             const int num = i + off;
             const float t = (float)num * inv_n;
             const bool at_end = (num == n);
@@ -629,7 +631,24 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
             uint32_t viol = rigid0_mask;
             uint32_t keep_r = 0, keep_x = 0;
             float keep_m = 0.f, keep_o = 0.f;
+            // first-violation-only calls (the planner's extension check: no per-world outputs, no cost) stop like the
+            // reference's loops do (primitives.py:225-241, env.py:230-238): steps after the first violating one are
+            // retired, and the remaining worlds are skipped once step 0 of the chunk violates.
+            int retired_from = 32;
+            auto retire = [&](uint32_t v) {
+                const int L = __ffs(v) - 1;
+                if (L < retired_from) {
+                    retired_from = L;
+                    if (lane >= L) {
+                        live = false;
+#pragma unroll
+                        for (int a = 0; a < A; ++a) { c[a][0] = PMP_FAR; c[a][1] = PMP_FAR; c[a][2] = PMP_FAR; }
+                    }
+                }
+            };
+            if (first_only && viol) retire(viol);
             for (int w = 0; w < W; ++w) {
+                if (first_only && retired_from == 0) break;
                 PmpUnitOut u;
                 u.plant_hit = false; u.exceeded = false; u.max_defl = 0.f; u.over = 0.f;
                 if (prm.mode != PMP_MODE_IGNORE_ALL) {
@@ -648,6 +667,7 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
                     xg = __ballot_sync(PMP_FULL, live && u.exceeded && pass);
                 }
                 viol |= rm | xg;
+                if (first_only && viol) retire(viol);
                 const float md = __uint_as_float(__reduce_max_sync(PMP_FULL, __float_as_uint(live ? u.max_defl : 0.f)));
                 float ov = live ? u.over : 0.f;
 #pragma unroll
@@ -666,6 +686,7 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
                 }
             }
             if (viol && first == nc) first = base + __ffs(viol) - 1;
+            if (first_only && first < nc) break;
         }
         // zero the mask words of chunks this edge did not reach
         if (args.rigid_mask || args.exceed_mask) {

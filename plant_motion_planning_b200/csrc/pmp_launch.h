@@ -7,6 +7,8 @@
 #define PMP_DECLARE_LAUNCHERS(A)                                                                                       \
     cudaError_t pmp_launch_edge_a##A(int nspad, const PmpEdgeArgs& args, bool wsmem, int grid, int block, size_t smem, \
                                      cudaStream_t st, int* regs);                                                      \
+    cudaError_t pmp_launch_edge_first_a##A(int nspad, const PmpEdgeArgs& args, bool wsmem, int grid, int block,        \
+                                           size_t smem, cudaStream_t st, int* regs);                                   \
     cudaError_t pmp_launch_config_a##A(int nspad, const PmpConfigArgs& args, dim3 grid, int block, size_t smem,        \
                                        cudaStream_t st, int* regs);
 

@@ -237,7 +237,11 @@ class EdgeChecker:
         return ConfigBatchResult(flags, defl, theta, ee)
 
     def validate_edges(self, q_from, q_to, backward: bool = False, want_masks: bool = False,
-                       max_steps: Optional[int] = None, out: Optional[EdgeBatchResult] = None) -> EdgeBatchResult:
+                       max_steps: Optional[int] = None, out: Optional[EdgeBatchResult] = None,
+                       first_hit_only: bool = False) -> EdgeBatchResult:
+        """``first_hit_only``: request only first_hit / n_steps.  The kernel then stops like the reference's loops
+        (steps after the first violating one and the remaining worlds are not evaluated) -- the planner's
+        accept/reject question, several times cheaper on edges that collide early."""
         torch = self._torch()
         q0 = self._prep(q_from, "q_from")
         q1 = self._prep(q_to, "q_to")
@@ -247,8 +251,10 @@ class EdgeChecker:
         ms = int(max_steps or self.config.max_steps)
         Cw = (ms + 31) // 32
         with torch.cuda.device(self._dev()):
-            if out is None:
-                mk = lambda shape, dt: torch.empty(shape, device=q0.device, dtype=dt)
+            mk = lambda shape, dt: torch.empty(shape, device=q0.device, dtype=dt)
+            if out is None and first_hit_only:
+                out = EdgeBatchResult(mk((E,), torch.int32), mk((E,), torch.int32), None, None, None, None)
+            elif out is None:
                 out = EdgeBatchResult(mk((E,), torch.int32), mk((E,), torch.int32), mk((E, W), torch.float32),
                                       mk((E, W), torch.float32), mk((E,), torch.float32), mk((E,), torch.float32))
                 if want_masks:

@@ -177,6 +177,37 @@ def test_long_edges_and_step_capacity(ctx):
     assert int(out.first_hit.max()) <= 40
 
 
+@pytest.mark.parametrize("mode", ["our_method", "avoid_all", "ignore_all"])
+@pytest.mark.parametrize("backward", [False, True])
+def test_first_hit_only_calls_stop_early_with_identical_answers(ctx, mode, backward):
+    """A call that asks only for first_hit / n_steps retires steps and worlds like the reference's loops
+    (primitives.py:225-241, env.py:230-238); the answers are bit-identical to the full evaluation, also with the
+    on-device gate and with a step capacity."""
+    from plant_motion_planning_b200.workloads import random_edges
+    torch, chk = ctx["torch"], ctx["chk"]
+    q0, q1 = random_edges(ctx["model"], 1024, seed=12)
+    q1[3] = q0[3]
+    q1[512:] = q0[512:] + 0.25 * (q1[512:] - q0[512:])          # short edges: some stay free in every mode
+    a, b = torch.from_numpy(q0), torch.from_numpy(q1)
+    seen_hit = seen_free = False
+    try:
+        for gate in (None, 7):
+            chk.set_config(mode=mode, device_gate_seed=gate, deflection_limit=0.10 if gate else 0.30)
+            for ms in (320, 40):
+                full = chk.validate_edges(a, b, backward=backward, max_steps=ms)
+                fast = chk.validate_edges(a, b, backward=backward, max_steps=ms, first_hit_only=True)
+                assert fast.max_deflection is None and fast.cost is None
+                fh, n = full.first_hit.cpu().numpy(), np.minimum(full.n_steps.cpu().numpy(), ms)
+                bad = np.nonzero(fh != fast.first_hit.cpu().numpy())[0]
+                assert len(bad) == 0, (gate, ms, bad[:8], fh[bad[:8]], fast.first_hit.cpu().numpy()[bad[:8]], n[bad[:8]])
+                assert torch.equal(full.n_steps, fast.n_steps)
+                seen_hit |= bool((fh < n).any())
+                seen_free |= bool((fh >= n).any())
+        assert seen_hit and seen_free
+    finally:
+        chk.set_config(mode="our_method", device_gate_seed=None, deflection_limit=0.30)
+
+
 def test_empty_batch_and_bad_shapes(ctx):
     torch, chk = ctx["torch"], ctx["chk"]
     out = chk.validate_edges(torch.zeros((0, 7)), torch.zeros((0, 7)))

@@ -83,6 +83,28 @@ def main():
                                              "path_configs": len(res[0]) if res else None}
         report["scenarios"].append(row)
         chk.close()
+    # the planner's accept/reject question: full evaluation vs first-violation-only calls on random tree-like edges
+    from plant_motion_planning_b200.workloads import random_edges
+    report["first_hit_only"] = []
+    for W in (4, 64):
+        chk = EdgeChecker(robot, synthetic_worlds(W), EdgeCheckConfig())
+        q0, q1 = random_edges(robot, 1 << 14, seed=5)
+        a, b = torch.from_numpy(q0).cuda(), torch.from_numpy(q1).cuda()
+        row = {"worlds": W, "edges": len(q0)}
+        for name, kw in (("full", {}), ("first_hit_only", {"first_hit_only": True})):
+            for _ in range(3):
+                out = chk.validate_edges(a, b, **kw)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                out = chk.validate_edges(a, b, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+            row[name + "_ms"] = e0.elapsed_time(e1) / 5
+            row["steps"] = int(out.n_steps.sum().item())
+            row["free_fraction"] = float((out.first_hit >= out.n_steps).float().mean().item())
+        report["first_hit_only"].append(row)
+        chk.close()
     # nearest-node kernel alone
     chk = EdgeChecker(robot, synthetic_worlds(1), EdgeCheckConfig())
     rng = np.random.RandomState(0)
