@@ -166,6 +166,9 @@ int pmp_check_configs(pmp_ctx* ctx, const float* q_dev, int32_t B, uint8_t* flag
  *                          raw flag of step s in world w -- what the host needs to replay the reference's
  *                          5 % random pass-through in its sequential order     (NULL ok)
  * Steps >= max_steps are not evaluated.
+ * A call with every optional output NULL asks the planner's accept/reject question only; the kernel then stops the
+ * way the reference's loops do (steps after the first violating one and the remaining worlds are not evaluated,
+ * primitives.py:225-241, env.py:230-238).  first_hit / n_steps are identical to those of a full call.
  * Replaces the loop of extend_towards_with_angle_constraint_multi_world (motion_planners/motion_planners/
  * primitives.py:196-255), check_forward_path_multi_world (rrt_connect_with_angle_constraints_v2.py:143-198)
  * and the cost accumulation of Command.execute_multi_world (pybullet_tools/kuka_primitives.py:467-521). */

@@ -280,10 +280,11 @@ def _smooth(path: Sequence[Conf], extend_fn, distance_fn, backend: FlagBackend, 
 
 
 def smooth_path_batched(checker, path: Sequence[Conf], distance_fn, rounds: int = 10, proposals: int = 256,
-                        seed: int = 0) -> List[Conf]:
+                        seed: int = 0, gate: bool = True) -> List[Conf]:
     """Additive batched smoother: every round proposes `proposals` random shortcuts between points of the current
-    waypoint polyline, validates ALL of them in one pmp_validate_edges launch (gate applied in batch order) and
-    applies the valid one that shortens the path most."""
+    waypoint polyline, validates ALL of them in one pmp_validate_edges launch and applies the valid one that shortens
+    the path most.  ``gate=True`` replays the reference's 5 % pass-through per edge in batch order (needs the step
+    masks); ``gate=False`` treats every exceeded deflection as a violation and uses the first-violation-only call."""
     rng = np.random.RandomState(seed)
     way = [np.asarray(w, dtype=np.float64) for w in waypoints_from_path(path)]
     for _ in range(rounds):
@@ -302,7 +303,12 @@ def smooth_path_batched(checker, path: Sequence[Conf], distance_fn, rounds: int 
         if not ok.any():
             continue
         idx = np.nonzero(ok)[0]
-        first, n, _ = extend_many(checker, P[idx, 0].astype(np.float32), P[idx, 1].astype(np.float32))
+        if gate:
+            first, n, _ = extend_many(checker, P[idx, 0].astype(np.float32), P[idx, 1].astype(np.float32))
+        else:
+            r = checker.validate_edges_host(P[idx, 0].astype(np.float32), P[idx, 1].astype(np.float32),
+                                            first_hit_only=True)
+            first, n = r["first_hit"], r["n_steps"]
         valid = first >= n
         if not valid.any():
             continue

@@ -322,7 +322,8 @@ class EdgeChecker:
 
     # ------------------------------------------------------------------ host API (numpy; the C-ABI *_host calls)
     def validate_edges_host(self, q_from: np.ndarray, q_to: np.ndarray, backward: bool = False,
-                            want_masks: bool = False, max_steps: Optional[int] = None, out: Optional[dict] = None) -> dict:
+                            want_masks: bool = False, max_steps: Optional[int] = None, out: Optional[dict] = None,
+                            first_hit_only: bool = False) -> dict:
         """HOST buffers in, HOST buffers out: H2D, kernel, D2H and the synchronisation happen inside the
         C-ABI call -- the entry a CPU-side planner uses."""
         q0 = np.ascontiguousarray(q_from, dtype=np.float32).reshape(-1, self.dof)
@@ -330,7 +331,9 @@ class EdgeChecker:
         E, W = q0.shape[0], self.num_worlds
         ms = int(max_steps or self.config.max_steps)
         Cw = (ms + 31) // 32
-        if out is None:
+        if out is None and first_hit_only:
+            out = {"first_hit": np.empty(E, np.int32), "n_steps": np.empty(E, np.int32)}
+        elif out is None:
             out = {
                 "first_hit": np.empty(E, np.int32), "n_steps": np.empty(E, np.int32),
                 "max_deflection": np.empty((E, W), np.float32), "over_limit": np.empty((E, W), np.float32),
@@ -342,7 +345,7 @@ class EdgeChecker:
         vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p()
         self._check(self._lib.pmp_validate_edges_host(
             self._ctx, vp(q0), vp(q1), E, ms, 1 if backward else 0, vp(out["first_hit"]), vp(out["n_steps"]),
-            vp(out["max_deflection"]), vp(out["over_limit"]), vp(out["ee_len"]), vp(out["cost"]),
+            vp(out.get("max_deflection")), vp(out.get("over_limit")), vp(out.get("ee_len")), vp(out.get("cost")),
             vp(out.get("rigid_mask")), vp(out.get("exceed_mask"))), "pmp_validate_edges_host")
         return out
 

@@ -26,7 +26,8 @@ class OracleChecker:
             out["theta"] = r["theta"].astype(np.float32)
         return out
 
-    def validate_edges_host(self, q0, q1, backward=False, want_masks=False, max_steps=None, out=None):
+    def validate_edges_host(self, q0, q1, backward=False, want_masks=False, max_steps=None, out=None,
+                            first_hit_only=False):
         return self.o.validate_edges(q0, q1, backward=backward, want_masks=want_masks,
                                      max_steps=int(max_steps or self.config.max_steps))
 

@@ -141,3 +141,7 @@ def test_smoothing_sequential_parity_and_batched_validity():
         cfgs = list(ext(a, b))
         fl = ob.flags(cfgs)
         assert not (fl & 1).any(), "batched smoother produced a segment the oracle rejects"
+    # ungated variant (first-violation-only launches): every segment is free of rigid AND deflection violations
+    way2 = birrt.smooth_path_batched(chk, path, dist, rounds=6, proposals=128, seed=2, gate=False)
+    assert way2[0] == tuple(path[0]) and np.allclose(way2[-1], path[-1])
+    assert length(way2) <= length(birrt.waypoints_from_path(path)) + 1e-9
