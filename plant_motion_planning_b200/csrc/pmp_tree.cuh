@@ -88,7 +88,7 @@ __device__ __forceinline__ void pmp_nn_range(const PmpNearestArgs& a, int& lo, i
 // continuous joints (their wrap costs three instructions per term, so arms without one get a kernel without it).
 // Padding joints have target = node = 0 and contribute nothing.
 template <int DP, int TGT, bool CIRC>
-__global__ void __launch_bounds__(PMP_NN_BLOCK) pmp_nearest_min_kernel(const PmpNearestArgs a) {
+__global__ void __launch_bounds__(PMP_NN_BLOCK, 2) pmp_nearest_min_kernel(const PmpNearestArgs a) {
     const int D = a.D;
     const int t0 = blockIdx.x * TGT;
     float tg[TGT][DP];
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(PMP_NN_BLOCK) pmp_nearest_min_kernel(const Pmp
 // Pass 2: every node whose float32 distance is within the filter's error band of the pass-1 minimum is evaluated
 // exactly in float64; the lexicographic minimum of (distance, index) over those is the reference's argmin.
 template <int DP, int TGT, bool CIRC>
-__global__ void __launch_bounds__(PMP_NN_BLOCK) pmp_nearest_kernel(const PmpNearestArgs a) {
+__global__ void __launch_bounds__(PMP_NN_BLOCK, 2) pmp_nearest_kernel(const PmpNearestArgs a) {
     __shared__ double sm_r[PMP_NN_BLOCK / 32][TGT];
     __shared__ int sm_i[PMP_NN_BLOCK / 32][TGT];
     const int D = a.D;
