@@ -4,7 +4,7 @@ The reference grows its two trees one edge at a time: `argmin(distance_fn)` over
 `env.step` + `collision_fn` per interpolation step (motion_planners/motion_planners/primitives.py:196-255;
 rrt_connect_with_angle_constraints_v2.py:240-290).  Here every iteration proposes ``batch`` targets at once and the
 whole extension -- nearest node, multi-world edge validation, append of the last safe configuration -- is one
-`pmp_tree_extend` call (three kernels, trees never leave HBM).  The connect step aims the other tree at the nodes
+`pmp_tree_extend` call (five kernels, trees never leave HBM).  The connect step aims the other tree at the nodes
 just added.  The host reads back 16 bytes per iteration (the `stats` vector) to learn whether the trees met.
 
 Semantics kept from the reference: extension stops at the first violating step and keeps the safe prefix

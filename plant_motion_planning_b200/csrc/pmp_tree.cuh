@@ -1,7 +1,7 @@
 // Device-resident tree growth for batched RRT extension: the callers either side of the edge
-// kernel.  Three small kernels, all launched on the caller's stream by pmp_tree_extend (pmp_edgecheck.cu):
+// kernel.  Small kernels launched on the caller's stream by pmp_tree_extend (pmp_edgecheck.cu) around the edge kernel:
 //
-//   pmp_nearest_kernel / pmp_nearest_finish_kernel
+//   pmp_nearest_min_kernel / pmp_nearest_kernel / pmp_nearest_finish_kernel
 //        nearest tree node of every target under the reference metric -- argmin over the tree of
 //        distance_fn(node, target) with the first minimum winning (motion_planners/motion_planners/utils.py:47-53,
 //        primitives.py:207; pybullet_tools/utils.py:3604-3627).  A float32 pass finds the minimum up to its rounding

@@ -304,7 +304,7 @@ class EdgeChecker:
 
     def tree_extend(self, tree: "DeviceTree", targets, max_steps: Optional[int] = None) -> "TreeExtension":
         """One batched extension of ``tree`` towards ``targets`` [B, D] (pmp_tree_extend): nearest node, multi-world
-        edge check, append of the last safe configuration -- three kernels, no host synchronisation."""
+        edge check, append of the last safe configuration -- five kernels, no host synchronisation."""
         torch = self._torch()
         targets = self._prep(targets, "targets")
         B = targets.shape[0]
