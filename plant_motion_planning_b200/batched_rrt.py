@@ -131,3 +131,52 @@ def batched_rrt_connect(checker, start: Sequence[float], goal: Sequence[float], 
     return BatchedPlan([to_conf(q) for q in dense], [to_conf(q) for q in way], it,
                        (len(_np(t_start.download()["parent"])), len(_np(t_goal.download()["parent"]))),
                        2 * batch * it, log)
+
+
+@dataclass
+class RankedPlan:
+    path: List[Conf]                   # waypoints of the selected candidate (straight joint-space segments)
+    ee_path_cost: float                # sum of end-effector segment lengths (the reference's ranking key)
+    deflection_over_limit: np.ndarray  # [W]
+    total_cost: np.ndarray             # [W] ee_path_cost + alpha * over
+    candidates: List[dict]             # per restart: waypoints, valid, ee_path_cost, over, seed
+
+
+def batched_restarts(checker, start: Sequence[float], goal: Sequence[float], *, restarts: int = 8, batch: int = 256,
+                     max_iterations: int = 200, smooth_rounds: int = 10, proposals: int = 256, seed: int = 0,
+                     alpha: Optional[float] = None) -> Optional[RankedPlan]:
+    """random_restarts + smoothing + forward re-check + end-effector-length selection
+    (motion_planners/motion_planners/meta.py:188-267; cost terms of Command.execute_multi_world,
+    pybullet_tools/kuka_primitives.py:467-521) in batched form: ``restarts`` independent batched RRT-Connect runs,
+    each shortened by the batched smoother, then ONE pmp_validate_edges launch over every segment of every candidate
+    gives the forward re-check (first_hit >= n_steps on all segments), the end-effector path length and the
+    deflection-over-limit of all candidates at once.  The valid candidate with the shortest end-effector path wins
+    (the reference's ranking key)."""
+    from . import birrt, planner_fns as F
+    distance_fn = F.get_distance_fn(checker.robot)
+    cands = []
+    for r in range(restarts):
+        plan = batched_rrt_connect(checker, start, goal, batch=batch, max_iterations=max_iterations, seed=seed + r)
+        if plan is None:
+            continue
+        way = birrt.smooth_path_batched(checker, plan.waypoints, distance_fn, rounds=smooth_rounds, proposals=proposals,
+                                        seed=seed + r, gate=False)
+        cands.append({"seed": seed + r, "waypoints": way, "iterations": plan.iterations})
+    if not cands:
+        return None
+    q0 = np.concatenate([np.asarray(c["waypoints"][:-1], dtype=np.float32) for c in cands])
+    q1 = np.concatenate([np.asarray(c["waypoints"][1:], dtype=np.float32) for c in cands])
+    owner = np.concatenate([np.full(len(c["waypoints"]) - 1, k) for k, c in enumerate(cands)])
+    out = checker.validate_edges_host(q0, q1)
+    ok_seg = out["first_hit"] >= out["n_steps"]
+    a = float(checker.config.alpha if alpha is None else alpha)
+    for k, c in enumerate(cands):
+        m = owner == k
+        c["valid"] = bool(ok_seg[m].all())
+        c["ee_path_cost"] = float(out["ee_len"][m].astype(np.float64).sum())
+        c["over"] = out["over_limit"][m].astype(np.float64).sum(axis=0)
+    valid = [c for c in cands if c["valid"]]
+    if not valid:
+        return None
+    best = min(valid, key=lambda c: c["ee_path_cost"])
+    return RankedPlan(best["waypoints"], best["ee_path_cost"], best["over"], best["ee_path_cost"] + a * best["over"], cands)

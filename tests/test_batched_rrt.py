@@ -281,3 +281,51 @@ def test_extend_many_equals_per_edge_gate_replay():
         assert first.tolist() == want
         assert np.random.rand() == after
         assert out["exceed_mask"].any() and (np.asarray(want) < np.minimum(n, cap)).any() and (np.asarray(want) >= n).any()
+
+
+def test_batched_restarts_select_the_shortest_valid_candidate():
+    """batched_restarts ranks all smoothed candidates with one edge-batch evaluation; the winner is valid under the
+    oracle, its cost report equals env.path_cost's (Command.execute_multi_world's totals) and no valid candidate has
+    a shorter end-effector path."""
+    from plant_motion_planning_b200.batched_rrt import batched_restarts
+    from plant_motion_planning_b200.env import MultiPlantWorld
+    robot = load_iiwa14()
+    worlds, cfg = S.script_worlds("multi_world_avoid_all")
+    ec = EdgeCheckConfig(deflection_limit=cfg["deflection_limit"], mode=cfg["mode"])
+    ck = OracleChecker(robot, worlds, ec)
+    res = batched_restarts(ck, S.START, S.GOAL, restarts=3, batch=16, max_iterations=40, smooth_rounds=4, proposals=32)
+    assert res is not None and len(res.candidates) >= 2
+    assert np.allclose(res.path[0], S.START) and np.allclose(res.path[-1], S.GOAL, atol=1e-6)
+    assert res.ee_path_cost == min(c["ee_path_cost"] for c in res.candidates if c["valid"])
+    raw = batched_rrt_connect(ck, S.START, S.GOAL, batch=16, max_iterations=40, seed=0)
+    dist = F.get_distance_fn(robot)
+    length = lambda p: sum(dist(a, b) for a, b in zip(p[:-1], p[1:]))
+    assert length(res.candidates[0]["waypoints"]) <= length(raw.waypoints) + 1e-9       # smoothing never lengthens
+    # the same totals from the facade's execute report over the dense step sequence of the winner
+    env = MultiPlantWorld(cfg["xs"], cfg["ys"], cfg["deflection_limit"], worlds=worlds, avoid_all=cfg["avoid_all"],
+                          robot=robot, checker_factory=lambda r, w, c: ck)
+    ext = F.get_extend_fn(robot)
+    dense = [q for a, b in zip(res.path[:-1], res.path[1:]) for q in ext(a, b)]
+    ee_len, over, total = env.path_cost(res.path[0], dense)
+    assert abs(ee_len - res.ee_path_cost) <= 1e-4
+    assert np.allclose(over, res.deflection_over_limit, atol=1e-3) and np.allclose(total, res.total_cost, atol=1e-3)
+
+
+@pytest.mark.gpu
+def test_batched_restarts_on_gpu(gpu):
+    from plant_motion_planning_b200 import EdgeChecker
+    from plant_motion_planning_b200.batched_rrt import batched_restarts
+    robot = load_iiwa14()
+    worlds, cfg = S.script_worlds("multi_world_avoid_all")
+    ec = EdgeCheckConfig(deflection_limit=cfg["deflection_limit"], mode=cfg["mode"])
+    chk = EdgeChecker(robot, worlds, ec)
+    res = batched_restarts(chk, S.START, S.GOAL, restarts=6, batch=128, max_iterations=60)
+    assert res is not None and sum(c["valid"] for c in res.candidates) >= 1
+    assert res.ee_path_cost == min(c["ee_path_cost"] for c in res.candidates if c["valid"])
+    # forward re-check of the winner by the oracle: every step of every segment is free
+    ext = F.get_extend_fn(robot)
+    dense = np.asarray([q for a, b in zip(res.path[:-1], res.path[1:]) for q in ext(a, b)], dtype=np.float32)
+    fl = OracleChecker(robot, worlds, ec).check_configs_host(dense, detail=False)["flags"]
+    assert fl.mean() <= 0.005
+    again = batched_restarts(chk, S.START, S.GOAL, restarts=6, batch=128, max_iterations=60)
+    assert again.path == res.path and again.ee_path_cost == res.ee_path_cost

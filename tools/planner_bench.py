@@ -63,6 +63,12 @@ def main():
                                        "edges_validated": plan.edges_validated if plan else None,
                                        "path_configs": len(plan.path) if plan else None,
                                        "waypoints": len(plan.waypoints) if plan else None}
+        from plant_motion_planning_b200.batched_rrt import batched_restarts
+        t, ranked = timed(lambda: batched_restarts(chk, START, GOAL, restarts=8, batch=256, max_iterations=300), repeats=2)
+        row["batched_restarts_8"] = {"seconds": t, "candidates": len(ranked.candidates) if ranked else 0,
+                                     "valid": sum(c["valid"] for c in ranked.candidates) if ranked else 0,
+                                     "ee_path_cost": ranked.ee_path_cost if ranked else None,
+                                     "waypoints": len(ranked.path) if ranked else None}
         # the reference-order driver on the same checker (sequential, one launch per extension; gate replayed on the host)
         xs = list(range(len(worlds)))
         env = MultiPlantWorld(xs, [0], limit, worlds=worlds, avoid_all=avoid, checker_factory=lambda r, w, c: chk,
