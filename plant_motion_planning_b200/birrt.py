@@ -287,17 +287,26 @@ def smooth_path_batched(checker, path: Sequence[Conf], distance_fn, rounds: int 
     masks); ``gate=False`` treats every exceeded deflection as a violation and uses the first-violation-only call."""
     rng = np.random.RandomState(seed)
     way = [np.asarray(w, dtype=np.float64) for w in waypoints_from_path(path)]
+    circ = np.asarray(getattr(getattr(checker, "robot", None), "circular", np.zeros(len(way[0]), dtype=bool)), dtype=bool)
+
+    def dist(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        """get_distance_fn (weights 1, 2-norm of difference_fn) for arrays of configurations."""
+        d = b - a
+        if circ.any():
+            d = np.where(circ, (d + np.pi) % (2 * np.pi) - np.pi, d)
+        return np.sqrt(np.sum(d * d, axis=-1))
+
     for _ in range(rounds):
         if len(way) <= 2:
             break
-        seg_len = np.array([distance_fn(tuple(a), tuple(b)) for a, b in zip(way[:-1], way[1:])])
+        W = np.stack(way)
+        seg_len = dist(W[:-1], W[1:])
         cum = np.concatenate([[0.0], np.cumsum(seg_len)])
         s = np.sort(rng.uniform(0.0, cum[-1], size=(proposals, 2)), axis=1)
         seg = np.clip(np.searchsorted(cum, s, side="right") - 1, 0, len(seg_len) - 1)
         frac = (s - cum[seg]) / np.maximum(seg_len[seg], 1e-300)
-        W = np.stack(way)
         P = W[seg] * (1 - frac[..., None]) + W[seg + 1] * frac[..., None]          # [proposals, 2, D]
-        direct = np.array([distance_fn(tuple(P[k, 0]), tuple(P[k, 1])) for k in range(proposals)])
+        direct = dist(P[:, 0], P[:, 1])
         gain = (s[:, 1] - s[:, 0]) - direct
         ok = (seg[:, 0] != seg[:, 1]) & (gain > 1e-9)
         if not ok.any():
