@@ -31,6 +31,7 @@ struct pmp_ctx {
     pmp_launch_info info;
     // scratch for the host-buffer entry points
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;        // second stream of the chunked host entry point (copies overlap kernels)
     void* d_scratch = nullptr;
     size_t scratch_bytes = 0;
     // pinned staging for small host calls (the per-step collision_fn adapter): one H2D, one kernel, one D2H
@@ -84,6 +85,11 @@ extern "C" int pmp_create(pmp_ctx** out, int device) {
         delete ctx;
         return fail(nullptr, PMP_E_CUDA, "cudaStreamCreate failed");
     }
+    if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return fail(nullptr, PMP_E_CUDA, "cudaStreamCreate failed");
+    }
     *out = ctx;
     return PMP_OK;
 }
@@ -100,6 +106,7 @@ extern "C" int pmp_destroy(pmp_ctx* ctx) {
     cudaFree(ctx->d_robot); cudaFree(ctx->d_links); cudaFree(ctx->d_scratch); cudaFree(ctx->d_tree_scratch); cudaFree(ctx->d_work_counter);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     delete ctx;
     return PMP_OK;
 }
@@ -251,9 +258,22 @@ static void pads(pmp_ctx* ctx, int& apad, int& nspad) {
     nspad = ctx->n_slots <= 1 ? 1 : (ctx->n_slots <= 2 ? 2 : 4);
 }
 
+static int validate_edges_impl(pmp_ctx* ctx, const float* q0, const float* q1, int32_t E, int32_t max_steps,
+                               int32_t backward, int32_t* first_hit, int32_t* n_steps, float* max_defl, float* over,
+                               float* ee_len, float* cost, uint32_t* rigid_mask, uint32_t* exceed_mask, void* stream,
+                               int32_t edge_base);
+
 extern "C" int pmp_validate_edges(pmp_ctx* ctx, const float* q0, const float* q1, int32_t E, int32_t max_steps,
                                   int32_t backward, int32_t* first_hit, int32_t* n_steps, float* max_defl, float* over,
                                   float* ee_len, float* cost, uint32_t* rigid_mask, uint32_t* exceed_mask, void* stream) {
+    return validate_edges_impl(ctx, q0, q1, E, max_steps, backward, first_hit, n_steps, max_defl, over, ee_len, cost,
+                               rigid_mask, exceed_mask, stream, 0);
+}
+
+static int validate_edges_impl(pmp_ctx* ctx, const float* q0, const float* q1, int32_t E, int32_t max_steps,
+                               int32_t backward, int32_t* first_hit, int32_t* n_steps, float* max_defl, float* over,
+                               float* ee_len, float* cost, uint32_t* rigid_mask, uint32_t* exceed_mask, void* stream,
+                               int32_t edge_base) {
     int rc = ready(ctx);
     if (rc) return rc;
     if (E < 0 || max_steps < 1) return fail(ctx, PMP_E_INVALID, "bad E / max_steps");
@@ -264,7 +284,7 @@ extern "C" int pmp_validate_edges(pmp_ctx* ctx, const float* q0, const float* q1
     a.robot = ctx->d_robot; a.stems = ctx->d_stems; a.n_stems = ctx->d_nstems; a.boxes = ctx->d_boxes;
     a.n_boxes = ctx->d_nboxes; a.prm = ctx->prm; a.q0 = q0; a.q1 = q1; a.E = E; a.max_steps = max_steps;
     a.backward = backward ? 1 : 0; a.first_hit = first_hit; a.n_steps = n_steps; a.max_defl = max_defl; a.over = over;
-    a.ee_len = ee_len; a.cost = cost; a.rigid_mask = rigid_mask; a.exceed_mask = exceed_mask;
+    a.ee_len = ee_len; a.cost = cost; a.rigid_mask = rigid_mask; a.exceed_mask = exceed_mask; a.edge_base = edge_base;
     if (!ctx->d_work_counter) CK(cudaMalloc(&ctx->d_work_counter, 64 * sizeof(int32_t)));
     a.work_counter = ctx->d_work_counter + (ctx->work_slot++ & 63u);   // launches in flight on other streams keep theirs
     CK(cudaMemsetAsync(a.work_counter, 0, sizeof(int32_t), (cudaStream_t)stream));
@@ -384,36 +404,49 @@ extern "C" int pmp_validate_edges_host(pmp_ctx* ctx, const float* q0, const floa
     if (!q0 || !q1 || !first_hit || !n_steps) return fail(ctx, PMP_E_INVALID, "q0, q1, first_hit, n_steps are required");
     CK(cudaSetDevice(ctx->device));
     const int D = ctx->h_robot.dof, W = ctx->n_worlds, C = (max_steps + 31) / 32;
-    const size_t bq = up256(sizeof(float) * (size_t)E * D), bi = up256(sizeof(int32_t) * (size_t)E),
-                 bw = up256(sizeof(float) * (size_t)E * W), bm = up256(sizeof(uint32_t) * (size_t)E * W * C);
-    size_t total = 2 * bq + 2 * bi + (max_defl ? bw : 0) + (over ? bw : 0) + (ee_len ? bi : 0) + (cost ? bi : 0) +
-                   (rigid_mask ? bm : 0) + (exceed_mask ? bm : 0);
-    rc = ensure_scratch(ctx, total);
+    // Large batches go through in chunks on two streams, so that the copies of one chunk (inputs in, per-world
+    // outputs back: up to 8 W + 16 bytes per edge) overlap the kernel of the other.
+    const int n_chunks = E >= (1 << 16) ? 8 : 1;
+    const int CE = (E + n_chunks - 1) / n_chunks;               // edges per chunk
+    const size_t bq = up256(sizeof(float) * (size_t)CE * D), bi = up256(sizeof(int32_t) * (size_t)CE),
+                 bw = up256(sizeof(float) * (size_t)CE * W), bm = up256(sizeof(uint32_t) * (size_t)CE * W * C);
+    const size_t per = 2 * bq + 2 * bi + (max_defl ? bw : 0) + (over ? bw : 0) + (ee_len ? bi : 0) + (cost ? bi : 0) +
+                       (rigid_mask ? bm : 0) + (exceed_mask ? bm : 0);
+    rc = ensure_scratch(ctx, (n_chunks > 1 ? 2 : 1) * per);
     if (rc) return rc;
-    char* p = (char*)ctx->d_scratch;
-    auto take = [&](size_t b) { char* r = p; p += b; return r; };
-    float* dq0 = (float*)take(bq); float* dq1 = (float*)take(bq);
-    int32_t* dfh = (int32_t*)take(bi); int32_t* dns = (int32_t*)take(bi);
-    float* dmd = max_defl ? (float*)take(bw) : nullptr;
-    float* dov = over ? (float*)take(bw) : nullptr;
-    float* del = ee_len ? (float*)take(bi) : nullptr;
-    float* dco = cost ? (float*)take(bi) : nullptr;
-    uint32_t* drm = rigid_mask ? (uint32_t*)take(bm) : nullptr;
-    uint32_t* dxm = exceed_mask ? (uint32_t*)take(bm) : nullptr;
-    cudaStream_t st = ctx->stream;
-    CK(cudaMemcpyAsync(dq0, q0, sizeof(float) * (size_t)E * D, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(dq1, q1, sizeof(float) * (size_t)E * D, cudaMemcpyHostToDevice, st));
-    rc = pmp_validate_edges(ctx, dq0, dq1, E, max_steps, backward, dfh, dns, dmd, dov, del, dco, drm, dxm, st);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(first_hit, dfh, sizeof(int32_t) * (size_t)E, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(n_steps, dns, sizeof(int32_t) * (size_t)E, cudaMemcpyDeviceToHost, st));
-    if (max_defl) CK(cudaMemcpyAsync(max_defl, dmd, sizeof(float) * (size_t)E * W, cudaMemcpyDeviceToHost, st));
-    if (over) CK(cudaMemcpyAsync(over, dov, sizeof(float) * (size_t)E * W, cudaMemcpyDeviceToHost, st));
-    if (ee_len) CK(cudaMemcpyAsync(ee_len, del, sizeof(float) * (size_t)E, cudaMemcpyDeviceToHost, st));
-    if (cost) CK(cudaMemcpyAsync(cost, dco, sizeof(float) * (size_t)E, cudaMemcpyDeviceToHost, st));
-    if (rigid_mask) CK(cudaMemcpyAsync(rigid_mask, drm, sizeof(uint32_t) * (size_t)E * W * C, cudaMemcpyDeviceToHost, st));
-    if (exceed_mask) CK(cudaMemcpyAsync(exceed_mask, dxm, sizeof(uint32_t) * (size_t)E * W * C, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    for (int c = 0; c < n_chunks; ++c) {
+        const int e0 = c * CE;
+        const int ne = E - e0 < CE ? E - e0 : CE;
+        if (ne <= 0) break;
+        cudaStream_t st = (c & 1) ? ctx->stream2 : ctx->stream;
+        char* p = (char*)ctx->d_scratch + (size_t)(c & 1) * per;
+        auto take = [&](size_t b) { char* r = p; p += b; return r; };
+        float* dq0 = (float*)take(bq); float* dq1 = (float*)take(bq);
+        int32_t* dfh = (int32_t*)take(bi); int32_t* dns = (int32_t*)take(bi);
+        float* dmd = max_defl ? (float*)take(bw) : nullptr;
+        float* dov = over ? (float*)take(bw) : nullptr;
+        float* del = ee_len ? (float*)take(bi) : nullptr;
+        float* dco = cost ? (float*)take(bi) : nullptr;
+        uint32_t* drm = rigid_mask ? (uint32_t*)take(bm) : nullptr;
+        uint32_t* dxm = exceed_mask ? (uint32_t*)take(bm) : nullptr;
+        const size_t o1 = (size_t)e0, oD = (size_t)e0 * D, oW = (size_t)e0 * W, oM = (size_t)e0 * W * C;
+        CK(cudaMemcpyAsync(dq0, q0 + oD, sizeof(float) * (size_t)ne * D, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dq1, q1 + oD, sizeof(float) * (size_t)ne * D, cudaMemcpyHostToDevice, st));
+        rc = validate_edges_impl(ctx, dq0, dq1, ne, max_steps, backward, dfh, dns, dmd, dov, del, dco, drm, dxm, st, e0);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(first_hit + o1, dfh, sizeof(int32_t) * (size_t)ne, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(n_steps + o1, dns, sizeof(int32_t) * (size_t)ne, cudaMemcpyDeviceToHost, st));
+        if (max_defl) CK(cudaMemcpyAsync(max_defl + oW, dmd, sizeof(float) * (size_t)ne * W, cudaMemcpyDeviceToHost, st));
+        if (over) CK(cudaMemcpyAsync(over + oW, dov, sizeof(float) * (size_t)ne * W, cudaMemcpyDeviceToHost, st));
+        if (ee_len) CK(cudaMemcpyAsync(ee_len + o1, del, sizeof(float) * (size_t)ne, cudaMemcpyDeviceToHost, st));
+        if (cost) CK(cudaMemcpyAsync(cost + o1, dco, sizeof(float) * (size_t)ne, cudaMemcpyDeviceToHost, st));
+        if (rigid_mask)
+            CK(cudaMemcpyAsync(rigid_mask + oM, drm, sizeof(uint32_t) * (size_t)ne * W * C, cudaMemcpyDeviceToHost, st));
+        if (exceed_mask)
+            CK(cudaMemcpyAsync(exceed_mask + oM, dxm, sizeof(uint32_t) * (size_t)ne * W * C, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (n_chunks > 1) CK(cudaStreamSynchronize(ctx->stream2));
     return PMP_OK;
 }
 

@@ -480,6 +480,8 @@ struct PmpEdgeArgs {
     uint32_t* rigid_mask;      // [E, W, C] or null
     uint32_t* exceed_mask;     // [E, W, C] or null
     int32_t* work_counter;     // [1] next unclaimed edge (zeroed before the launch)
+    int32_t edge_base;         // index of edge 0 in the caller's batch (the host entry point launches in chunks);
+                               // enters the on-device gate's hash so that chunking does not change decisions
 };
 
 // Edge-batch kernel.  Persistent CTAs; warp = edge, lane = step.
@@ -663,7 +665,7 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
                 if (prm.gate_threshold != 0u && xm != 0u) {
                     // on-device stand-in for `rand() < 0.95` (pybullet_tools/utils.py:3843): counter-based, so the
                     // decision of (edge, step, world) does not depend on evaluation order
-                    const bool pass = pmp_gate_hash(prm.gate_seed, (uint32_t)e, (uint32_t)i, (uint32_t)w) < prm.gate_threshold;
+                    const bool pass = pmp_gate_hash(prm.gate_seed, (uint32_t)(e + args.edge_base), (uint32_t)i, (uint32_t)w) < prm.gate_threshold;
                     xg = __ballot_sync(PMP_FULL, live && u.exceeded && pass);
                 }
                 viol |= rm | xg;

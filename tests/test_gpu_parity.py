@@ -284,6 +284,23 @@ def test_host_api_equals_device_api(ctx):
                  ("over_limit", dev.over_limit), ("ee_len", dev.ee_len), ("cost", dev.cost)):
         assert np.array_equal(host[k], t.cpu().numpy()), k
     assert np.array_equal(host["rigid_mask"], dev.rigid_mask.cpu().numpy().view(np.uint32))
+    # large batches take the chunked two-stream route of the host entry point: same bits, also with the on-device gate
+    # (whose hash sees the index of the edge in the caller's batch, not in the chunk)
+    from plant_motion_planning_b200.workloads import synthetic_edges
+    b0, b1 = synthetic_edges(ctx["model"], (1 << 16) + 37, seed=3, steps=12)
+    try:
+        chk.set_config(device_gate_seed=11, deflection_limit=0.05, max_steps=32)
+        dev = chk.validate_edges(torch.from_numpy(b0), torch.from_numpy(b1), want_masks=True)
+        host = chk.validate_edges_host(b0, b1, want_masks=True)
+        for k, t in (("first_hit", dev.first_hit), ("n_steps", dev.n_steps), ("max_deflection", dev.max_deflection),
+                     ("over_limit", dev.over_limit), ("ee_len", dev.ee_len), ("cost", dev.cost)):
+            assert np.array_equal(host[k], t.cpu().numpy()), k
+        assert np.array_equal(host["exceed_mask"], dev.exceed_mask.cpu().numpy().view(np.uint32))
+        assert host["exceed_mask"].any()
+        fast = chk.validate_edges_host(b0, b1, first_hit_only=True)
+        assert np.array_equal(fast["first_hit"], host["first_hit"])
+    finally:
+        chk.set_config(device_gate_seed=None, deflection_limit=0.30, max_steps=320)
     hc = chk.check_configs_host(ctx["Q"][:100])
     dc = chk.check_configs(torch.from_numpy(ctx["Q"][:100]))
     assert np.array_equal(hc["flags"], dc.flags.cpu().numpy())
