@@ -302,7 +302,20 @@ static int validate_edges_impl(pmp_ctx* ctx, const float* q0, const float* q1, i
                (size_t)warps * PMP_MAX_DOF * (sizeof(double) + 3 * sizeof(float)) +
                (size_t)warps * 3 * apad * 33 * sizeof(float);          // swept-bound staging tile per warp
     };
-    int wpc = (E + ctx->sm_count - 1) / ctx->sm_count;      // warps (= edges in flight) per CTA
+    // a call that asks for nothing but first_hit / n_steps gets the early-stopping instantiation; when such a batch is
+    // too small to fill the machine with one warp per edge, the worlds of an edge are split over several warps
+    const bool first_only = !max_defl && !over && !ee_len && !cost && !rigid_mask && !exceed_mask;
+    int split = 1;
+    if (first_only && W > 1) {
+        const int target = ctx->sm_count * 16;
+        if (E < target) split = (target + E - 1) / E;
+        if (split > 16) split = 16;
+        if (split > W) split = W;
+    }
+    a.world_split = split;
+    const int items = E * split;
+    if (split > 1) CK(cudaMemsetAsync(first_hit, 0x7f, sizeof(int32_t) * (size_t)E, (cudaStream_t)stream));
+    int wpc = (items + ctx->sm_count - 1) / ctx->sm_count;      // warps (= work items in flight) per CTA
     if (wpc > 16) wpc = 16;
     if (wpc < 1) wpc = 1;
     // shared memory: robot table + per-warp staging always; world tables when they fit next to them.  A CTA of fewer
@@ -319,13 +332,11 @@ static int validate_edges_impl(pmp_ctx* ctx, const float* q0, const float* q1, i
     if (smem_for(block, false) > lim) return fail(ctx, PMP_E_INVALID, "shared memory budget exceeded for this block size");
     const size_t smem = smem_for(block, wsmem);
     const int warps = block / 32;
-    int grid = (E + warps - 1) / warps;
+    int grid = (items + warps - 1) / warps;
     const int cap = ctx->sm_count * per_sm;
     if (grid > cap) grid = cap;
     cudaError_t err;
     int regs = 0;
-    // a call that asks for nothing but first_hit / n_steps gets the early-stopping instantiation
-    const bool first_only = !max_defl && !over && !ee_len && !cost && !rigid_mask && !exceed_mask;
     cudaStream_t st_ = (cudaStream_t)stream;
     if (first_only) {
         if (apad == 12) err = pmp_launch_edge_first_a12(nspad, a, wsmem, grid, block, smem, st_, &regs);

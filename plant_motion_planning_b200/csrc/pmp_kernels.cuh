@@ -480,6 +480,8 @@ struct PmpEdgeArgs {
     uint32_t* rigid_mask;      // [E, W, C] or null
     uint32_t* exceed_mask;     // [E, W, C] or null
     int32_t* work_counter;     // [1] next unclaimed edge (zeroed before the launch)
+    int32_t world_split;       // first-violation-only launches of small batches: warps per edge, each taking the
+                               // worlds w = part, part + split, ... (1 otherwise)
     int32_t edge_base;         // index of edge 0 in the caller's batch (the host entry point launches in chunks);
                                // enters the on-device gate's hash so that chunking does not change decisions
 };
@@ -525,11 +527,17 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
 
     // Edges are claimed one at a time from a global counter: their cost varies by an order of magnitude (free space
     // vs. a sweep through a plant), and with a static stride the last warps of every SM would run alone.
+    // Small first-violation-only batches (a planner's few hundred proposals) would leave most SMs idle with one warp
+    // per edge; there the worlds of an edge are dealt round-robin to `world_split` warps, which combine their answers
+    // with atomicMin (first_hit is pre-set to a large value by the host glue).
+    const int split = FIRST ? args.world_split : 1;
+    const int n_items = args.E * split;
     for (;;) {
-        int e = 0;
-        if (lane == 0) e = atomicAdd(args.work_counter, 1);
-        e = __shfl_sync(PMP_FULL, e, 0);
-        if (e >= args.E) break;
+        int item = 0;
+        if (lane == 0) item = atomicAdd(args.work_counter, 1);
+        item = __shfl_sync(PMP_FULL, item, 0);
+        if (item >= n_items) break;
+        const int e = item / split, part = item - e * split;
         // ---- interpolation set-up: oracle num_steps / edge_configs (pybullet_tools/utils.py:3604-3676) ----
         __syncwarp();
         if (lane < D) {
@@ -564,6 +572,12 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
             pe[0] = e0[0]; pe[1] = e0[1]; pe[2] = e0[2];
         }
         for (int base = 0, chunk = 0; base < nc; base += 32, ++chunk) {
+            if (FIRST && split > 1 && chunk > 0) {
+                // another warp of this edge may already have found a violation before this chunk
+                int g = 0;
+                if (lane == 0) g = *reinterpret_cast<volatile int32_t*>(args.first_hit + e);
+                if (__shfl_sync(PMP_FULL, g, 0) < base) break;
+            }
             const int i = base + lane;
             bool live = i < nc;
             const int num = i + off;
@@ -649,7 +663,7 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
                 }
             };
             if (first_only && viol) retire(viol);
-            for (int w = 0; w < W; ++w) {
+            for (int w = part; w < W; w += split) {
                 if (first_only && retired_from == 0) break;
                 PmpUnitOut u;
                 u.plant_hit = false; u.exceeded = false; u.max_defl = 0.f; u.over = 0.f;
@@ -699,6 +713,13 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
                 if (args.rigid_mask) args.rigid_mask[o] = 0u;
                 if (args.exceed_mask) args.exceed_mask[o] = 0u;
             }
+        }
+        if (FIRST && split > 1) {
+            if (lane == 0) {
+                atomicMin(args.first_hit + e, first);
+                if (part == 0) args.n_steps[e] = n;
+            }
+            continue;
         }
         if (lane == 0) {
             args.first_hit[e] = first;
