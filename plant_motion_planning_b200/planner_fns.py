@@ -89,10 +89,13 @@ def get_refine_fn(robot, num_steps=0) -> Callable:
     num_steps = num_steps + 1
 
     def fn(q1, q2) -> Iterator[Tuple[float, ...]]:
-        q = q1
+        # the reference's `(1. / (num_steps - i)) * np.array(difference_fn(q2, q)) + q` element by element in Python
+        # floats: the same IEEE operations in the same order (bit-identical results, pinned by
+        # tests/golden/reference_planner_fns.json) without a numpy round trip per step
+        q = tuple(float(v) for v in q1)
         for i in range(num_steps):
-            positions = (1. / (num_steps - i)) * np.array(difference_fn(q2, q)) + q
-            q = tuple(positions)
+            c = 1. / (num_steps - i)
+            q = tuple(c * d + v for d, v in zip(difference_fn(q2, q), q))
             yield q
     return fn
 
