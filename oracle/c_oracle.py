@@ -72,7 +72,8 @@ class COracle:
                  native=False):
         self.lib = load(native)
         self.rt = pack_robot(robot, obstacles)
-        self.wt = pack_worlds(list(worlds), stem_radius)
+        from plant_motion_planning_b200.model.tables import WorldTables
+        self.wt = worlds if isinstance(worlds, WorldTables) else pack_worlds(list(worlds), stem_radius)
         t = self.rt
         d = _capi.RobotDesc()
         d.dof, d.n_spheres, d.n_links, d.n_fixed = t.dof, t.n_spheres, t.n_links, t.n_fixed

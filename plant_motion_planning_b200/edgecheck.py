@@ -126,9 +126,15 @@ class EdgeChecker:
         d.fixed_mask = _capi.uptr(t.fixed_mask)
         self._check(self._lib.pmp_set_robot(self._ctx, C.byref(d)), "pmp_set_robot")
 
-    def set_worlds(self, worlds: Sequence[PlantWorld]) -> None:
-        self.worlds: List[PlantWorld] = list(worlds)
-        wt: WorldTables = pack_worlds(self.worlds, self.config.stem_radius)
+    def set_worlds(self, worlds) -> None:
+        """``worlds``: PlantWorld objects, or ready-made WorldTables (model/batch_sampler.sample_world_tables for
+        large world counts)."""
+        if isinstance(worlds, WorldTables):
+            self.worlds = None
+            wt = worlds
+        else:
+            self.worlds = list(worlds)
+            wt = pack_worlds(self.worlds, self.config.stem_radius)
         self.world_tables = wt
         d = _capi.WorldDesc()
         d.n_worlds, d.max_stems, d.max_boxes, d.n_slots = wt.n_worlds, wt.max_stems, wt.max_boxes, wt.n_slots
@@ -153,6 +159,8 @@ class EdgeChecker:
         old = self.config
         self.config = replace(self.config, **changes)
         if self.config.stem_radius != old.stem_radius:
+            if self.worlds is None:
+                raise ValueError("worlds were given as tables: re-pack them with the new stem_radius and call set_worlds")
             self.set_worlds(self.worlds)
         self._push_params()
 
