@@ -55,6 +55,56 @@ __device__ __forceinline__ float pmp_rsqrt_ftz(float x) {
     return y;
 }
 
+// Packed FP32 pairs (sm_100: FADD2 / FMUL2 / FFMA2 do two IEEE float32 operations per lane in one issue slot; the
+// kernel is issue-bound, so the sphere loops below work on two arm spheres at a time).  A pair is a 64-bit register
+// pair; pmp_bc() broadcasts a scalar, which the assembler turns into the instruction's scalar-operand form.
+typedef unsigned long long pmp_f2;
+__device__ __forceinline__ pmp_f2 pmp_pk(float lo, float hi) {
+    pmp_f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ pmp_f2 pmp_bc(float v) { return pmp_pk(v, v); }
+__device__ __forceinline__ void pmp_upk(pmp_f2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ pmp_f2 pmp_fma2(pmp_f2 a, pmp_f2 b, pmp_f2 c) {
+    pmp_f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ pmp_f2 pmp_mul2(pmp_f2 a, pmp_f2 b) {
+    pmp_f2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ pmp_f2 pmp_add2(pmp_f2 a, pmp_f2 b) {
+    pmp_f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ pmp_f2 pmp_sub2(pmp_f2 a, pmp_f2 b) {
+    pmp_f2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ float pmp_hsum2(pmp_f2 v) {
+    float lo, hi;
+    pmp_upk(v, lo, hi);
+    return lo + hi;
+}
+
+// Sphere centres as pairs: cp[i][k] = (c[2i][k], c[2i+1][k]).
+template <int A>
+__device__ __forceinline__ void pmp_pack_centres(const float (&c)[A][3], pmp_f2 (&cp)[A / 2][3]) {
+#pragma unroll
+    for (int a = 0; a < A; a += 2) {
+        cp[a >> 1][0] = pmp_pk(c[a][0], c[a + 1][0]);
+        cp[a >> 1][1] = pmp_pk(c[a][1], c[a + 1][1]);
+        cp[a >> 1][2] = pmp_pk(c[a][2], c[a + 1][2]);
+    }
+}
+
 // Sphere (centre c, radius r) against a static primitive: oracle _prim_hit.
 __device__ __forceinline__ bool pmp_prim_hit(int kind, const float* __restrict__ R, const float* __restrict__ t,
                                              const float* __restrict__ h, float cx, float cy, float cz, float r) {
@@ -174,11 +224,14 @@ struct PmpSweptBound {
     float x, y, z, r;    // r < 0: this lane carries no bound
 };
 
-template <int A, int NSLOT, bool DETAIL, bool CULL>
+// CPF: functor (pair, coordinate) -> the centres of arm spheres 2 pair and 2 pair + 1 as one packed pair.  The edge
+// kernel serves them from its per-warp shared-memory tile (one LDS.64 each), which keeps 3 A registers free for the
+// packed arithmetic; the configuration kernel from registers.
+template <int A, int NSLOT, bool DETAIL, bool CULL, class CPF>
 __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ wt, int n_stems,
                                                       const float* __restrict__ boxes, int n_boxes,
                                                       const PmpRobotTab& rt, const PmpKernelParams& prm,
-                                                      const float (&c)[A][3], float* __restrict__ defl_out,
+                                                      CPF cpf, float* __restrict__ defl_out,
                                                       float* __restrict__ theta_out,
                                                       const PmpSweptBound bound = PmpSweptBound{0.f, 0.f, 0.f, -1.f}) {
     PmpUnitOut out;
@@ -266,14 +319,21 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
         bool touch = false;
         {
             const float ux = Rv[2], uy = Rv[5], uz = Rv[8];
+            static_assert(A % 2 == 0, "sphere loops work on pairs");
 #pragma unroll
-            for (int a = 0; a < A; ++a) {
-                const float wx = c[a][0] - tv[0], wy = c[a][1] - tv[1], wz = c[a][2] - tv[2];
-                const float tau = pmp_clamp(fmaf(wx, ux, fmaf(wy, uy, wz * uz)), z0, z1);
-                const float dx = fmaf(-tau, ux, wx), dy = fmaf(-tau, uy, wy), dz = fmaf(-tau, uz, wz);
-                const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                const float rr = rt.sph_radius[a] + rad;
-                touch |= d2 < rr * rr;
+            for (int a = 0; a < A; a += 2) {          // spheres a (low half) and a + 1 (high half)
+                const pmp_f2 wx = pmp_sub2(cpf(a >> 1, 0), pmp_bc(tv[0]));
+                const pmp_f2 wy = pmp_sub2(cpf(a >> 1, 1), pmp_bc(tv[1]));
+                const pmp_f2 wz = pmp_sub2(cpf(a >> 1, 2), pmp_bc(tv[2]));
+                float t0, t1;
+                pmp_upk(pmp_fma2(wx, pmp_bc(ux), pmp_fma2(wy, pmp_bc(uy), pmp_mul2(wz, pmp_bc(uz)))), t0, t1);
+                const pmp_f2 tau = pmp_pk(pmp_clamp(t0, z0, z1), pmp_clamp(t1, z0, z1));
+                const pmp_f2 dx = pmp_fma2(tau, pmp_bc(-ux), wx), dy = pmp_fma2(tau, pmp_bc(-uy), wy),
+                             dz = pmp_fma2(tau, pmp_bc(-uz), wz);
+                float e0, e1;
+                pmp_upk(pmp_fma2(dx, dx, pmp_fma2(dy, dy, pmp_mul2(dz, dz))), e0, e1);
+                const float rr0 = rt.sph_radius[a] + rad, rr1 = rt.sph_radius[a + 1] + rad;
+                touch |= (e0 < rr0 * rr0) | (e1 < rr1 * rr1);
             }
         }
         float thx = 0.f, thy = 0.f;
@@ -289,28 +349,44 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
                 const float axx = Rv[0], axy = Rv[3], axz = Rv[6];
                 float ayx, ayy, ayz;
                 pmp_mat_vec(Rv, 0.f, cx, sx, ayx, ayy, ayz);
-                const float bxx = axy * uz - axz * uy, bxy = axz * ux - axx * uz, bxz = axx * uy - axy * ux;
-                const float byx = ayy * uz - ayz * uy, byy = ayz * ux - ayx * uz, byz = ayx * uy - ayy * ux;
-                float Hxx = 0.f, Hxy = 0.f, Hyy = 0.f, gx = 0.f, gy = 0.f, S = 0.f;
+                // n b = u x a (the negated cross products a x u): the sign of sc = -tau / dist is folded into them
+                const float nbxx = axz * uy - axy * uz, nbxy = axx * uz - axz * ux, nbxz = axy * ux - axx * uy;
+                const float nbyx = ayz * uy - ayy * uz, nbyy = ayx * uz - ayz * ux, nbyz = ayy * ux - ayx * uy;
+                // accumulators: low half = even spheres, high half = odd spheres
+                pmp_f2 Hxx2 = pmp_bc(0.f), Hxy2 = pmp_bc(0.f), Hyy2 = pmp_bc(0.f), gx2 = pmp_bc(0.f), gy2 = pmp_bc(0.f),
+                       S2 = pmp_bc(0.f);
 #pragma unroll
-                for (int a = 0; a < A; ++a) {
-                    const float wx = c[a][0] - tv[0], wy = c[a][1] - tv[1], wz = c[a][2] - tv[2];
-                    const float tau = pmp_clamp(fmaf(wx, ux, fmaf(wy, uy, wz * uz)), z0, z1);
-                    const float dx = fmaf(-tau, ux, wx), dy = fmaf(-tau, uy, wy), dz = fmaf(-tau, uz, wz);
-                    const float d2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, 1e-24f)));   // > 0: rsqrt stays finite
-                    const float inv = pmp_rsqrt_ftz(d2);
-                    const float pen = fmaxf((rt.sph_radius[a] + rad) - d2 * inv, 0.f);
-                    const float sc = -tau * inv;
-                    const float Jx = sc * fmaf(dx, bxx, fmaf(dy, bxy, dz * bxz));
-                    const float Jy = sc * fmaf(dx, byx, fmaf(dy, byy, dz * byz));
-                    const float pJx = pen * Jx, pJy = pen * Jy;
-                    Hxx = fmaf(pJx, Jx, Hxx);
-                    Hxy = fmaf(pJx, Jy, Hxy);
-                    Hyy = fmaf(pJy, Jy, Hyy);
-                    gx = fmaf(pen, pJx, gx);
-                    gy = fmaf(pen, pJy, gy);
-                    S += pen;
+                for (int a = 0; a < A; a += 2) {
+                    const pmp_f2 wx = pmp_sub2(cpf(a >> 1, 0), pmp_bc(tv[0]));
+                    const pmp_f2 wy = pmp_sub2(cpf(a >> 1, 1), pmp_bc(tv[1]));
+                    const pmp_f2 wz = pmp_sub2(cpf(a >> 1, 2), pmp_bc(tv[2]));
+                    float t0, t1;
+                    pmp_upk(pmp_fma2(wx, pmp_bc(ux), pmp_fma2(wy, pmp_bc(uy), pmp_mul2(wz, pmp_bc(uz)))), t0, t1);
+                    const pmp_f2 tau = pmp_pk(pmp_clamp(t0, z0, z1), pmp_clamp(t1, z0, z1));
+                    const pmp_f2 dx = pmp_fma2(tau, pmp_bc(-ux), wx), dy = pmp_fma2(tau, pmp_bc(-uy), wy),
+                                 dz = pmp_fma2(tau, pmp_bc(-uz), wz);
+                    // + 1e-24 > 0: rsqrt stays finite
+                    const pmp_f2 d2 = pmp_fma2(dx, dx, pmp_fma2(dy, dy, pmp_fma2(dz, dz, pmp_bc(1e-24f))));
+                    float e0, e1;
+                    pmp_upk(d2, e0, e1);
+                    const pmp_f2 inv = pmp_pk(pmp_rsqrt_ftz(e0), pmp_rsqrt_ftz(e1));
+                    // d2 * inv - (r_a + rad) = -(penetration)
+                    float n0, n1;
+                    pmp_upk(pmp_fma2(d2, inv, pmp_pk(-(rt.sph_radius[a] + rad), -(rt.sph_radius[a + 1] + rad))), n0, n1);
+                    const pmp_f2 pen = pmp_pk(fmaxf(-n0, 0.f), fmaxf(-n1, 0.f));
+                    const pmp_f2 sc = pmp_mul2(tau, inv);
+                    const pmp_f2 Jx = pmp_mul2(sc, pmp_fma2(dx, pmp_bc(nbxx), pmp_fma2(dy, pmp_bc(nbxy), pmp_mul2(dz, pmp_bc(nbxz)))));
+                    const pmp_f2 Jy = pmp_mul2(sc, pmp_fma2(dx, pmp_bc(nbyx), pmp_fma2(dy, pmp_bc(nbyy), pmp_mul2(dz, pmp_bc(nbyz)))));
+                    const pmp_f2 pJx = pmp_mul2(pen, Jx), pJy = pmp_mul2(pen, Jy);
+                    Hxx2 = pmp_fma2(pJx, Jx, Hxx2);
+                    Hxy2 = pmp_fma2(pJx, Jy, Hxy2);
+                    Hyy2 = pmp_fma2(pJy, Jy, Hyy2);
+                    gx2 = pmp_fma2(pen, pJx, gx2);
+                    gy2 = pmp_fma2(pen, pJy, gy2);
+                    S2 = pmp_add2(S2, pen);
                 }
+                const float Hxx = pmp_hsum2(Hxx2), Hxy = pmp_hsum2(Hxy2), Hyy = pmp_hsum2(Hyy2), gx = pmp_hsum2(gx2),
+                            gy = pmp_hsum2(gy2), S = pmp_hsum2(S2);
                 // a stem that nothing touches in its initial pose is never pushed: it stays at theta = 0
                 const bool act = touch && (S > 0.f);
                 if (!dense && !__any_sync(PMP_FULL, act)) break;   // later steps would be no-ops for every lane
@@ -436,9 +512,12 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
         for (int b = 0; b < n_boxes; ++b) {
             const float* bx = boxes + b * PMP_BOX_STRIDE;
 #pragma unroll
-            for (int a = 0; a < A; ++a)
-                out.plant_hit |= pmp_prim_hit(PMP_PRIM_BOX, bx, bx + 9, bx + 12, c[a][0], c[a][1], c[a][2],
-                                              rt.sph_radius[a]);
+            for (int a = 0; a < A; a += 2) {
+                float x0, x1, y0, y1, zz0, zz1;
+                pmp_upk(cpf(a >> 1, 0), x0, x1); pmp_upk(cpf(a >> 1, 1), y0, y1); pmp_upk(cpf(a >> 1, 2), zz0, zz1);
+                out.plant_hit |= pmp_prim_hit(PMP_PRIM_BOX, bx, bx + 9, bx + 12, x0, y0, zz0, rt.sph_radius[a]);
+                out.plant_hit |= pmp_prim_hit(PMP_PRIM_BOX, bx, bx + 9, bx + 12, x1, y1, zz1, rt.sph_radius[a + 1]);
+            }
         }
     }
     return out;
@@ -494,6 +573,10 @@ struct PmpEdgeArgs {
 #define PMP_EDGE_MINB 1
 #endif
 // FIRST: first-violation-only instantiation (no optional output requested), which stops like the reference's loops.
+// Per-warp tile of sphere centres: (pair of spheres, coordinate) rows of 32 lanes x 2 floats, padded to 66 floats so
+// that both access patterns are conflict-free -- a lane reading its own pairs as 64-bit words (the world loop) and
+// lane la reading sphere la of another step (the swept bounds).  3 * A * 33 floats per warp.
+#define PMP_TILE_AT(a, k, step) (((((a) >> 1) * 3 + (k)) * 66) + (step) * 2 + ((a) & 1))
 template <int A, int NSLOT, bool WSMEM, bool FIRST>
 __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(const PmpEdgeArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -605,9 +688,9 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
                 __syncwarp();
 #pragma unroll
                 for (int a = 0; a < A; ++a) {
-                    sm_tile[(3 * a + 0) * 33 + lane] = c[a][0];
-                    sm_tile[(3 * a + 1) * 33 + lane] = c[a][1];
-                    sm_tile[(3 * a + 2) * 33 + lane] = c[a][2];
+                    sm_tile[PMP_TILE_AT(a, 0, lane)] = c[a][0];
+                    sm_tile[PMP_TILE_AT(a, 1, lane)] = c[a][1];
+                    sm_tile[PMP_TILE_AT(a, 2, lane)] = c[a][2];
                 }
                 __syncwarp();
                 const int la = lane & (L - 1), g0 = lane & ~(L - 1);
@@ -618,7 +701,7 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
                     for (int j = 0; j < jn; ++j) {
 #pragma unroll
                         for (int k = 0; k < 3; ++k) {
-                            const float v = sm_tile[(3 * la + k) * 33 + g0 + j];
+                            const float v = sm_tile[PMP_TILE_AT(la, k, g0 + j)];
                             lo[k] = fminf(lo[k], v); hi[k] = fmaxf(hi[k], v);
                         }
                     }
@@ -650,6 +733,15 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
             // first-violation-only calls (the planner's extension check: no per-world outputs, no cost) stop like the
             // reference's loops do (primitives.py:225-241, env.py:230-238): steps after the first violating one are
             // retired, and the remaining worlds are skipped once step 0 of the chunk violates.
+            // the world loop reads the centres back from the tile, two spheres per 64-bit load
+            // (volatile: the compiler would otherwise hoist all 3 A / 2 loads out of the world loop and keep the
+            // centres in registers after all, which is exactly the pressure this layout is meant to remove)
+            const uint32_t my_tile = (uint32_t)__cvta_generic_to_shared(sm_tile + 2 * lane);
+            auto cpf = [my_tile](int pair, int k) {
+                pmp_f2 v;
+                asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(my_tile + (uint32_t)((pair * 3 + k) * 66 * 4)));
+                return v;
+            };
             int retired_from = 32;
             auto retire = [&](uint32_t v) {
                 const int L = __ffs(v) - 1;
@@ -658,7 +750,10 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
                     if (lane >= L) {
                         live = false;
 #pragma unroll
-                        for (int a = 0; a < A; ++a) { c[a][0] = PMP_FAR; c[a][1] = PMP_FAR; c[a][2] = PMP_FAR; }
+                        for (int a = 0; a < A; ++a) {
+                            sm_tile[PMP_TILE_AT(a, 0, lane)] = PMP_FAR; sm_tile[PMP_TILE_AT(a, 1, lane)] = PMP_FAR;
+                            sm_tile[PMP_TILE_AT(a, 2, lane)] = PMP_FAR;
+                        }
                     }
                 }
             };
@@ -671,7 +766,7 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
                     u = pmp_world_eval<A, NSLOT, false, true>(
                         stems_base + (size_t)w * prm.max_stems * PMP_STEM_STRIDE, sm_nstems[w],
                         args.boxes + (size_t)w * prm.max_boxes * PMP_BOX_STRIDE,
-                        prm.mode == PMP_MODE_AVOID_ALL ? args.n_boxes[w] : 0, rt, prm, c, nullptr, nullptr, bound);
+                        prm.mode == PMP_MODE_AVOID_ALL ? args.n_boxes[w] : 0, rt, prm, cpf, nullptr, nullptr, bound);
                 }
                 const uint32_t rm = rigid0_mask | __ballot_sync(PMP_FULL, live && u.plant_hit);
                 const uint32_t xm = __ballot_sync(PMP_FULL, live && u.exceeded);
@@ -765,6 +860,9 @@ __global__ void __launch_bounds__(128, 2) pmp_config_kernel(const PmpConfigArgs 
 #pragma unroll
         for (int a = 0; a < A; ++a) { c[a][0] = PMP_FAR; c[a][1] = PMP_FAR; c[a][2] = PMP_FAR; }
     }
+    pmp_f2 cp[A / 2][3];
+    pmp_pack_centres<A>(c, cp);
+    auto cpf = [&cp](int pair, int k) { return cp[pair][k]; };
     if (live && args.ee && blockIdx.y == 0) { args.ee[3 * b] = ee[0]; args.ee[3 * b + 1] = ee[1]; args.ee[3 * b + 2] = ee[2]; }
     // worlds are spread over blockIdx.y so that small batches (the scalar collision_fn adapter: B = 1..50) use many
     // SMs instead of one thread walking all W worlds; the arm FK above is simply recomputed per world chunk
@@ -780,7 +878,7 @@ __global__ void __launch_bounds__(128, 2) pmp_config_kernel(const PmpConfigArgs 
         if (prm.mode != PMP_MODE_IGNORE_ALL) {
             u = pmp_world_eval<A, NSLOT, true, false>(args.stems + (size_t)w * P * PMP_STEM_STRIDE, ns,
                                                args.boxes + (size_t)w * prm.max_boxes * PMP_BOX_STRIDE,
-                                               prm.mode == PMP_MODE_AVOID_ALL ? args.n_boxes[w] : 0, rt, prm, c, dptr, tptr);
+                                               prm.mode == PMP_MODE_AVOID_ALL ? args.n_boxes[w] : 0, rt, prm, cpf, dptr, tptr);
         } else {
             for (int s = 0; s < ns; ++s) {
                 if (dptr) dptr[s] = 0.f;
