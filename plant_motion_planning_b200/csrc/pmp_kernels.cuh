@@ -319,6 +319,7 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
         bool touch = false;
         {
             const float ux = Rv[2], uy = Rv[5], uz = Rv[8];
+            float margin = -1.f;
             static_assert(A % 2 == 0, "sphere loops work on pairs");
 #pragma unroll
             for (int a = 0; a < A; a += 2) {          // spheres a (low half) and a + 1 (high half)
@@ -330,11 +331,14 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
                 const pmp_f2 tau = pmp_pk(pmp_clamp(t0, z0, z1), pmp_clamp(t1, z0, z1));
                 const pmp_f2 dx = pmp_fma2(tau, pmp_bc(-ux), wx), dy = pmp_fma2(tau, pmp_bc(-uy), wy),
                              dz = pmp_fma2(tau, pmp_bc(-uz), wz);
-                float e0, e1;
-                pmp_upk(pmp_fma2(dx, dx, pmp_fma2(dy, dy, pmp_mul2(dz, dz))), e0, e1);
-                const float rr0 = rt.sph_radius[a] + rad, rr1 = rt.sph_radius[a + 1] + rad;
-                touch |= (e0 < rr0 * rr0) | (e1 < rr1 * rr1);
+                const pmp_f2 d2 = pmp_fma2(dx, dx, pmp_fma2(dy, dy, pmp_mul2(dz, dz)));
+                // touching <=> (r_a + rad)^2 - d2 > 0; the largest such margin over all spheres decides
+                const pmp_f2 nrr = pmp_sub2(pmp_bc(-rad), *reinterpret_cast<const pmp_f2*>(&rt.sph_radius[a]));
+                float m0, m1;
+                pmp_upk(pmp_sub2(pmp_mul2(nrr, nrr), d2), m0, m1);
+                margin = fmaxf(fmaxf(margin, m0), m1);
             }
+            touch = margin > 0.f;
         }
         float thx = 0.f, thy = 0.f;
         float cx = 1.f, sx = 0.f, cy = 1.f, sy = 0.f;
@@ -372,7 +376,8 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
                     const pmp_f2 inv = pmp_pk(pmp_rsqrt_ftz(e0), pmp_rsqrt_ftz(e1));
                     // d2 * inv - (r_a + rad) = -(penetration)
                     float n0, n1;
-                    pmp_upk(pmp_fma2(d2, inv, pmp_pk(-(rt.sph_radius[a] + rad), -(rt.sph_radius[a + 1] + rad))), n0, n1);
+                    const pmp_f2 nrr = pmp_sub2(pmp_bc(-rad), *reinterpret_cast<const pmp_f2*>(&rt.sph_radius[a]));
+                    pmp_upk(pmp_fma2(d2, inv, nrr), n0, n1);
                     const pmp_f2 pen = pmp_pk(fmaxf(-n0, 0.f), fmaxf(-n1, 0.f));
                     const pmp_f2 sc = pmp_mul2(tau, inv);
                     const pmp_f2 Jx = pmp_mul2(sc, pmp_fma2(dx, pmp_bc(nbxx), pmp_fma2(dy, pmp_bc(nbxy), pmp_mul2(dz, pmp_bc(nbxz)))));

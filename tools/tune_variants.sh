@@ -12,7 +12,7 @@ for v in "$@"; do
   set -- $v
   tag=t$1_b$2${TAG:-}
   FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xptxas -v -DPMP_EDGE_MAXT=$1 -DPMP_EDGE_MINB=$2 ${EXTRA:-}"
-  for f in pmp_edgecheck pmp_inst_a12 pmp_inst_a16 pmp_inst_a32; do
+  for f in pmp_edgecheck pmp_inst_a12 pmp_inst_a16 pmp_inst_a32 pmp_inst_a12f pmp_inst_a16f pmp_inst_a32f; do
     nvcc $FLAGS -c -o $OUT/obj/${f}_$tag.o $C/$f.cu > $OUT/obj/${f}_$tag.log 2>&1 &
   done
   wait
