@@ -284,7 +284,7 @@ def main() -> None:
         "bound": "fp32", "unit": "TFLOP/s", "peak": peak_tf,
         "peak_source": "measured on this GPU in this run: dependent-FMA probe kernel (pmp_measure_fp32_peak); "
                        "MEASURED_PEAKS.json has no FP32 CUDA-core figure (theoretical 148 SM x 128 x 2 x 1.965 GHz = 74.4)",
-        "kernel": f"pmp_edge_kernel<{info['n_sphere_pad']},{info['n_slot_pad']},{'true' if info['worlds_in_smem'] else 'false'}>",
+        "kernel": f"pmp_edge_kernel<{info['n_sphere_pad']},{info['n_slot_pad']},{'true' if info['worlds_in_smem'] else 'false'},false>",
         "flops_per_unit": F,
         "achieved": (units_gpu * F / (dense_ms * 1e-3) / 1e12) if dense_ms else None,
         "frac": (units_gpu * F / (dense_ms * 1e-3) / 1e12 / peak_tf) if dense_ms else None,
