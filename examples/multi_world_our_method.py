@@ -31,13 +31,30 @@ def main():
     ap.add_argument("--smooth", action="store_true")
     ap.add_argument("--batched", action="store_true", help="batched RRT-Connect on device-resident trees (pmp_tree_extend)")
     ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--plant_dir", default=None, help="our_method_multi_branch.py: directory with plant.urdf + "
+                    "plant_params.pkl (e.g. the reference's environments/multi_branch/env1); deflection limit 0.30")
+    ap.add_argument("--single_branch", default=None, metavar="ENV", help="our_method_single_branch.py: one of the "
+                    "fixed single-stem plant sets env0..env8 (plant_motion_planning/utils.py:120-230)")
     args = ap.parse_args()
-    cfg = SCRIPTS[args.script]
+    cfg = dict(SCRIPTS[args.script])
     limit = cfg["deflection_limit"] if args.deflection_limit is None else args.deflection_limit
 
     np.random.seed(cfg["seed"])
     random.seed(cfg["seed"])
-    env = MultiPlantWorld(cfg["xs"], cfg["ys"], limit, *cfg["args"], cfg["limits"], avoid_all=cfg["avoid_all"])
+    if args.plant_dir or args.single_branch:
+        # the two single-world scripts: one saved multi-branch plant (scripts/our_method_multi_branch.py:82-133) or a
+        # fixed set of single-stem plants (scripts/our_method_single_branch.py); seeds fixed here as SURVEY 8d says
+        from plant_motion_planning_b200.scenarios import single_branch_world
+        if args.plant_dir:
+            limit = 0.30 if args.deflection_limit is None else args.deflection_limit
+            env = MultiPlantWorld([0], [0], limit, loadPath=args.plant_dir)
+        else:
+            env = MultiPlantWorld([0], [0], limit, worlds=[single_branch_world(args.single_branch)])
+        cfg.update(mode="our_method", avoid_all=False, seed=1)
+        np.random.seed(1)
+        random.seed(1)
+    else:
+        env = MultiPlantWorld(cfg["xs"], cfg["ys"], limit, *cfg["args"], cfg["limits"], avoid_all=cfg["avoid_all"])
     if cfg["mode"] == "ignore_all":
         env.checker.set_config(mode="ignore_all")
     robot = env.sample_robot
