@@ -86,8 +86,9 @@ def main():
         print("Unable to find a plan!")
         return 1
     path, ee_len, over = res
-    print(f"plan: {len(path)} configurations, {len(log.edges)} edges checked in {backend.launches} kernel launches, "
-          f"{time.time() - t0:.2f} s")
+    if not args.batched:
+        print(f"plan: {len(path)} configurations, {len(log.edges)} edges checked in {backend.launches} kernel launches, "
+              f"{time.time() - t0:.2f} s")
     if args.smooth:
         path = birrt.smooth_path_multi_world(path, ext, dist, backend, max_iterations=20)
         ee_len, over, _ = env.path_cost(START, path)
