@@ -254,51 +254,23 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
         const int pslot = __float_as_int(rec[PMP_S_PSLOT]);
         const int oslot = __float_as_int(rec[PMP_S_OSLOT]);
         const int flags = __float_as_int(rec[PMP_S_FLAGS]);
-        // ---- joint frame: rest pose from the table while the ancestor chain is undeflected ----
-        float Rv[9], tv[3];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) Rv[i] = rec[PMP_S_RW0 + i];
-        tv[0] = rec[PMP_S_TW0]; tv[1] = rec[PMP_S_TW0 + 1]; tv[2] = rec[PMP_S_TW0 + 2];
+        // ---- is the ancestor chain undeflected (warp-uniform)?  Then the joint frame is the table's rest frame. ----
         bool moved = false;
-        bool chain_at_rest = true;     // warp-uniform: no lane has a deflected ancestor, so Rv/tv are the table values
+        bool chain_at_rest = true;
         if (pslot >= 0) {
             moved = FM[0];
 #pragma unroll
             for (int k = 1; k < NSLOT; ++k)
                 if (pslot == k) moved = FM[k];   // warp-uniform
             chain_at_rest = !__any_sync(PMP_FULL, moved);
-            if (dense || !chain_at_rest) {
-                float Rp[9], tp[3];
-#pragma unroll
-                for (int i = 0; i < 9; ++i) Rp[i] = FR[0][i];
-                tp[0] = FT[0][0]; tp[1] = FT[0][1]; tp[2] = FT[0][2];
-#pragma unroll
-                for (int k = 1; k < NSLOT; ++k) {
-                    if (pslot == k) {
-#pragma unroll
-                        for (int i = 0; i < 9; ++i) Rp[i] = FR[k][i];
-                        tp[0] = FT[k][0]; tp[1] = FT[k][1]; tp[2] = FT[k][2];
-                    }
-                }
-                float Ro[9], Rc[9];
-#pragma unroll
-                for (int i = 0; i < 9; ++i) Ro[i] = rec[PMP_S_RO + i];
-                pmp_mat_mul(Rp, Ro, Rc);
-                float x, y, z;
-                pmp_mat_vec(Rp, rec[PMP_S_TO], rec[PMP_S_TO + 1], rec[PMP_S_TO + 2], x, y, z);
-                if (moved) {
-#pragma unroll
-                    for (int i = 0; i < 9; ++i) Rv[i] = Rc[i];
-                    tv[0] = x + tp[0]; tv[1] = y + tp[1]; tv[2] = z + tp[2];
-                }
-            }
         }
         const float z0 = rec[PMP_S_Z0], z1 = rec[PMP_S_Z1], rad = rec[PMP_S_RAD], lim = rec[PMP_S_LIM];
-        // ---- phase 0: can ANY step of this warp touch the stem at rest?  One swept-bound test per lane. ----
+        // ---- phase 0: can ANY step of this warp touch the stem at rest?  One swept-bound test per lane, on the rest
+        // frame read straight from the record (no register copy of the frame is made for the 4 stems in 5 that end here)
         bool maybe = true;
         if (CULL && !dense && chain_at_rest) {
-            const float ux = Rv[2], uy = Rv[5], uz = Rv[8];
-            const float wx = bound.x - tv[0], wy = bound.y - tv[1], wz = bound.z - tv[2];
+            const float ux = rec[PMP_S_RW0 + 2], uy = rec[PMP_S_RW0 + 5], uz = rec[PMP_S_RW0 + 8];
+            const float wx = bound.x - rec[PMP_S_TW0], wy = bound.y - rec[PMP_S_TW0 + 1], wz = bound.z - rec[PMP_S_TW0 + 2];
             const float tau = pmp_clamp(fmaf(wx, ux, fmaf(wy, uy, wz * uz)), z0, z1);
             const float dx = fmaf(-tau, ux, wx), dy = fmaf(-tau, uy, wy), dz = fmaf(-tau, uz, wz);
             const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
@@ -314,6 +286,36 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
             for (int k = 0; k < NSLOT; ++k)
                 if (oslot == k) FM[k] = false;
             continue;
+        }
+        // ---- joint frame: the table's rest frame, or parent frame . origin when an ancestor is deflected ----
+        float Rv[9], tv[3];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Rv[i] = rec[PMP_S_RW0 + i];
+        tv[0] = rec[PMP_S_TW0]; tv[1] = rec[PMP_S_TW0 + 1]; tv[2] = rec[PMP_S_TW0 + 2];
+        if (pslot >= 0 && (dense || !chain_at_rest)) {
+            float Rp[9], tp[3];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Rp[i] = FR[0][i];
+            tp[0] = FT[0][0]; tp[1] = FT[0][1]; tp[2] = FT[0][2];
+#pragma unroll
+            for (int k = 1; k < NSLOT; ++k) {
+                if (pslot == k) {
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) Rp[i] = FR[k][i];
+                    tp[0] = FT[k][0]; tp[1] = FT[k][1]; tp[2] = FT[k][2];
+                }
+            }
+            float Ro[9], Rc[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Ro[i] = rec[PMP_S_RO + i];
+            pmp_mat_mul(Rp, Ro, Rc);
+            float x, y, z;
+            pmp_mat_vec(Rp, rec[PMP_S_TO], rec[PMP_S_TO + 1], rec[PMP_S_TO + 2], x, y, z);
+            if (moved) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) Rv[i] = Rc[i];
+                tv[0] = x + tp[0]; tv[1] = y + tp[1]; tv[2] = z + tp[2];
+            }
         }
         // ---- phase 1: does any arm sphere touch the stem in its initial pose?  (exact, no rsqrt / Jacobian) ----
         bool touch = false;
