@@ -6,7 +6,7 @@ stays inside one warp, so NCCL is used for exactly one collective per batch.
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Tuple
 
 
 def shard_bounds(n_edges: int, rank: int, world_size: int) -> Tuple[int, int]:

@@ -15,7 +15,7 @@ from __future__ import annotations
 import ctypes as C
 import math
 from dataclasses import dataclass, replace
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import numpy as np
 

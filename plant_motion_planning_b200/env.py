@@ -24,7 +24,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .edgecheck import FLAG_EXCEEDED, FLAG_RIGID, EdgeCheckConfig, EdgeChecker
+from .edgecheck import FLAG_RIGID, EdgeCheckConfig, EdgeChecker
 from .model.plants import PlantWorld, load_plant, sample_world
 from .model.robot import RobotModel
 from .planner_fns import GATE_PROBABILITY, get_limits_fn

@@ -17,7 +17,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .plants import (OBS_MOD3, PLANT_JOINT_LIMIT, SCALING, STEM_COM_Z, STEM_HALF_WIDTH, PlantWorld, Stem, sample_plant)
+from .plants import OBS_MOD3, PLANT_JOINT_LIMIT, SCALING, STEM_COM_Z, STEM_HALF_WIDTH, PlantWorld, Stem
 from .tables import (BOX_STRIDE, F_HAS_PARENT, F_IS_MAIN, F_OBS_ROOT, F_PLANT_START, MAX_SLOTS, MAX_STEMS, S_COMZ, S_FLAGS,
                      S_LIM, S_OBSV, S_OSLOT, S_PSLOT, S_RAD, S_RO, S_RW0, S_TO, S_TW0, S_Z0, S_Z1, STEM_STRIDE,
                      WorldTables, assign_slots)

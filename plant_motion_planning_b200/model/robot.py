@@ -20,7 +20,7 @@ from typing import Dict, Iterable, List, Optional, Sequence, Set, Tuple
 
 import numpy as np
 
-from .transforms import Frame, axis_angle_matrix, matrix_to_quat, skew
+from .transforms import Frame, axis_angle_matrix, skew
 from .urdf import UrdfTree, parse_urdf
 
 # Kernel-side capacity limits (mirrored in csrc/pmp_tables.h).

@@ -14,9 +14,9 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .plants import DEFAULT_STEM_RADIUS, OBS_ANGLE, OBS_MOD3, PlantWorld, Stem
+from .plants import OBS_ANGLE, OBS_MOD3, PlantWorld, Stem
 from .robot import (MAX_FIXED_PRIMS, PRIM_BOX, FixedPrim, RobotModel, joint_constant_matrices)
-from .transforms import Frame, rot_x, rot_y, rpy_to_matrix
+from .transforms import Frame, rpy_to_matrix
 
 STEM_STRIDE = 48          # floats per stem record
 BOX_STRIDE = 16           # floats per world box record
