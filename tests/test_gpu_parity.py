@@ -210,6 +210,36 @@ def test_first_hit_only_calls_stop_early_with_identical_answers(ctx, mode, backw
         chk.set_config(mode="our_method", device_gate_seed=None, deflection_limit=0.30)
 
 
+def test_worlds_without_plants(ctx):
+    """A world with no stems and no plant base (an empty plot) next to planted ones, and a checker whose only world
+    is empty: only the arm's own rigid tests can fire there, deflections are zero."""
+    from oracle.c_oracle import COracle
+    from plant_motion_planning_b200 import EdgeCheckConfig, EdgeChecker
+    from plant_motion_planning_b200.model.plants import PlantWorld
+    from plant_motion_planning_b200.workloads import random_edges
+    torch, model = ctx["torch"], ctx["model"]
+    empty = PlantWorld(stems=[], base_boxes=[])
+    Q = ctx["Q"][:512]
+    for worlds in ([empty, ctx["worlds"][0], empty], [empty]):
+        for mode in ("our_method", "avoid_all"):
+            chk = EdgeChecker(model, worlds, EdgeCheckConfig(mode=mode))
+            g = chk.check_configs(torch.from_numpy(Q))
+            c = COracle(model, worlds, mode=mode).check_configs(Q)
+            fl = g.flags.cpu().numpy()
+            assert np.array_equal(fl[:, 0], fl[:, -1]) and not (fl[:, 0] & 2).any()
+            assert (fl != c["flags"]).mean() <= 2e-3
+            assert np.abs(g.deflection.cpu().numpy()[:, 0]).max() == 0.0
+            q0, q1 = random_edges(model, 64, seed=2)
+            out = chk.validate_edges(torch.from_numpy(q0), torch.from_numpy(q1))
+            ce = COracle(model, worlds, mode=mode).validate_edges(q0, q1)
+            assert np.array_equal(out.n_steps.cpu().numpy(), ce["n_steps"])
+            assert (out.first_hit.cpu().numpy() != ce["first_hit"]).mean() <= 0.05
+            assert float(out.max_deflection[:, 0].abs().max()) == 0.0
+            fast = chk.validate_edges(torch.from_numpy(q0), torch.from_numpy(q1), first_hit_only=True)
+            assert torch.equal(fast.first_hit, out.first_hit)
+            chk.close()
+
+
 def test_empty_batch_and_bad_shapes(ctx):
     torch, chk = ctx["torch"], ctx["chk"]
     out = chk.validate_edges(torch.zeros((0, 7)), torch.zeros((0, 7)))
