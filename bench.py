@@ -347,8 +347,15 @@ def main() -> None:
         ref = co.validate_edges(q0[:n], q1[:n], max_steps=args.edge_steps)
         el = time.perf_counter() - t0
         agree = float(np.mean(ref["first_hit"] == hout["first_hit"][:n]))
+        # one core, on a sample a tenth of that (SURVEY 8d asks for both figures)
+        n1 = max(64, n // (10 * max(co.max_threads, 1)))
+        t0 = time.perf_counter()
+        co.validate_edges(q0[:n1], q1[:n1], max_steps=args.edge_steps, n_threads=1)
+        el1 = time.perf_counter() - t0
         cpu_baseline = {"value": n * args.edge_steps * W / el, "unit": UNIT, "cores": co.max_threads, "kind": "port",
                         "sample": f"first {n} edges of the same sweep x {args.edge_steps} steps x {W} worlds, {el:.1f} s",
+                        "single_core_value": n1 * args.edge_steps * W / el1,
+                        "single_core_sample": f"first {n1} edges, {el1:.1f} s",
                         "first_hit_agreement_with_gpu": agree}
 
     if rank == 0:
