@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "pmp_kernels.cuh"   // packed-pair helpers (pmp_f2, pmp_fma2, ...)
 #include "pmp_tables.h"
 
 #define PMP_NN_TGT_MAX 8      // targets per CTA: 8 for D <= 8, 4 above (targets and running minima live in registers)
@@ -60,15 +61,22 @@ __device__ __noinline__ double pmp_nn_exact(const float* __restrict__ node, cons
     return __dsqrt_rn(s);
 }
 
-// float32 squared distance used as the filter (relative error <= (D + 2) * 2^-24, plus 1.3e-5 per continuous joint)
+// float32 squared distances of one node to TWO targets, used as the filter (relative error <= (D + 2) * 2^-24, plus
+// 1.3e-5 per continuous joint): packed pairs, low half = target 2p, high half = target 2p + 1.
 template <int DP, bool CIRC>
-__device__ __forceinline__ float pmp_nn_s32(const float (&t)[DP], const float (&q)[DP], uint32_t circ) {
-    float s = 0.f;
+__device__ __forceinline__ pmp_f2 pmp_nn_s32x2(const pmp_f2 (&t)[DP], const float (&q)[DP], uint32_t circ) {
+    pmp_f2 s = pmp_bc(0.f);
 #pragma unroll
     for (int j = 0; j < DP; ++j) {
-        float d = t[j] - q[j];
-        if (CIRC && ((circ >> j) & 1u)) d = fmaf(-6.2831853071795865f, rintf(d * 0.15915494309189535f), d);
-        s = fmaf(d, d, s);
+        pmp_f2 d = pmp_sub2(t[j], pmp_bc(q[j]));
+        if (CIRC && ((circ >> j) & 1u)) {
+            float d0, d1;
+            pmp_upk(d, d0, d1);
+            d0 = fmaf(-6.2831853071795865f, rintf(d0 * 0.15915494309189535f), d0);
+            d1 = fmaf(-6.2831853071795865f, rintf(d1 * 0.15915494309189535f), d1);
+            d = pmp_pk(d0, d1);
+        }
+        s = pmp_fma2(d, d, s);
     }
     return s;
 }
@@ -91,12 +99,14 @@ template <int DP, int TGT, bool CIRC>
 __global__ void __launch_bounds__(PMP_NN_BLOCK, 2) pmp_nearest_min_kernel(const PmpNearestArgs a) {
     const int D = a.D;
     const int t0 = blockIdx.x * TGT;
-    float tg[TGT][DP];
+    static_assert(TGT % 2 == 0, "targets are processed in pairs");
+    pmp_f2 tg[TGT / 2][DP];
 #pragma unroll
-    for (int t = 0; t < TGT; ++t)
+    for (int t = 0; t < TGT; t += 2)
 #pragma unroll
         for (int j = 0; j < DP; ++j)
-            tg[t][j] = (t0 + t < a.B && j < D) ? a.targets[(size_t)(t0 + t) * D + j] : 0.f;
+            tg[t >> 1][j] = pmp_pk((t0 + t < a.B && j < D) ? a.targets[(size_t)(t0 + t) * D + j] : 0.f,
+                                   (t0 + t + 1 < a.B && j < D) ? a.targets[(size_t)(t0 + t + 1) * D + j] : 0.f);
     int lo, hi;
     pmp_nn_range(a, lo, hi);
     float best[TGT];
@@ -107,7 +117,12 @@ __global__ void __launch_bounds__(PMP_NN_BLOCK, 2) pmp_nearest_min_kernel(const 
 #pragma unroll
         for (int j = 0; j < DP; ++j) q[j] = j < D ? a.nodes[(size_t)n * D + j] : 0.f;
 #pragma unroll
-        for (int t = 0; t < TGT; ++t) best[t] = fminf(best[t], pmp_nn_s32<DP, CIRC>(tg[t], q, a.circular_mask));
+        for (int t = 0; t < TGT; t += 2) {
+            float s0, s1;
+            pmp_upk(pmp_nn_s32x2<DP, CIRC>(tg[t >> 1], q, a.circular_mask), s0, s1);
+            best[t] = fminf(best[t], s0);
+            best[t + 1] = fminf(best[t + 1], s1);
+        }
     }
 #pragma unroll
     for (int t = 0; t < TGT; ++t) {
@@ -126,13 +141,17 @@ __global__ void __launch_bounds__(PMP_NN_BLOCK, 2) pmp_nearest_kernel(const PmpN
     __shared__ int sm_i[PMP_NN_BLOCK / 32][TGT];
     const int D = a.D;
     const int t0 = blockIdx.x * TGT;
-    float tg[TGT][DP], thr[TGT];
+    pmp_f2 tg[TGT / 2][DP];
+    float thr[TGT];
     const float band = 3.0e-5f * (float)__popc(a.circular_mask);     // absolute error of the wrapped terms
 #pragma unroll
-    for (int t = 0; t < TGT; ++t) {
+    for (int t = 0; t < TGT; t += 2)
 #pragma unroll
         for (int j = 0; j < DP; ++j)
-            tg[t][j] = (t0 + t < a.B && j < D) ? a.targets[(size_t)(t0 + t) * D + j] : 0.f;
+            tg[t >> 1][j] = pmp_pk((t0 + t < a.B && j < D) ? a.targets[(size_t)(t0 + t) * D + j] : 0.f,
+                                   (t0 + t + 1 < a.B && j < D) ? a.targets[(size_t)(t0 + t + 1) * D + j] : 0.f);
+#pragma unroll
+    for (int t = 0; t < TGT; ++t) {
         const float m = t0 + t < a.B ? __uint_as_float(a.min32[t0 + t]) : 0.f;
         thr[t] = (m + 2.f * band) * 1.00001f + 1e-30f;    // + underflow range of the float32 squares
     }
@@ -148,11 +167,17 @@ __global__ void __launch_bounds__(PMP_NN_BLOCK, 2) pmp_nearest_kernel(const PmpN
 #pragma unroll
         for (int j = 0; j < DP; ++j) q[j] = j < D ? a.nodes[(size_t)n * D + j] : 0.f;
 #pragma unroll
-        for (int t = 0; t < TGT; ++t) {
-            if (pmp_nn_s32<DP, CIRC>(tg[t], q, a.circular_mask) <= thr[t] && t0 + t < a.B) {
-                const double r = pmp_nn_exact(a.nodes + (size_t)n * D, a.targets + (size_t)(t0 + t) * D, D,
-                                              a.circular_mask);
-                if (pmp_nn_better(r, n, best_r[t], best_i[t])) { best_r[t] = r; best_i[t] = n; }
+        for (int t2 = 0; t2 < TGT; t2 += 2) {
+            float s01[2];
+            pmp_upk(pmp_nn_s32x2<DP, CIRC>(tg[t2 >> 1], q, a.circular_mask), s01[0], s01[1]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int t = t2 + h;
+                if (s01[h] <= thr[t] && t0 + t < a.B) {
+                    const double r = pmp_nn_exact(a.nodes + (size_t)n * D, a.targets + (size_t)(t0 + t) * D, D,
+                                                  a.circular_mask);
+                    if (pmp_nn_better(r, n, best_r[t], best_i[t])) { best_r[t] = r; best_i[t] = n; }
+                }
             }
         }
     }
