@@ -86,6 +86,7 @@ def get_distance_fn(robot, weights=None, norm=2) -> Callable:
 
 def get_refine_fn(robot, num_steps=0) -> Callable:
     difference_fn = get_difference_fn(robot)
+    any_circular = any(_circular(robot))
     num_steps = num_steps + 1
 
     def fn(q1, q2) -> Iterator[Tuple[float, ...]]:
@@ -93,6 +94,13 @@ def get_refine_fn(robot, num_steps=0) -> Callable:
         # floats: the same IEEE operations in the same order (bit-identical results, pinned by
         # tests/golden/reference_planner_fns.json) without a numpy round trip per step
         q = tuple(float(v) for v in q1)
+        if not any_circular:                  # difference_fn is a plain subtraction: skip the call per step
+            target = tuple(q2)
+            for i in range(num_steps):
+                c = 1. / (num_steps - i)
+                q = tuple(c * (b - a) + a for a, b in zip(q, target))
+                yield q
+            return
         for i in range(num_steps):
             c = 1. / (num_steps - i)
             q = tuple(c * d + v for d, v in zip(difference_fn(q2, q), q))
