@@ -167,13 +167,17 @@ __global__ void __launch_bounds__(PMP_NN_BLOCK, 2) pmp_nearest_kernel(const PmpN
 #pragma unroll
         for (int j = 0; j < DP; ++j) q[j] = j < D ? a.nodes[(size_t)n * D + j] : 0.f;
 #pragma unroll
-        for (int t2 = 0; t2 < TGT; t2 += 2) {
-            float s01[2];
-            pmp_upk(pmp_nn_s32x2<DP, CIRC>(tg[t2 >> 1], q, a.circular_mask), s01[0], s01[1]);
+        float sq[TGT];
+        bool any = false;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int t = t2 + h;
-                if (s01[h] <= thr[t] && t0 + t < a.B) {
+        for (int t2 = 0; t2 < TGT; t2 += 2) {
+            pmp_upk(pmp_nn_s32x2<DP, CIRC>(tg[t2 >> 1], q, a.circular_mask), sq[t2], sq[t2 + 1]);
+            any |= (sq[t2] <= thr[t2]) | (sq[t2 + 1] <= thr[t2 + 1]);
+        }
+        if (any) {                                   // rare: about one node per target passes the filter
+#pragma unroll
+            for (int t = 0; t < TGT; ++t) {
+                if (sq[t] <= thr[t] && t0 + t < a.B) {
                     const double r = pmp_nn_exact(a.nodes + (size_t)n * D, a.targets + (size_t)(t0 + t) * D, D,
                                                   a.circular_mask);
                     if (pmp_nn_better(r, n, best_r[t], best_i[t])) { best_r[t] = r; best_i[t] = n; }
