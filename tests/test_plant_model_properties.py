@@ -103,3 +103,51 @@ def test_mirror_symmetry(stem):
     Rb, _ = O.frames_from_theta(w, b.reshape(1, 1, 2))
     ua, ub = Ra[0, 0][:, 2], Rb[0, 0][:, 2]
     assert np.allclose(ua * np.array([1.0, -1.0, 1.0]), ub, atol=1e-12)  # the stem axes are mirror images
+
+
+def test_two_contacts_blend_continuously(stem):
+    """No arg-max over spheres: as a second sphere is withdrawn its influence fades without a jump, and once it no
+    longer touches the stem the answer is the single-contact one."""
+    w, s, z0, z1, rs = stem
+    r = 0.05
+    prm = O.OracleParams()
+    c1 = s.origin.t + np.array([r + rs - 0.02, 0.0, 0.7])
+    ys = np.linspace(r + rs - 0.02, r + rs + 0.01, 300)
+    th = []
+    for y in ys:
+        c2 = s.origin.t + np.array([0.0, y, 0.5])
+        t, _, _, _ = O.plant_equilibrium(w, np.stack([c1, c2])[None], np.array([r, r]), prm)
+        th.append(t[0, 0])
+    th = np.array(th)
+    single, _ = _solve(w, c1, r)
+    assert np.allclose(th[ys > r + rs + 1e-9], single, atol=1e-12)
+    assert np.linalg.norm(np.diff(th, axis=0), axis=1).max() <= 2e-3          # 0.1 mm steps of the second sphere
+    assert abs(th[0, 0]) > 0.01 and abs(th[0, 1]) > 0.01                      # both contacts bend it at the start
+
+
+def test_pushed_child_does_not_load_its_parent_but_a_pushed_parent_carries_its_children():
+    import random
+    from plant_motion_planning_b200.model.plants import sample_world
+    np.random.seed(1)
+    random.seed(1)
+    w = sample_world(1, 2, 1, ((0.3, 0.3), (0.0, 0.0)))
+    prm = O.OracleParams()
+    R0, t0 = O.frames_from_theta(w, np.zeros((1, w.num_stems, 2)))
+    child = next(k for k, st in enumerate(w.stems) if st.parent == 0)
+    _, _, rs = stem_capsule(w.stems[child], None)
+    # a sphere pressed into the middle of the child stem, from the side
+    mid = t0[0, child] + R0[0, child] @ np.array([0.0, 0.0, w.stems[child].half_height])
+    side = R0[0, child] @ np.array([1.0, 0.0, 0.0])
+    centre = mid + side * (0.05 + rs - 0.015)
+    far = np.linalg.norm(centre - (t0[0, 0] + R0[0, 0] @ np.array([0.0, 0.0, w.stems[0].half_height])))
+    theta, R, t, _ = O.plant_equilibrium(w, centre.reshape(1, 1, 3), np.array([0.05]), prm)
+    if far > 0.05 + rs + 0.01:                       # the sphere does not also touch the main stem
+        assert np.all(theta[0, 0] == 0.0)
+    assert np.linalg.norm(theta[0, child]) > 1e-3
+    # push the main stem instead: its children keep theta = 0 but their world frames move with it
+    base_mid = t0[0, 0] + R0[0, 0] @ np.array([0.0, 0.0, 0.6 * w.stems[0].half_height])
+    c2 = base_mid + np.array([0.05 + rs - 0.01, 0.0, 0.0])
+    theta2, R2, t2, _ = O.plant_equilibrium(w, c2.reshape(1, 1, 3), np.array([0.05]), prm)
+    assert np.linalg.norm(theta2[0, 0]) > 1e-3
+    moved = [k for k, st in enumerate(w.stems) if st.parent == 0 and np.all(theta2[0, k] == 0.0)]
+    assert moved and all(np.abs(R2[0, k] - R0[0, k]).max() > 1e-4 for k in moved)
