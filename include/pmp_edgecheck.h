@@ -27,7 +27,7 @@ extern "C" {
 #define PMP_MAX_FIXED 16
 #define PMP_MAX_STEMS 32
 #define PMP_MAX_WORLD_BOXES 32
-#define PMP_MAX_SLOTS 8
+#define PMP_MAX_SLOTS 4   /* parent-frame register slots compiled into the kernels */
 #define PMP_STEM_STRIDE 48 /* floats per stem record, layout in csrc/pmp_tables.h */
 #define PMP_BOX_STRIDE 16  /* floats per plant-base box record: R[9] t[3] half[3] pad */
 
@@ -84,6 +84,29 @@ typedef struct pmp_robot_desc {
     const uint32_t* fixed_mask;/* [F] bit a set => arm sphere a is tested against it */
 } pmp_robot_desc;
 
+/* Convex hulls of the arm's collision meshes (copied by pmp_set_robot_hulls; optional).  With hulls set, self and
+ * fixed-obstacle collisions are decided EXACTLY on them -- Bullet's test behind p.getClosestPoints(distance=0),
+ * pybullet_tools/utils.py:3390-3441: GJK distance of the margin-free convex shapes minus both collision margins <= 0 --
+ * and the arm spheres (with their covering radii) only cull.  Without hulls the sphere model decides.
+ * The plant contact solve always works on the spheres. */
+#define PMP_MAX_HULLS 16
+#define PMP_MAX_HULL_PAIRS 64
+#define PMP_MAX_HULL_VERTS 16384
+typedef struct pmp_hull_desc {
+    int32_t n_hulls;               /* <= PMP_MAX_HULLS; 0 removes the hulls */
+    const int32_t* hull_joint;     /* [n_hulls] joint the hull rides on */
+    const int32_t* hull_off;       /* [n_hulls+1] vertex ranges in hull_verts */
+    const float* hull_verts;       /* [3*hull_off[n_hulls]] vertices in the joint frame (<= PMP_MAX_HULL_VERTS) */
+    const float* hull_margin;      /* [n_hulls] collision margin outside the hull (btConvexHullShape: 0.001) */
+    int32_t n_pairs;               /* self pairs (get_self_link_pairs, pybullet_tools/utils.py:3740-3751) */
+    const int32_t* pairs;          /* [2*n_pairs] hull indices */
+    const int32_t* sph_hull;       /* [n_spheres] hull that arm sphere a approximates (-1 = none) */
+    const float* sph_radius_outer; /* [n_spheres] radii with which the spheres of a hull COVER hull (+) margin */
+    float fixed_margin;            /* collision margin carved out of the static boxes (btBoxShape: 0.001) */
+    int32_t n_fixed_exact;         /* the first n_fixed_exact static primitives (boxes / spheres) are obstacles
+                                      tested against every hull (product(moving links, fixed), utils.py:4008-4014) */
+} pmp_hull_desc;
+
 /* Sampled plant worlds (copied by pmp_set_worlds).  Replaces the per-world Bullet bodies created by
  * SinglePlantEnv.__init__ (env.py:63-73) and their CharacterizePlant observers. */
 typedef struct pmp_world_desc {
@@ -115,7 +138,11 @@ typedef struct pmp_params {
                                 with a counter-based generator, so that it can run inside the kernel.  The raw step
                                 masks are never gated; replay them on the host to reproduce the reference's
                                 np.random stream exactly. */
-    int32_t reserved;
+    float arm_lag_gain;      /* 0 = the arm is at the commanded configuration.  Otherwise the per-sub-step position gain
+                                of the reference's arm motor (0.01, env.py:154,170): collision and deflection tests of
+                                step i see a_i = a_{i-1} + c (q_i - a_{i-1}), a_0 = q_0, c = 1 - (1 - gain)^substeps,
+                                the joint-limit test sees q_i (pybullet_tools/utils.py:3980) */
+    int32_t arm_lag_substeps;/* simulation sub-steps per interpolation step (50, env.py:157,216) */
 } pmp_params;
 
 /* The counter-based hash of the on-device gate (murmur3 finaliser over the mixed coordinates). */
@@ -131,6 +158,8 @@ static inline PMP_HOST_DEVICE uint32_t pmp_gate_hash(uint32_t seed, uint32_t e, 
 }
 
 int pmp_create(pmp_ctx** out, int device);
+/* after pmp_set_robot (which clears any hulls); NULL or n_hulls == 0 switches back to the sphere model */
+int pmp_set_robot_hulls(pmp_ctx* ctx, const pmp_hull_desc* hulls);
 int pmp_destroy(pmp_ctx* ctx);
 const char* pmp_last_error(pmp_ctx* ctx); /* ctx may be NULL: last creation error */
 int pmp_set_robot(pmp_ctx* ctx, const pmp_robot_desc* robot);
@@ -171,11 +200,15 @@ int pmp_check_configs(pmp_ctx* ctx, const float* q_dev, int32_t B, uint8_t* flag
  * primitives.py:225-241, env.py:230-238).  first_hit / n_steps are identical to those of a full call.
  * Replaces the loop of extend_towards_with_angle_constraint_multi_world (motion_planners/motion_planners/
  * primitives.py:196-255), check_forward_path_multi_world (rrt_connect_with_angle_constraints_v2.py:143-198)
- * and the cost accumulation of Command.execute_multi_world (pybullet_tools/kuka_primitives.py:467-521). */
+ * and the cost accumulation of Command.execute_multi_world (pybullet_tools/kuka_primitives.py:467-521).
+ *
+ * edge_base: index of edge 0 of this call in the caller's whole batch.  It enters only the on-device gate's hash
+ * (seed, edge_base + e, step, world), so that a batch validated in pieces (chunks, shards over ranks) draws exactly
+ * the pass-through decisions of the unsplit batch; pass 0 for a whole batch. */
 int pmp_validate_edges(pmp_ctx* ctx, const float* q0_dev, const float* q1_dev, int32_t E, int32_t max_steps,
                        int32_t backward, int32_t* first_hit_dev, int32_t* n_steps_dev, float* max_defl_dev,
                        float* over_dev, float* ee_len_dev, float* cost_dev, uint32_t* rigid_mask_dev,
-                       uint32_t* exceed_mask_dev, void* stream);
+                       uint32_t* exceed_mask_dev, void* stream, int32_t edge_base);
 
 /* Same with HOST buffers: copies q0/q1 to the device, runs the kernel, copies the requested outputs back
  * and synchronises.  This is the call a CPU-side planner makes. */

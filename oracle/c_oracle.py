@@ -19,78 +19,72 @@ LIB = os.path.join(HERE, "_build", "liboracle_edgecheck.so")
 
 
 def build(force: bool = False) -> str:
-    deps = [os.path.join(HERE, "edgecheck_oracle.c"), os.path.join(HERE, "..", "include", "pmp_edgecheck.h")]
+    deps = [os.path.join(HERE, "edgecheck_oracle.c"), os.path.join(HERE, "hull_gjk.c"),
+            os.path.join(HERE, "..", "include", "pmp_edgecheck.h")]
     if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
         # -march=native binaries are rebuilt on the machine that runs them when possible
         subprocess.run(["make", "-C", HERE, "-B"], check=True, capture_output=True)
     return LIB
 
 
-_lib = None
+_libs = {}
 NATIVE_LIB = os.path.join(HERE, "_build", "liboracle_edgecheck_native.so")
+SINGLE_LIB = os.path.join(HERE, "_build", "liboracle_edgecheck_f32.so")
+NATIVE_SINGLE_LIB = os.path.join(HERE, "_build", "liboracle_edgecheck_f32_native.so")
 
 
 def build_native() -> bool:
     """Rebuild with -march=native on THIS machine (used by bench.py for the timed CPU baseline)."""
     try:
         subprocess.run(["make", "-C", HERE, "native"], check=True, capture_output=True)
-        return os.path.exists(NATIVE_LIB)
+        return os.path.exists(NATIVE_LIB) and os.path.exists(NATIVE_SINGLE_LIB)
     except Exception:
         return False
 
 
-def load(native: bool = False):
-    global _lib
-    if _lib is None:
-        path = LIB
+def load(native: bool = False, single: bool = False):
+    """The C twin: double precision (parity tests) or, with ``single``, the float32 build (CPU baseline)."""
+    key = (bool(native), bool(single))
+    if key not in _libs:
+        path = SINGLE_LIB if single else LIB
         if native and build_native():
-            path = NATIVE_LIB
-        elif not os.path.exists(LIB):
+            path = NATIVE_SINGLE_LIB if single else NATIVE_LIB
+        else:
             build()
         try:
-            _lib = C.CDLL(path)
+            lib = C.CDLL(path)
         except OSError:
             build(force=True)
-            _lib = C.CDLL(LIB)
+            lib = C.CDLL(SINGLE_LIB if single else LIB)
         vp = C.c_void_p
-        _lib.pmp_oracle_validate_edges.argtypes = [C.POINTER(_capi.RobotDesc), C.POINTER(_capi.WorldDesc),
-                                                   C.POINTER(_capi.Params), vp, vp, C.c_int32, C.c_int32, C.c_int32] + \
-            [vp] * 8 + [C.c_int32]
-        _lib.pmp_oracle_check_configs.argtypes = [C.POINTER(_capi.RobotDesc), C.POINTER(_capi.WorldDesc),
-                                                  C.POINTER(_capi.Params), vp, C.c_int32, vp, vp, vp, vp, C.c_int32]
-        _lib.pmp_oracle_validate_edges.restype = C.c_int
-        _lib.pmp_oracle_check_configs.restype = C.c_int
-        _lib.pmp_oracle_max_threads.restype = C.c_int
-    return _lib
+        lib.pmp_oracle_validate_edges.argtypes = [C.POINTER(_capi.RobotDesc), C.POINTER(_capi.WorldDesc),
+                                                  C.POINTER(_capi.Params), vp, vp, C.c_int32, C.c_int32, C.c_int32] + \
+            [vp] * 8 + [C.c_int32, vp]
+        lib.pmp_oracle_check_configs.argtypes = [C.POINTER(_capi.RobotDesc), C.POINTER(_capi.WorldDesc),
+                                                 C.POINTER(_capi.Params), vp, C.c_int32, vp, vp, vp, vp, C.c_int32, vp]
+        lib.pmp_oracle_validate_edges.restype = C.c_int
+        lib.pmp_oracle_check_configs.restype = C.c_int
+        lib.pmp_oracle_max_threads.restype = C.c_int
+        _libs[key] = lib
+    return _libs[key]
 
 
 class COracle:
     """Holds the packed tables (same packer as the CUDA path) and calls the C twin."""
 
     def __init__(self, robot, worlds, obstacles=None, resolution=np.radians(3), deflection_limit=0.30, alpha=0.1,
-                 iterations=4, max_step=0.5, reg_eps=1e-4, stem_radius=None, mode="our_method", dense=False,
-                 native=False):
-        self.lib = load(native)
+                 iterations=4, max_step=0.5, reg_eps=1e-4, stem_margin=1e-3, gravity_sag=True, arm_lag_gain=0.0,
+                 arm_lag_substeps=50, mode="our_method", dense=False, native=False, use_hulls=True, single=False):
+        """``single``: the float32 build of the twin (the CPU baseline of bench.py); parity tests use the double one."""
+        self.lib = load(native, single)
         self.rt = pack_robot(robot, obstacles)
-        from plant_motion_planning_b200.model.tables import WorldTables
-        self.wt = worlds if isinstance(worlds, WorldTables) else pack_worlds(list(worlds), stem_radius)
-        t = self.rt
-        d = _capi.RobotDesc()
-        d.dof, d.n_spheres, d.n_links, d.n_fixed = t.dof, t.n_spheres, t.n_links, t.n_fixed
-        d.joint_C, d.joint_A, d.joint_B = _capi.fptr(t.joint_C), _capi.fptr(t.joint_A), _capi.fptr(t.joint_B)
-        d.joint_t, d.lower, d.upper = _capi.fptr(t.joint_t), _capi.fptr(t.lower), _capi.fptr(t.upper)
-        d.circular = _capi.bptr(t.circular)
-        d.base_R, d.base_t = _capi.fptr(t.base_R), _capi.fptr(t.base_t)
-        d.sph_joint, d.sph_center = _capi.iptr(t.sph_joint), _capi.fptr(t.sph_center)
-        d.sph_radius, d.self_mask = _capi.fptr(t.sph_radius), _capi.uptr(t.self_mask)
-        d.link_joint, d.link_R = _capi.iptr(t.link_joint), _capi.fptr(t.link_R)
-        d.link_t, d.link_com = _capi.fptr(t.link_t), _capi.fptr(t.link_com)
-        d.ee_joint = t.ee_joint
-        d.ee_local = (C.c_float * 3)(*[float(v) for v in t.ee_local])
-        d.fixed_kind, d.fixed_R = _capi.iptr(t.fixed_kind), _capi.fptr(t.fixed_R)
-        d.fixed_t, d.fixed_half = _capi.fptr(t.fixed_t), _capi.fptr(t.fixed_half)
-        d.fixed_mask = _capi.uptr(t.fixed_mask)
-        self.rd = d
+        from plant_motion_planning_b200.model.tables import WorldTables, default_obstacles
+        self.wt = worlds if isinstance(worlds, WorldTables) else pack_worlds(list(worlds), stem_margin, gravity_sag)
+        self.rd = _capi.robot_desc(self.rt)
+        self.hd, self._hull_keep = None, None
+        if use_hulls and getattr(robot, "hulls", None) is not None:
+            n_obs = len(default_obstacles() if obstacles is None else list(obstacles))
+            self.hd, self._hull_keep = _capi.hull_desc(robot.hulls, n_obs)
         w = _capi.WorldDesc()
         self._stems = np.ascontiguousarray(self.wt.stems.reshape(-1))
         self._boxes = np.ascontiguousarray(self.wt.boxes.reshape(-1))
@@ -99,7 +93,10 @@ class COracle:
         w.n_boxes, w.boxes = _capi.iptr(self.wt.n_boxes), _capi.fptr(self._boxes)
         self.wd = w
         self.prm = _capi.Params(float(resolution), deflection_limit, alpha, max_step, reg_eps, iterations, MODES[mode],
-                                1 if dense else 0, 0, 0.0, 0)
+                                1 if dense else 0, 0, 0.0, float(arm_lag_gain), int(arm_lag_substeps))
+
+    def _hp(self):
+        return C.byref(self.hd) if self.hd is not None else None
 
     @property
     def max_threads(self) -> int:
@@ -119,7 +116,7 @@ class COracle:
         rc = self.lib.pmp_oracle_validate_edges(
             C.byref(self.rd), C.byref(self.wd), C.byref(self.prm), vp(q0), vp(q1), E, max_steps, 1 if backward else 0,
             vp(out["first_hit"]), vp(out["n_steps"]), vp(out["max_deflection"]), vp(out["over_limit"]), vp(out["ee_len"]),
-            vp(out["cost"]), vp(out.get("rigid_mask")), vp(out.get("exceed_mask")), int(n_threads))
+            vp(out["cost"]), vp(out.get("rigid_mask")), vp(out.get("exceed_mask")), int(n_threads), self._hp())
         assert rc == 0
         return out
 
@@ -131,6 +128,6 @@ class COracle:
         vp = lambda a: C.c_void_p(a.ctypes.data)
         rc = self.lib.pmp_oracle_check_configs(C.byref(self.rd), C.byref(self.wd), C.byref(self.prm), vp(q), B,
                                                vp(out["flags"]), vp(out["deflection"]), vp(out["theta"]), vp(out["ee"]),
-                                               int(n_threads))
+                                               int(n_threads), self._hp())
         assert rc == 0
         return out

@@ -22,21 +22,32 @@ Each function cites the reference lines it restates (paths relative to
 
 Quasi-static plant model (replaces env.py:127-163 -- spring torques + 50 x stepSimulation):
   every stem s has two angles th = (tx, ty), |th| <= limit, pose  T_s = T_parent . origin_s . Rx(tx) . Ry(ty);
-  its collision body is a capsule on the local z axis, z in [z0, z1], radius r_s.  Stems are visited
-  parents first.  For each stem, starting from th = 0, K damped Gauss-Newton steps on the arm-sphere
-  penetrations are applied (all quantities in the world frame, u = stem axis, o = joint origin):
-     for every arm sphere a:  tau = clamp((c_a - o).u, z0, z1),  dv = c_a - o - tau u,  dist = |dv|,
-         pen_a = max(r_a + r_s - dist, 0),
-         J_a = d(pen_a)/d(th) = -(tau / dist) (dv . (ax x u),  dv . (ay x u))      (ax, ay = joint axes)
+  its collision body is the reference's box (rand_gen_plants_programmatically_main.py:30-51): half extents (w, w, h)
+  centred zc = z_offset + h up the stem's z axis, with Bullet's 1 mm margin carved out of it (core half extents
+  w - m, h - m; the margin is added back as a radius, so faces stay where the reference puts them and edges are
+  rounded by m).  Stems are visited parents first.  A stem starts from its REST pose th0 -- the static balance of
+  the reference's springs and gravity without contact (stems are 10 kg; the reference's observers capture their
+  reference pose at th = 0, so the sag counts as deflection) -- computed by oracle/dynamic_oracle.static_rest_pose.
+  If no arm sphere overlaps the box in that pose the stem stays there; otherwise K damped Gauss-Newton steps on the
+  arm-sphere penetrations are applied.  In the stem's link frame (R_s = R_v Rx Ry, joint origin o):
+     for every arm sphere a:  pf = R_s^T (c_a - o)  (relative to the joint),  p = pf - zc e_z  (relative to the box
+         centre),  q = clamp(p, +-half),  d = p - q,  dist = |d|,  pen_a = max(r_a + m - dist, 0),
+         J_a = d(dist)/d(th) = ((cy, 0, sy) . (d x pf), (0, 1, 0) . (d x pf)) / dist
      H = sum_a pen_a J_a J_a^T,  g = sum_a pen_a^2 J_a,  S = sum_a pen_a,  lam = eps S
      dth = adj(H + lam I) g / max(det(H + lam I), lam (lam + tr H))   (skipped when S = 0; the max is an identity in
      exact arithmetic, it guards the float32 cancellation), each component clamped to +-max_step,
      th <- clamp(th + dth, +-limit)
   i.e. a least-squares removal of the penetrations weighted by their depth: for a single contact it is the
-  minimum-norm joint motion that removes the penetration to first order (= the minimum-spring-energy response
-  of a frictionless contact), and it is continuous in the arm configuration (no arg-max over spheres), which
-  is what makes float32-vs-float64 parity meaningful.  Children see their parent's final pose; a pushed child
-  does not load its parent; untouched stems stay at th = 0 (no gravity sag).
+  minimum-norm joint motion that removes the penetration to first order, and it is continuous in the arm
+  configuration (no arg-max over spheres), which is what makes float32-vs-float64 parity meaningful.  Children see
+  their parent's final pose; a pushed child does not load its parent (measured gap to the time-stepped restatement:
+  DESIGN.md section 4, tools/dynamic_gap_report.py).
+
+Arm lag (optional, OracleParams.arm_lag_gain > 0): the reference drives the arm with a position motor that closes
+1 % of the joint error per sub-step (env.py:154,170) for 50 sub-steps per interpolation step, after teleporting it to
+the first step of an edge (env.py:222-227, primitives.py:220), so the collision / deflection tests of step i see
+    a_0 = q_0,  a_i = a_{i-1} + c (q_i - a_{i-1}),  c = 1 - (1 - gain)^substeps
+while the joint-limit test sees q_i itself (pybullet_tools/utils.py:3980).
 """
 from __future__ import annotations
 
@@ -48,7 +59,7 @@ import numpy as np
 
 from plant_motion_planning_b200.model.plants import OBS_ANGLE, OBS_MOD3, PlantWorld
 from plant_motion_planning_b200.model.robot import PRIM_BOX, PRIM_CYLINDER, PRIM_SPHERE, FixedPrim, RobotModel
-from plant_motion_planning_b200.model.tables import default_obstacles, stem_capsule
+from plant_motion_planning_b200.model.tables import default_obstacles
 from plant_motion_planning_b200.model.transforms import matrix_to_quat
 
 MODE_OUR_METHOD, MODE_AVOID_ALL, MODE_IGNORE_ALL = 0, 1, 2
@@ -61,9 +72,47 @@ class OracleParams:
     iterations: int = 4
     max_step: float = 0.5
     reg_eps: float = 1e-4
-    stem_radius: Optional[float] = None
+    stem_margin: float = 1.0e-3               # Bullet's collision margin of the stem boxes (carved out of the box)
+    gravity_sag: bool = True                  # stems rest at their spring/gravity balance, not at th = 0
+    arm_lag_gain: float = 0.0                 # per-sub-step position gain of the arm motor (reference: 0.01); 0 = no lag
+    arm_lag_substeps: int = 50                # env.py:157, 216
     alpha: float = 0.1                        # kuka_primitives.py:476
     mode: int = MODE_OUR_METHOD
+
+
+def stem_box(stem, margin: float):
+    """(core half width, core half height, zc): the stem's box with Bullet's margin carved out
+    (rand_gen_plants_programmatically_main.py:30-37: halfExtents (w, w, h), collisionFramePosition z = spacing + h)."""
+    return (max(stem.half_width - margin, 0.0), max(stem.half_height - margin, 0.0), stem.z_offset + stem.half_height)
+
+
+def rest_theta(world: PlantWorld, prm: "OracleParams") -> np.ndarray:
+    """Rest pose [P, 2] of the world's stems (zeros without gravity sag).  Cached on the world object."""
+    if not prm.gravity_sag or world.num_stems == 0:
+        return np.zeros((world.num_stems, 2))
+    cached = getattr(world, "_oracle_rest_theta", None)
+    if cached is None:
+        from oracle.dynamic_oracle import static_rest_pose
+        cached = static_rest_pose(world)
+        world._oracle_rest_theta = cached
+    return cached
+
+
+def lag_closure(gain: float, substeps: int) -> float:
+    """Fraction of the joint error the arm motor closes during one interpolation step: 1 - (1 - gain)^substeps."""
+    return 1.0 - (1.0 - gain) ** substeps if gain > 0.0 else 1.0
+
+
+def lagged_configs(Q: np.ndarray, prm: "OracleParams") -> np.ndarray:
+    """Configurations the arm actually has at the steps of one edge: a_0 = q_0, a_i = a_{i-1} + c (q_i - a_{i-1})."""
+    Q = np.asarray(Q, dtype=np.float64)
+    c = lag_closure(prm.arm_lag_gain, prm.arm_lag_substeps)
+    if c >= 1.0 or Q.shape[0] == 0:
+        return Q.copy()
+    out = Q.copy()
+    for i in range(1, Q.shape[0]):
+        out[i] = out[i - 1] + c * (Q[i] - out[i - 1])
+    return out
 
 
 # ----------------------------------------------------------------------------- planner callables
@@ -232,14 +281,19 @@ def _prim_hit(prim: FixedPrim, c: np.ndarray, r) -> np.ndarray:
 
 
 def rigid_hit(model: RobotModel, obstacles: Sequence[FixedPrim], Q: np.ndarray,
-              centers: Optional[np.ndarray] = None, inflate: float = 0.0) -> np.ndarray:
+              centers: Optional[np.ndarray] = None, inflate: float = 0.0,
+              Q_limits: Optional[np.ndarray] = None) -> np.ndarray:
     """get_collision_fn_with_controls_v3 (pybullet_tools/utils.py:3965-4016), world-independent part:
     joint limits, self pairs, moving links x fixed bodies.
     ``inflate`` (tests only): every sphere radius grows by it and the limits shrink by it, so
     rigid_hit(+eps) != rigid_hit(-eps) marks configurations within eps of a decision boundary."""
     Q = np.atleast_2d(Q)
+    if getattr(model, "hulls", None) is not None and inflate == 0.0:
+        return limits_violated(model, Q if Q_limits is None else np.atleast_2d(Q_limits)) | \
+            hull_rigid_hit(model, obstacles, Q)
     c = sphere_centers(model, Q) if centers is None else centers
-    hit = limits_violated(model, Q, inflate)
+    # the limit test sees the commanded configuration, the geometry the (possibly lagged) simulated one
+    hit = limits_violated(model, Q if Q_limits is None else np.atleast_2d(Q_limits), inflate)
     A = model.num_spheres
     rad = model.sph_radius + inflate
     for a in range(A):
@@ -257,6 +311,40 @@ def rigid_hit(model: RobotModel, obstacles: Sequence[FixedPrim], Q: np.ndarray,
     return hit
 
 
+def hull_clearance(model: RobotModel, obstacles: Sequence[FixedPrim], Q: np.ndarray) -> np.ndarray:
+    """Smallest signed Bullet distance [B] over the self pairs and the (hull, obstacle) pairs of a model that carries
+    the convex hulls of its collision meshes: GJK distance of the margin-free shapes minus both margins
+    (pybullet_tools/utils.py:3390-3441 on btConvexHullShape / btBoxShape / btSphereShape; see oracle/hull_oracle.py).
+    Intersecting cores report -(margin_a + margin_b)."""
+    from oracle import hull_oracle as H
+    hm = model.hulls
+    Q = np.atleast_2d(np.asarray(Q, dtype=np.float64))
+    R, t = joint_frames(model, Q)
+    B = Q.shape[0]
+    shapes = [H.Shape(v, m, n) for v, m, n in zip(hm.verts, hm.margin, hm.link_names)]
+    nH = len(shapes)
+    frames = np.zeros((B, nH + len(obstacles), 12))
+    for k in range(nH):
+        j = int(hm.joint[k])
+        frames[:, k, :9] = R[:, j].reshape(B, 9)
+        frames[:, k, 9:] = t[:, j]
+    for f, prim in enumerate(obstacles):
+        if prim.kind == PRIM_BOX:
+            shapes.append(H.Shape.bullet_box(prim.half, hm.fixed_margin, prim.name))
+        elif prim.kind == PRIM_SPHERE:
+            shapes.append(H.Shape(np.zeros((1, 3)), float(prim.half[0]), prim.name))
+        else:
+            raise NotImplementedError("exact hull test supports box and sphere obstacles")
+        frames[:, nH + f] = H.frame12(prim.R, prim.t)[None]
+    pairs = [tuple(int(v) for v in p) for p in hm.pairs] + [(h, nH + f) for f in range(len(obstacles)) for h in range(nH)]
+    d = H.batch_distances(shapes, frames, pairs)
+    return d.min(axis=1) if d.shape[1] else np.full(B, np.inf)
+
+
+def hull_rigid_hit(model: RobotModel, obstacles: Sequence[FixedPrim], Q: np.ndarray) -> np.ndarray:
+    return hull_clearance(model, obstacles, Q) <= 0.0
+
+
 # ----------------------------------------------------------------------------- plants
 def _rx_ry(tx: np.ndarray, ty: np.ndarray) -> np.ndarray:
     cx, sx, cy, sy = np.cos(tx), np.sin(tx), np.cos(ty), np.sin(ty)
@@ -272,7 +360,7 @@ def plant_equilibrium(world: PlantWorld, centers: np.ndarray, radii: np.ndarray,
     """Quasi-static stand-in for MultiPlantWorld.step (env.py:127-163, 212-219); see module docstring.
 
     Returns theta [B,P,2], R [B,P,3,3], t [B,P,3] (final stem link frames) and rest_pen [B] =
-    deepest sphere-vs-capsule penetration at zero deflection (> 0 <=> the arm touches the undeflected plant).
+    deepest sphere-vs-box penetration in the rest pose (> 0 <=> the arm touches the undeflected plant).
     """
     B = centers.shape[0]
     P = world.num_stems
@@ -280,7 +368,8 @@ def plant_equilibrium(world: PlantWorld, centers: np.ndarray, radii: np.ndarray,
     Rs = np.zeros((B, P, 3, 3))
     ts = np.zeros((B, P, 3))
     rest_pen = np.full(B, -np.inf)
-    ex = np.array([1.0, 0.0, 0.0])
+    th0 = rest_theta(world, prm)
+    m = prm.stem_margin
     for s, stem in enumerate(world.stems):
         if stem.parent < 0:
             Rp = np.broadcast_to(np.eye(3), (B, 3, 3))
@@ -289,17 +378,15 @@ def plant_equilibrium(world: PlantWorld, centers: np.ndarray, radii: np.ndarray,
             Rp, tp = Rs[:, stem.parent], ts[:, stem.parent]
         Rv = Rp @ stem.origin.R[None]
         tv = np.einsum("bij,j->bi", Rp, stem.origin.t) + tp
-        z0, z1, rs = stem_capsule(stem, prm.stem_radius)
-        tx = np.zeros(B)
-        ty = np.zeros(B)
+        hw, hh, zc = stem_box(stem, m)
+        half = np.array([hw, hw, hh])
+        tx = np.full(B, th0[s, 0])
+        ty = np.full(B, th0[s, 1])
+        touch = np.zeros(B, dtype=bool)
         iters = prm.iterations if solve else 1
         for it in range(iters):
-            cx, sx, cy, sy = np.cos(tx), np.sin(tx), np.cos(ty), np.sin(ty)
-            u = np.einsum("bij,bj->bi", Rv, np.stack([sy, -sx * cy, cx * cy], axis=1))
-            ax = np.einsum("bij,j->bi", Rv, ex)
-            ay = np.einsum("bij,bj->bi", Rv, np.stack([np.zeros(B), cx, sx], axis=1))
-            bx = np.cross(ax, u)
-            by = np.cross(ay, u)
+            cy, sy = np.cos(ty), np.sin(ty)
+            Rl = Rv @ _rx_ry(tx, ty)
             Hxx = np.zeros(B)
             Hxy = np.zeros(B)
             Hyy = np.zeros(B)
@@ -308,16 +395,19 @@ def plant_equilibrium(world: PlantWorld, centers: np.ndarray, radii: np.ndarray,
             S = np.zeros(B)
             raw_max = np.full(B, -np.inf)
             for a in range(centers.shape[1]):
-                w = centers[:, a] - tv
-                tau = np.clip(np.sum(w * u, axis=1), z0, z1)
-                dv = w - tau[:, None] * u
-                dist = np.sqrt(np.sum(dv * dv, axis=1))
-                raw = radii[a] + rs - dist
+                pf = np.einsum("bji,bj->bi", Rl, centers[:, a] - tv)        # R_l^T (c - o)
+                p = pf.copy()
+                p[:, 2] -= zc
+                q = np.clip(p, -half, half)
+                d = p - q
+                dist = np.sqrt(np.sum(d * d, axis=1))
+                raw = radii[a] + m - dist
                 raw_max = np.maximum(raw_max, raw)
                 pen = np.maximum(raw, 0.0)
-                sc = -tau / np.maximum(dist, 1e-12)
-                Jx = sc * np.sum(dv * bx, axis=1)
-                Jy = sc * np.sum(dv * by, axis=1)
+                mm = np.cross(d, pf)
+                inv = 1.0 / np.maximum(dist, 1e-12)
+                Jx = inv * (cy * mm[:, 0] + sy * mm[:, 2])
+                Jy = inv * mm[:, 1]
                 Hxx += pen * Jx * Jx
                 Hxy += pen * Jx * Jy
                 Hyy += pen * Jy * Jy
@@ -327,20 +417,21 @@ def plant_equilibrium(world: PlantWorld, centers: np.ndarray, radii: np.ndarray,
             if it == 0:
                 # rest_pen is only used by the avoid_all test, where no stem is ever deflected
                 rest_pen = np.maximum(rest_pen, raw_max)
+                touch = raw_max > 0.0       # a stem that nothing touches in its initial pose is never pushed
             if not solve:
                 break
             lam = prm.reg_eps * S
             a11 = Hxx + lam
             a22 = Hyy + lam
-            act = S > 0.0
+            act = touch & (S > 0.0)
             # det(H + lam I) = lam^2 + lam tr(H) + det(H) >= lam (lam + tr H); the bound only matters in float32
             det = np.where(act, np.maximum(a11 * a22 - Hxy * Hxy, lam * (lam + Hxx + Hyy)), 1.0)
             dx = np.where(act, (a22 * gx - Hxy * gy) / det, 0.0)
             dy = np.where(act, (a11 * gy - Hxy * gx) / det, 0.0)
             dx = np.clip(dx, -prm.max_step, prm.max_step)
             dy = np.clip(dy, -prm.max_step, prm.max_step)
-            tx = np.clip(tx + dx, -stem.limit, stem.limit)
-            ty = np.clip(ty + dy, -stem.limit, stem.limit)
+            tx = np.where(act, np.clip(tx + dx, -stem.limit, stem.limit), tx)
+            ty = np.where(act, np.clip(ty + dy, -stem.limit, stem.limit), ty)
         theta[:, s, 0], theta[:, s, 1] = tx, ty
         Rs[:, s] = Rv @ _rx_ry(tx, ty)
         ts[:, s] = tv
@@ -482,15 +573,17 @@ class ConfigResult:
 
 
 def check_configs(model: RobotModel, worlds: Sequence[PlantWorld], Q: np.ndarray, prm: OracleParams,
-                  obstacles: Optional[Sequence[FixedPrim]] = None) -> ConfigResult:
+                  obstacles: Optional[Sequence[FixedPrim]] = None, Q_limits: Optional[np.ndarray] = None) -> ConfigResult:
     """One (configuration x world) evaluation = collision_fn after env.step
-    (env.py:212-238; pybullet_tools/utils.py:3827-3857) without the 5 % random pass-through."""
+    (env.py:212-238; pybullet_tools/utils.py:3827-3857) without the 5 % random pass-through.
+    ``Q_limits``: the COMMANDED configurations for the joint-limit test when ``Q`` holds the lagged ones the
+    geometry is in (pybullet_tools/utils.py:3980 tests q, everything else the simulation state)."""
     obstacles = default_obstacles() if obstacles is None else obstacles
     Q = np.atleast_2d(np.asarray(Q, dtype=np.float64))
     B, W = Q.shape[0], len(worlds)
     Pmax = max(1, max(w.num_stems for w in worlds))
     c = sphere_centers(model, Q)
-    base_hit = rigid_hit(model, obstacles, Q, c)
+    base_hit = rigid_hit(model, obstacles, Q, c, Q_limits=Q_limits)
     rigid = np.repeat(base_hit[:, None], W, axis=1)
     exceeded = np.zeros((B, W), dtype=bool)
     defl = np.zeros((B, W, Pmax))
@@ -535,7 +628,10 @@ def validate_edge(model: RobotModel, worlds: Sequence[PlantWorld], q1, q2, prm: 
     q1f = np.asarray(q1, dtype=np.float64)
     q2f = np.asarray(q2, dtype=np.float64)
     Q = edge_configs(model, q1f, q2f, prm.resolution, backward)
-    res = check_configs(model, worlds, Q, prm, obstacles)
+    if prm.arm_lag_gain > 0.0:
+        res = check_configs(model, worlds, lagged_configs(Q, prm), prm, obstacles, Q_limits=Q)
+    else:
+        res = check_configs(model, worlds, Q, prm, obstacles)
     n = Q.shape[0]
     viol = np.any(res.rigid | res.exceeded, axis=1)
     first = int(np.argmax(viol)) if viol.any() else n

@@ -44,7 +44,16 @@ class Params(C.Structure):
     _fields_ = [
         ("resolution", C.c_double), ("deflection_limit", C.c_float), ("alpha", C.c_float),
         ("max_step", C.c_float), ("reg_eps", C.c_float), ("iterations", C.c_int32), ("mode", C.c_int32),
-        ("dense", C.c_int32), ("gate_seed", C.c_uint32), ("gate_probability", C.c_float), ("reserved", C.c_int32),
+        ("dense", C.c_int32), ("gate_seed", C.c_uint32), ("gate_probability", C.c_float),
+        ("arm_lag_gain", C.c_float), ("arm_lag_substeps", C.c_int32),
+    ]
+
+
+class HullDesc(C.Structure):
+    _fields_ = [
+        ("n_hulls", C.c_int32), ("hull_joint", c_int32_p), ("hull_off", c_int32_p), ("hull_verts", c_float_p),
+        ("hull_margin", c_float_p), ("n_pairs", C.c_int32), ("pairs", c_int32_p), ("sph_hull", c_int32_p),
+        ("sph_radius_outer", c_float_p), ("fixed_margin", C.c_float), ("n_fixed_exact", C.c_int32),
     ]
 
 
@@ -57,7 +66,7 @@ class LaunchInfo(C.Structure):
 
 
 EXPORTS = [
-    "pmp_create", "pmp_destroy", "pmp_last_error", "pmp_set_robot", "pmp_set_worlds", "pmp_set_params",
+    "pmp_create", "pmp_destroy", "pmp_last_error", "pmp_set_robot", "pmp_set_robot_hulls", "pmp_set_worlds", "pmp_set_params",
     "pmp_num_worlds", "pmp_max_stems", "pmp_fk", "pmp_check_configs", "pmp_validate_edges",
     "pmp_validate_edges_host", "pmp_check_configs_host", "pmp_get_launch_info", "pmp_measure_fp32_peak",
     "pmp_nearest", "pmp_edge_points", "pmp_tree_extend",
@@ -100,7 +109,8 @@ def load() -> C.CDLL:
     lib.pmp_max_stems.argtypes = [vp]
     lib.pmp_fk.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp]
     lib.pmp_check_configs.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, vp]
-    lib.pmp_validate_edges.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32] + [vp] * 9
+    lib.pmp_set_robot_hulls.argtypes = [vp, C.POINTER(HullDesc)]
+    lib.pmp_validate_edges.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32] + [vp] * 9 + [C.c_int32]
     lib.pmp_validate_edges_host.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32] + [vp] * 8
     lib.pmp_check_configs_host.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp]
     lib.pmp_get_launch_info.argtypes = [vp, C.POINTER(LaunchInfo)]
@@ -133,3 +143,49 @@ def uptr(a: np.ndarray):
 def bptr(a: np.ndarray):
     assert a.dtype == np.uint8 and a.flags["C_CONTIGUOUS"]
     return a.ctypes.data_as(c_uint8_p)
+
+
+def robot_desc(t) -> RobotDesc:
+    """pmp_robot_desc over the arrays of a model.tables.RobotTables (which must outlive the call it is passed to)."""
+    d = RobotDesc()
+    d.dof, d.n_spheres, d.n_links, d.n_fixed = t.dof, t.n_spheres, t.n_links, t.n_fixed
+    d.joint_C, d.joint_A, d.joint_B = fptr(t.joint_C), fptr(t.joint_A), fptr(t.joint_B)
+    d.joint_t, d.lower, d.upper = fptr(t.joint_t), fptr(t.lower), fptr(t.upper)
+    d.circular = bptr(t.circular)
+    d.base_R, d.base_t = fptr(t.base_R), fptr(t.base_t)
+    d.sph_joint, d.sph_center = iptr(t.sph_joint), fptr(t.sph_center)
+    d.sph_radius, d.self_mask = fptr(t.sph_radius), uptr(t.self_mask)
+    d.link_joint, d.link_R = iptr(t.link_joint), fptr(t.link_R)
+    d.link_t, d.link_com = fptr(t.link_t), fptr(t.link_com)
+    d.ee_joint = t.ee_joint
+    d.ee_local = (C.c_float * 3)(*[float(v) for v in t.ee_local])
+    d.fixed_kind, d.fixed_R = iptr(t.fixed_kind), fptr(t.fixed_R)
+    d.fixed_t, d.fixed_half = fptr(t.fixed_t), fptr(t.fixed_half)
+    d.fixed_mask = uptr(t.fixed_mask)
+    return d
+
+
+def hull_desc(hulls, n_fixed_exact: int):
+    """(pmp_hull_desc, keep-alive list) for a model.robot.HullModel; `n_fixed_exact` = number of obstacle primitives
+    at the head of the static-primitive table."""
+    H = len(hulls.verts)
+    off = np.zeros(H + 1, dtype=np.int32)
+    for i, v in enumerate(hulls.verts):
+        off[i + 1] = off[i] + len(v)
+    keep = {
+        "joint": np.ascontiguousarray(hulls.joint, dtype=np.int32), "off": off,
+        "verts": np.ascontiguousarray(np.concatenate(hulls.verts, axis=0), dtype=np.float32).reshape(-1),
+        "margin": np.ascontiguousarray(hulls.margin, dtype=np.float32),
+        "pairs": np.ascontiguousarray(hulls.pairs, dtype=np.int32).reshape(-1),
+        "sph_hull": np.ascontiguousarray(hulls.sph_hull, dtype=np.int32),
+        "outer": np.ascontiguousarray(hulls.sph_radius_outer, dtype=np.float32),
+    }
+    d = HullDesc()
+    d.n_hulls = H
+    d.hull_joint, d.hull_off, d.hull_verts = iptr(keep["joint"]), iptr(keep["off"]), fptr(keep["verts"])
+    d.hull_margin = fptr(keep["margin"])
+    d.n_pairs = len(hulls.pairs)
+    d.pairs, d.sph_hull, d.sph_radius_outer = iptr(keep["pairs"]), iptr(keep["sph_hull"]), fptr(keep["outer"])
+    d.fixed_margin = float(hulls.fixed_margin)
+    d.n_fixed_exact = int(n_fixed_exact)
+    return d, keep

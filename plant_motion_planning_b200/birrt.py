@@ -155,13 +155,30 @@ def check_forward_path(path2: List[TreeNode], backend: FlagBackend, nodes1: List
     return True
 
 
+def is_default_metric(distance_fn) -> bool:
+    """True when `distance_fn` is known to be planner_fns.get_distance_fn with unit weights and the 2-norm (it carries
+    a `default_metric` attribute); anything else is evaluated node by node, like the reference's argmin."""
+    return bool(getattr(distance_fn, "default_metric", False))
+
+
+def euclidean_distance(q1: Conf, q2: Conf) -> float:
+    """motion_planners/motion_planners/utils.py:159-160 get_distance: the plain 2-norm of q2 - q1 (no wrap, no weights).
+    The reference's restart driver calls smooth_path_multi_world WITHOUT a distance_fn (meta.py:213-215), so the
+    smoother falls back to this (smoothing.py:66-67) -- it sets the np.random.choice probabilities."""
+    return float(np.linalg.norm(np.asarray(q2, dtype=np.float64) - np.asarray(q1, dtype=np.float64)))
+
+
 def rrt_connect_multi_world(start: Conf, goal: Conf, distance_fn, sample_fn, extend_fn, backend: FlagBackend,
                             max_iterations: int = 2000, log: Optional[PlanLog] = None, circular=None,
-                            vectorized_nearest: bool = True):
+                            vectorized_nearest: Optional[bool] = None):
     """Returns (path of configurations, node path) or (None, None).  `vectorized_nearest` assumes the default metric
     (unit weights, 2-norm, wrap on `circular` joints); pass False to call `distance_fn` node by node."""
     if first_violation(backend.flags([start]), True) == 0:
         return None
+    if vectorized_nearest is None:
+        vectorized_nearest = is_default_metric(distance_fn)
+    if circular is None:
+        circular = getattr(distance_fn, "circular", None)
     if vectorized_nearest:
         nodes1, nodes2 = ConfigTree([TreeNode(start)], circular), ConfigTree([TreeNode(goal)], circular)
     else:
@@ -194,7 +211,11 @@ def plan(env, start: Conf, goal: Conf, distance_fn, sample_fn, extend_fn, backen
     for name, q in (("Initial", start), ("End", goal)):
         if first_violation(backend.flags([q]), True) == 0:
             raise ValueError(f"{name} configuration is in collision")       # the reference exit()s here
-    res = rrt_connect_multi_world(start, goal, distance_fn, sample_fn, extend_fn, backend, max_iterations, log)
+    # the vectorised nearest-node search is the DEFAULT metric (unit weights, 2-norm, wrap on continuous joints);
+    # it needs the robot's circular mask, else a wrapped joint would pick a different nearest node than distance_fn
+    circular = getattr(getattr(env, "sample_robot", None), "circular", None)
+    res = rrt_connect_multi_world(start, goal, distance_fn, sample_fn, extend_fn, backend, max_iterations, log,
+                                  circular=circular, vectorized_nearest=is_default_metric(distance_fn))
     if res is None or res[0] is None:
         return None
     path = res[0]
@@ -343,7 +364,8 @@ def random_restarts_multi_world(start: Conf, goal: Conf, distance_fn, sample_fn,
         path = res[0]
         accepted = None
         for _ in range(smooth_attempts):
-            sm = smooth_path_multi_world(path, extend_fn, distance_fn, backend, max_iterations=smoothing_iterations, log=log)
+            # the reference passes no distance_fn here (meta.py:213-215): plain Euclidean get_distance
+            sm = smooth_path_multi_world(path, extend_fn, euclidean_distance, backend, max_iterations=smoothing_iterations, log=log)
             k = first_violation(backend.flags(sm), True) if sm else 0
             if log is not None:
                 log.edges.append(("resmooth-check", len(sm), k))
@@ -437,9 +459,10 @@ def extend_many(checker, q_from: np.ndarray, q_to: np.ndarray, backward: bool = 
     """Validate a batch of candidate extensions / shortcuts in ONE launch (pmp_validate_edges_host) and apply the
     gate per edge in batch order.  Returns (first_violation[E], n_steps[E], result dict)."""
     from .planner_fns import replay_gate
-    out = checker.validate_edges_host(q_from, q_to, backward=backward, want_masks=True)
+    ms = int(checker.config.max_steps)
+    out = checker.validate_edges_host(q_from, q_to, backward=backward, want_masks=True, max_steps=ms)
     E = out["n_steps"].shape[0]
-    cap = out["rigid_mask"].shape[2] * 32
+    cap = ms          # steps >= max_steps are not evaluated (their mask bits are 0): never count them as safe
     n_all = np.minimum(out["n_steps"], cap).astype(np.int32)
     # edges without any "deflection exceeded" bit draw no random number: their first violation is the lowest set bit
     # of the rigid masks OR-ed over the worlds (vectorised); only the others need the sequential gate replay

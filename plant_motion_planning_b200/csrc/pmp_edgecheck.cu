@@ -7,9 +7,11 @@
 #include <string.h>
 
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "pmp_launch.h"
+#include "pmp_hull.cuh"
 #include "pmp_tree.cuh"
 
 struct pmp_ctx {
@@ -22,6 +24,13 @@ struct pmp_ctx {
     PmpLinkTab h_links;
     PmpRobotTab* d_robot = nullptr;
     PmpLinkTab* d_links = nullptr;
+    // convex hulls of the arm's collision meshes (pmp_set_robot_hulls) and the pre-pass scratch (one bit per step)
+    bool has_hulls = false;
+    PmpHullTab h_hulls;
+    PmpHullTab* d_hulls = nullptr;
+    float4* d_hull_verts = nullptr;
+    void* d_rigid_scratch = nullptr;
+    size_t rigid_scratch_bytes = 0;
     float* d_stems = nullptr;
     int32_t* d_nstems = nullptr;
     float* d_boxes = nullptr;
@@ -103,6 +112,7 @@ extern "C" int pmp_destroy(pmp_ctx* ctx) {
     if (!ctx) return PMP_OK;
     cudaSetDevice(ctx->device);
     free_worlds(ctx);
+    cudaFree(ctx->d_hulls); cudaFree(ctx->d_hull_verts); cudaFree(ctx->d_rigid_scratch);
     cudaFree(ctx->d_robot); cudaFree(ctx->d_links); cudaFree(ctx->d_scratch); cudaFree(ctx->d_tree_scratch); cudaFree(ctx->d_work_counter);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -119,7 +129,10 @@ extern "C" int pmp_set_robot(pmp_ctx* ctx, const pmp_robot_desc* r) {
     if (r->n_fixed < 0 || r->n_fixed > PMP_MAX_FIXED) return fail(ctx, PMP_E_INVALID, "n_fixed out of range");
     if (r->ee_joint < 0 || r->ee_joint >= r->dof) return fail(ctx, PMP_E_INVALID, "ee_joint out of range");
     CK(cudaSetDevice(ctx->device));
-    PmpRobotTab& t = ctx->h_robot;
+    // the tables are built and validated in locals and committed only on success: a rejected description leaves the
+    // context (host mirrors and device tables) exactly as it was
+    static_assert(std::is_trivially_copyable<PmpRobotTab>::value && std::is_trivially_copyable<PmpLinkTab>::value, "POD tables");
+    PmpRobotTab t;
     memset(&t, 0, sizeof(t));
     const int D = r->dof, A = r->n_spheres, F = r->n_fixed, L = r->n_links;
     memcpy(t.joint_C, r->joint_C, sizeof(float) * 9 * D);
@@ -132,9 +145,10 @@ extern "C" int pmp_set_robot(pmp_ctx* ctx, const pmp_robot_desc* r) {
     memcpy(t.base_t, r->base_t, sizeof(float) * 3);
     memcpy(t.sph_center, r->sph_center, sizeof(float) * 3 * A);
     memcpy(t.sph_radius, r->sph_radius, sizeof(float) * A);
+    memcpy(t.sph_radius_outer, r->sph_radius, sizeof(float) * A);
     memcpy(t.self_mask, r->self_mask, sizeof(uint32_t) * A);
     memcpy(t.sph_joint, r->sph_joint, sizeof(int32_t) * A);
-    for (int a = A; a < PMP_MAX_SPHERES; ++a) { t.sph_joint[a] = -1; t.sph_radius[a] = -1.0e3f; }
+    for (int a = A; a < PMP_MAX_SPHERES; ++a) { t.sph_joint[a] = -1; t.sph_radius[a] = -1.0e3f; t.sph_radius_outer[a] = -1.0e3f; }
     for (int a = 0; a < A; ++a) {
         if (t.sph_joint[a] < 0 || t.sph_joint[a] >= D) return fail(ctx, PMP_E_INVALID, "sph_joint out of range");
         if (a && t.sph_joint[a] < t.sph_joint[a - 1]) return fail(ctx, PMP_E_INVALID, "spheres must be sorted by joint");
@@ -150,7 +164,7 @@ extern "C" int pmp_set_robot(pmp_ctx* ctx, const pmp_robot_desc* r) {
     t.ee_joint = r->ee_joint; t.dof = D; t.n_spheres = A; t.n_fixed = F;
     t.circular_mask = 0;
     for (int j = 0; j < D; ++j) if (r->circular && r->circular[j]) t.circular_mask |= (1u << j);
-    PmpLinkTab& lt = ctx->h_links;
+    PmpLinkTab lt;
     memset(&lt, 0, sizeof(lt));
     lt.n_links = L;
     if (L) {
@@ -158,12 +172,123 @@ extern "C" int pmp_set_robot(pmp_ctx* ctx, const pmp_robot_desc* r) {
         memcpy(lt.link_R, r->link_R, sizeof(float) * 9 * L);
         memcpy(lt.link_t, r->link_t, sizeof(float) * 3 * L);
         memcpy(lt.link_com, r->link_com, sizeof(float) * 3 * L);
+        for (int l = 0; l < L; ++l)
+            if (lt.link_joint[l] < -1 || lt.link_joint[l] >= D) return fail(ctx, PMP_E_INVALID, "link_joint out of range");
     }
+    for (int f = 0; f < F; ++f)
+        if (t.fixed_kind[f] < PMP_PRIM_BOX || t.fixed_kind[f] > PMP_PRIM_SPHERE) return fail(ctx, PMP_E_INVALID, "unknown fixed_kind");
     if (!ctx->d_robot) CK(cudaMalloc(&ctx->d_robot, sizeof(PmpRobotTab)));
     if (!ctx->d_links) CK(cudaMalloc(&ctx->d_links, sizeof(PmpLinkTab)));
     CK(cudaMemcpy(ctx->d_robot, &t, sizeof(t), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_links, &lt, sizeof(lt), cudaMemcpyHostToDevice));
+    ctx->h_robot = t;
+    ctx->h_links = lt;
     ctx->has_robot = true;
+    ctx->has_hulls = false;      // hulls describe one robot: a new robot starts on its sphere model
+    return PMP_OK;
+}
+
+extern "C" int pmp_set_robot_hulls(pmp_ctx* ctx, const pmp_hull_desc* h) {
+    if (!ctx) return PMP_E_INVALID;
+    if (!ctx->has_robot) return fail(ctx, PMP_E_STATE, "pmp_set_robot must come first");
+    CK(cudaSetDevice(ctx->device));
+    PmpRobotTab t = ctx->h_robot;
+    const int A = t.n_spheres, D = t.dof;
+    if (!h || h->n_hulls == 0) {
+        t.has_hulls = 0;
+        for (int a = 0; a < A; ++a) t.sph_radius_outer[a] = t.sph_radius[a];
+        CK(cudaMemcpy(ctx->d_robot, &t, sizeof(t), cudaMemcpyHostToDevice));
+        ctx->h_robot = t;
+        ctx->has_hulls = false;
+        return PMP_OK;
+    }
+    if (h->n_hulls < 0 || h->n_hulls > PMP_MAX_HULLS) return fail(ctx, PMP_E_INVALID, "n_hulls out of range");
+    if (h->n_pairs < 0 || h->n_pairs > PMP_MAX_HULL_PAIRS) return fail(ctx, PMP_E_INVALID, "n_pairs out of range");
+    if (h->n_fixed_exact < 0 || h->n_fixed_exact > t.n_fixed) return fail(ctx, PMP_E_INVALID, "n_fixed_exact out of range");
+    if (!h->hull_joint || !h->hull_off || !h->hull_verts || !h->hull_margin || !h->sph_hull || !h->sph_radius_outer ||
+        (h->n_pairs && !h->pairs))
+        return fail(ctx, PMP_E_INVALID, "null array in pmp_hull_desc");
+    PmpHullTab ht;
+    memset(&ht, 0, sizeof(ht));
+    const int H = h->n_hulls;
+    ht.n_hulls = H; ht.n_pairs = h->n_pairs; ht.n_fixed_exact = h->n_fixed_exact; ht.fixed_margin = h->fixed_margin;
+    if (!(h->fixed_margin >= 0.f)) return fail(ctx, PMP_E_INVALID, "fixed_margin must be >= 0");
+    if (h->hull_off[0] != 0) return fail(ctx, PMP_E_INVALID, "hull_off[0] must be 0");
+    for (int i = 0; i < H; ++i) {
+        if (h->hull_joint[i] < 0 || h->hull_joint[i] >= D) return fail(ctx, PMP_E_INVALID, "hull_joint out of range");
+        if (h->hull_off[i + 1] <= h->hull_off[i]) return fail(ctx, PMP_E_INVALID, "every hull needs at least one vertex");
+        if (!(h->hull_margin[i] >= 0.f)) return fail(ctx, PMP_E_INVALID, "hull_margin must be >= 0");
+        ht.hull_joint[i] = h->hull_joint[i]; ht.hull_off[i] = h->hull_off[i]; ht.hull_margin[i] = h->hull_margin[i];
+        ht.sph_lo[i] = 0; ht.sph_hi[i] = 0;
+    }
+    ht.hull_off[H] = h->hull_off[H];
+    const int NV = h->hull_off[H];
+    if (NV > PMP_MAX_HULL_VERTS) return fail(ctx, PMP_E_INVALID, "too many hull vertices");
+    for (int p = 0; p < 2 * h->n_pairs; ++p) {
+        if (h->pairs[p] < 0 || h->pairs[p] >= H) return fail(ctx, PMP_E_INVALID, "hull pair index out of range");
+        ht.pairs[p] = h->pairs[p];
+    }
+    for (int f = 0; f < h->n_fixed_exact; ++f)
+        if (t.fixed_kind[f] != PMP_PRIM_BOX && t.fixed_kind[f] != PMP_PRIM_SPHERE)
+            return fail(ctx, PMP_E_INVALID, "the exact hull test supports box and sphere obstacles");
+    // the spheres of a hull must be one contiguous run (they are sorted by joint and a hull rides on one joint)
+    for (int i = 0; i < H; ++i) {
+        int lo = -1, hi = -1;
+        for (int a = 0; a < A; ++a) {
+            if (h->sph_hull[a] == i) {
+                if (lo < 0) lo = a;
+                else if (hi != a) return fail(ctx, PMP_E_INVALID, "spheres of a hull must be contiguous");
+                hi = a + 1;
+            }
+        }
+        if (lo < 0) return fail(ctx, PMP_E_INVALID, "every hull needs at least one covering sphere");
+        ht.sph_lo[i] = lo; ht.sph_hi[i] = hi;
+    }
+    for (int a = 0; a < A; ++a) {
+        if (h->sph_hull[a] < -1 || h->sph_hull[a] >= H) return fail(ctx, PMP_E_INVALID, "sph_hull out of range");
+        if (!(h->sph_radius_outer[a] >= t.sph_radius[a])) return fail(ctx, PMP_E_INVALID, "sph_radius_outer must be >= sph_radius");
+        t.sph_radius_outer[a] = h->sph_radius_outer[a];
+    }
+    std::vector<float4> verts((size_t)NV);
+    for (int i = 0; i < NV; ++i) verts[i] = make_float4(h->hull_verts[3 * i], h->hull_verts[3 * i + 1], h->hull_verts[3 * i + 2], 0.f);
+    t.has_hulls = 1;
+    cudaFree(ctx->d_hull_verts); ctx->d_hull_verts = nullptr;
+    CK(cudaMalloc(&ctx->d_hull_verts, sizeof(float4) * (size_t)NV));
+    if (!ctx->d_hulls) CK(cudaMalloc(&ctx->d_hulls, sizeof(PmpHullTab)));
+    CK(cudaMemcpy(ctx->d_hull_verts, verts.data(), sizeof(float4) * (size_t)NV, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_hulls, &ht, sizeof(ht), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_robot, &t, sizeof(t), cudaMemcpyHostToDevice));
+    ctx->h_robot = t;
+    ctx->h_hulls = ht;
+    ctx->has_hulls = true;
+    return PMP_OK;
+}
+
+// hull pre-pass: limits | self | fixed of every step (edge mode) or configuration, on `stream`
+static int launch_rigid(pmp_ctx* ctx, const float* q0, const float* q1, int32_t E, int32_t max_steps, int32_t backward,
+                        uint32_t* rigid_pre, const float* q, int32_t B, uint8_t* rigid_flags, cudaStream_t st) {
+    PmpRigidArgs a;
+    a.robot = ctx->d_robot; a.hulls = ctx->d_hulls; a.hull_verts = ctx->d_hull_verts; a.prm = ctx->prm;
+    a.q0 = q0; a.q1 = q1; a.E = E; a.max_steps = max_steps; a.backward = backward ? 1 : 0; a.rigid_pre = rigid_pre;
+    a.q = q; a.B = B; a.rigid_flags = rigid_flags;
+    const long long items = q ? (B + 31) / 32 : (long long)E * ((max_steps + 31) / 32);
+    long long grid = (items + PMP_RIGID_WARPS - 1) / PMP_RIGID_WARPS;
+    const long long cap = (long long)ctx->sm_count * 8;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    pmp_rigid_kernel<<<(int)grid, 32 * PMP_RIGID_WARPS, 0, st>>>(a);
+    CK(cudaGetLastError());
+    ctx->info.kernel_launches++;
+    return PMP_OK;
+}
+
+static int ensure_rigid_scratch(pmp_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->rigid_scratch_bytes) return PMP_OK;
+    cudaFree(ctx->d_rigid_scratch);
+    ctx->d_rigid_scratch = nullptr; ctx->rigid_scratch_bytes = 0;
+    const size_t want = bytes + bytes / 4;
+    CK(cudaMalloc(&ctx->d_rigid_scratch, want));
+    ctx->rigid_scratch_bytes = want;
     return PMP_OK;
 }
 
@@ -218,6 +343,15 @@ extern "C" int pmp_set_params(pmp_ctx* ctx, const pmp_params* p) {
     ctx->prm.mode = p->mode;
     ctx->prm.dense = p->dense;
     if (!(p->gate_probability >= 0.f && p->gate_probability <= 1.f)) return fail(ctx, PMP_E_INVALID, "gate_probability outside [0, 1]");
+    if (!(p->arm_lag_gain >= 0.f && p->arm_lag_gain < 1.f)) return fail(ctx, PMP_E_INVALID, "arm_lag_gain outside [0, 1)");
+    if (p->arm_lag_gain > 0.f && p->arm_lag_substeps < 1) return fail(ctx, PMP_E_INVALID, "arm_lag_substeps must be >= 1");
+    ctx->prm.lag_kappa = 0.f; ctx->prm.lag_log2rho = 0.f;
+    if (p->arm_lag_gain > 0.f) {
+        // closure per interpolation step c = 1 - (1 - gain)^substeps; lag of a uniform ramp = kappa (1 - rho^i) steps
+        const double rho = pow(1.0 - (double)p->arm_lag_gain, (double)p->arm_lag_substeps), c = 1.0 - rho;
+        ctx->prm.lag_kappa = (float)(rho / c);
+        ctx->prm.lag_log2rho = (float)log2(rho);
+    }
     ctx->prm.gate_seed = p->gate_seed;
     ctx->prm.gate_threshold = p->gate_probability >= 1.f ? 0xFFFFFFFFu : (uint32_t)((double)p->gate_probability * 4294967296.0);
     ctx->has_params = true;
@@ -254,26 +388,27 @@ extern "C" int pmp_fk(pmp_ctx* ctx, const float* q_dev, int32_t B, float* pos, f
 // ---- kernel selection (instantiations live in pmp_inst_a*.cu) ---------------------------------------
 static void pads(pmp_ctx* ctx, int& apad, int& nspad) {
     const int A = ctx->h_robot.n_spheres;
-    apad = A <= 12 ? 12 : (A <= 16 ? 16 : 32);
+    apad = A <= 12 ? 12 : (A <= 16 ? 16 : (A <= 20 ? 20 : 32));
     nspad = ctx->n_slots <= 1 ? 1 : (ctx->n_slots <= 2 ? 2 : 4);
 }
 
 static int validate_edges_impl(pmp_ctx* ctx, const float* q0, const float* q1, int32_t E, int32_t max_steps,
                                int32_t backward, int32_t* first_hit, int32_t* n_steps, float* max_defl, float* over,
                                float* ee_len, float* cost, uint32_t* rigid_mask, uint32_t* exceed_mask, void* stream,
-                               int32_t edge_base);
+                               int32_t edge_base, uint32_t* rigid_pre_scratch = nullptr);
 
 extern "C" int pmp_validate_edges(pmp_ctx* ctx, const float* q0, const float* q1, int32_t E, int32_t max_steps,
                                   int32_t backward, int32_t* first_hit, int32_t* n_steps, float* max_defl, float* over,
-                                  float* ee_len, float* cost, uint32_t* rigid_mask, uint32_t* exceed_mask, void* stream) {
+                                  float* ee_len, float* cost, uint32_t* rigid_mask, uint32_t* exceed_mask, void* stream,
+                                  int32_t edge_base) {
     return validate_edges_impl(ctx, q0, q1, E, max_steps, backward, first_hit, n_steps, max_defl, over, ee_len, cost,
-                               rigid_mask, exceed_mask, stream, 0);
+                               rigid_mask, exceed_mask, stream, edge_base);
 }
 
 static int validate_edges_impl(pmp_ctx* ctx, const float* q0, const float* q1, int32_t E, int32_t max_steps,
                                int32_t backward, int32_t* first_hit, int32_t* n_steps, float* max_defl, float* over,
                                float* ee_len, float* cost, uint32_t* rigid_mask, uint32_t* exceed_mask, void* stream,
-                               int32_t edge_base) {
+                               int32_t edge_base, uint32_t* rigid_pre_scratch) {
     int rc = ready(ctx);
     if (rc) return rc;
     if (E < 0 || max_steps < 1) return fail(ctx, PMP_E_INVALID, "bad E / max_steps");
@@ -281,6 +416,20 @@ static int validate_edges_impl(pmp_ctx* ctx, const float* q0, const float* q1, i
     if (!q0 || !q1 || !first_hit || !n_steps) return fail(ctx, PMP_E_INVALID, "q0, q1, first_hit, n_steps are required");
     CK(cudaSetDevice(ctx->device));
     PmpEdgeArgs a;
+    a.rigid_pre = nullptr;
+    if (ctx->has_hulls) {
+        // exact self / obstacle test on the hulls: one bit per step, consumed by the edge kernel below.  The scratch
+        // belongs to the context (or to the caller's chunk); launches of one context are ordered by their stream.
+        uint32_t* pre = rigid_pre_scratch;
+        if (!pre) {
+            rc = ensure_rigid_scratch(ctx, sizeof(uint32_t) * (size_t)E * ((max_steps + 31) / 32));
+            if (rc) return rc;
+            pre = (uint32_t*)ctx->d_rigid_scratch;
+        }
+        rc = launch_rigid(ctx, q0, q1, E, max_steps, backward, pre, nullptr, 0, nullptr, (cudaStream_t)stream);
+        if (rc) return rc;
+        a.rigid_pre = pre;
+    }
     a.robot = ctx->d_robot; a.stems = ctx->d_stems; a.n_stems = ctx->d_nstems; a.boxes = ctx->d_boxes;
     a.n_boxes = ctx->d_nboxes; a.prm = ctx->prm; a.q0 = q0; a.q1 = q1; a.E = E; a.max_steps = max_steps;
     a.backward = backward ? 1 : 0; a.first_hit = first_hit; a.n_steps = n_steps; a.max_defl = max_defl; a.over = over;
@@ -341,10 +490,12 @@ static int validate_edges_impl(pmp_ctx* ctx, const float* q0, const float* q1, i
     if (first_only) {
         if (apad == 12) err = pmp_launch_edge_first_a12(nspad, a, wsmem, grid, block, smem, st_, &regs);
         else if (apad == 16) err = pmp_launch_edge_first_a16(nspad, a, wsmem, grid, block, smem, st_, &regs);
+        else if (apad == 20) err = pmp_launch_edge_first_a20(nspad, a, wsmem, grid, block, smem, st_, &regs);
         else err = pmp_launch_edge_first_a32(nspad, a, wsmem, grid, block, smem, st_, &regs);
     } else {
         if (apad == 12) err = pmp_launch_edge_a12(nspad, a, wsmem, grid, block, smem, st_, &regs);
         else if (apad == 16) err = pmp_launch_edge_a16(nspad, a, wsmem, grid, block, smem, st_, &regs);
+        else if (apad == 20) err = pmp_launch_edge_a20(nspad, a, wsmem, grid, block, smem, st_, &regs);
         else err = pmp_launch_edge_a32(nspad, a, wsmem, grid, block, smem, st_, &regs);
     }
     ctx->info.regs_per_thread = regs;
@@ -366,6 +517,14 @@ extern "C" int pmp_check_configs(pmp_ctx* ctx, const float* q, int32_t B, uint8_
     PmpConfigArgs a;
     a.robot = ctx->d_robot; a.stems = ctx->d_stems; a.n_stems = ctx->d_nstems; a.boxes = ctx->d_boxes;
     a.n_boxes = ctx->d_nboxes; a.prm = ctx->prm; a.q = q; a.B = B; a.flags = flags; a.defl = defl; a.theta = theta; a.ee = ee;
+    a.rigid_pre = nullptr;
+    if (ctx->has_hulls) {
+        rc = ensure_rigid_scratch(ctx, (size_t)B);
+        if (rc) return rc;
+        rc = launch_rigid(ctx, nullptr, nullptr, 0, 32, 0, nullptr, q, B, (uint8_t*)ctx->d_rigid_scratch, (cudaStream_t)stream);
+        if (rc) return rc;
+        a.rigid_pre = (const uint8_t*)ctx->d_rigid_scratch;
+    }
     int apad, nspad;
     pads(ctx, apad, nspad);
     // small batches (the scalar collision_fn adapter) spread over SMs: 32 threads per CTA
@@ -383,6 +542,7 @@ extern "C" int pmp_check_configs(pmp_ctx* ctx, const float* q, int32_t B, uint8_
     int regs = 0;
     if (apad == 12) err = pmp_launch_config_a12(nspad, a, grid, block, smem, (cudaStream_t)stream, &regs);
     else if (apad == 16) err = pmp_launch_config_a16(nspad, a, grid, block, smem, (cudaStream_t)stream, &regs);
+    else if (apad == 20) err = pmp_launch_config_a20(nspad, a, grid, block, smem, (cudaStream_t)stream, &regs);
     else err = pmp_launch_config_a32(nspad, a, grid, block, smem, (cudaStream_t)stream, &regs);
     ctx->info.regs_per_thread = regs;
     if (err != cudaSuccess) return fail(ctx, PMP_E_CUDA, std::string("config kernel launch: ") + cudaGetErrorString(err));
@@ -421,10 +581,24 @@ extern "C" int pmp_validate_edges_host(pmp_ctx* ctx, const float* q0, const floa
     const int CE = (E + n_chunks - 1) / n_chunks;               // edges per chunk
     const size_t bq = up256(sizeof(float) * (size_t)CE * D), bi = up256(sizeof(int32_t) * (size_t)CE),
                  bw = up256(sizeof(float) * (size_t)CE * W), bm = up256(sizeof(uint32_t) * (size_t)CE * W * C);
+    const size_t bp = ctx->has_hulls ? up256(sizeof(uint32_t) * (size_t)CE * C) : 0;     // hull pre-pass bits
     const size_t per = 2 * bq + 2 * bi + (max_defl ? bw : 0) + (over ? bw : 0) + (ee_len ? bi : 0) + (cost ? bi : 0) +
-                       (rigid_mask ? bm : 0) + (exceed_mask ? bm : 0);
+                       (rigid_mask ? bm : 0) + (exceed_mask ? bm : 0) + bp;
     rc = ensure_scratch(ctx, (n_chunks > 1 ? 2 : 1) * per);
     if (rc) return rc;
+    // An error inside the loop must not return while copies of earlier chunks are still writing into caller memory:
+    // every failure path drains both streams first.
+    auto bail = [&](int code) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->stream2);
+        return code;
+    };
+#define CKB(call)                                                                                             \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            return bail(fail(ctx, PMP_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)));           \
+    } while (0)
     for (int c = 0; c < n_chunks; ++c) {
         const int e0 = c * CE;
         const int ne = E - e0 < CE ? E - e0 : CE;
@@ -440,25 +614,27 @@ extern "C" int pmp_validate_edges_host(pmp_ctx* ctx, const float* q0, const floa
         float* dco = cost ? (float*)take(bi) : nullptr;
         uint32_t* drm = rigid_mask ? (uint32_t*)take(bm) : nullptr;
         uint32_t* dxm = exceed_mask ? (uint32_t*)take(bm) : nullptr;
+        uint32_t* dpre = bp ? (uint32_t*)take(bp) : nullptr;
         const size_t o1 = (size_t)e0, oD = (size_t)e0 * D, oW = (size_t)e0 * W, oM = (size_t)e0 * W * C;
-        CK(cudaMemcpyAsync(dq0, q0 + oD, sizeof(float) * (size_t)ne * D, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(dq1, q1 + oD, sizeof(float) * (size_t)ne * D, cudaMemcpyHostToDevice, st));
-        rc = validate_edges_impl(ctx, dq0, dq1, ne, max_steps, backward, dfh, dns, dmd, dov, del, dco, drm, dxm, st, e0);
-        if (rc) return rc;
-        CK(cudaMemcpyAsync(first_hit + o1, dfh, sizeof(int32_t) * (size_t)ne, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(n_steps + o1, dns, sizeof(int32_t) * (size_t)ne, cudaMemcpyDeviceToHost, st));
-        if (max_defl) CK(cudaMemcpyAsync(max_defl + oW, dmd, sizeof(float) * (size_t)ne * W, cudaMemcpyDeviceToHost, st));
-        if (over) CK(cudaMemcpyAsync(over + oW, dov, sizeof(float) * (size_t)ne * W, cudaMemcpyDeviceToHost, st));
-        if (ee_len) CK(cudaMemcpyAsync(ee_len + o1, del, sizeof(float) * (size_t)ne, cudaMemcpyDeviceToHost, st));
-        if (cost) CK(cudaMemcpyAsync(cost + o1, dco, sizeof(float) * (size_t)ne, cudaMemcpyDeviceToHost, st));
+        CKB(cudaMemcpyAsync(dq0, q0 + oD, sizeof(float) * (size_t)ne * D, cudaMemcpyHostToDevice, st));
+        CKB(cudaMemcpyAsync(dq1, q1 + oD, sizeof(float) * (size_t)ne * D, cudaMemcpyHostToDevice, st));
+        rc = validate_edges_impl(ctx, dq0, dq1, ne, max_steps, backward, dfh, dns, dmd, dov, del, dco, drm, dxm, st, e0, dpre);
+        if (rc) return bail(rc);
+        CKB(cudaMemcpyAsync(first_hit + o1, dfh, sizeof(int32_t) * (size_t)ne, cudaMemcpyDeviceToHost, st));
+        CKB(cudaMemcpyAsync(n_steps + o1, dns, sizeof(int32_t) * (size_t)ne, cudaMemcpyDeviceToHost, st));
+        if (max_defl) CKB(cudaMemcpyAsync(max_defl + oW, dmd, sizeof(float) * (size_t)ne * W, cudaMemcpyDeviceToHost, st));
+        if (over) CKB(cudaMemcpyAsync(over + oW, dov, sizeof(float) * (size_t)ne * W, cudaMemcpyDeviceToHost, st));
+        if (ee_len) CKB(cudaMemcpyAsync(ee_len + o1, del, sizeof(float) * (size_t)ne, cudaMemcpyDeviceToHost, st));
+        if (cost) CKB(cudaMemcpyAsync(cost + o1, dco, sizeof(float) * (size_t)ne, cudaMemcpyDeviceToHost, st));
         if (rigid_mask)
-            CK(cudaMemcpyAsync(rigid_mask + oM, drm, sizeof(uint32_t) * (size_t)ne * W * C, cudaMemcpyDeviceToHost, st));
+            CKB(cudaMemcpyAsync(rigid_mask + oM, drm, sizeof(uint32_t) * (size_t)ne * W * C, cudaMemcpyDeviceToHost, st));
         if (exceed_mask)
-            CK(cudaMemcpyAsync(exceed_mask + oM, dxm, sizeof(uint32_t) * (size_t)ne * W * C, cudaMemcpyDeviceToHost, st));
+            CKB(cudaMemcpyAsync(exceed_mask + oM, dxm, sizeof(uint32_t) * (size_t)ne * W * C, cudaMemcpyDeviceToHost, st));
     }
     CK(cudaStreamSynchronize(ctx->stream));
     if (n_chunks > 1) CK(cudaStreamSynchronize(ctx->stream2));
     return PMP_OK;
+#undef CKB
 }
 
 static int ensure_stage(pmp_ctx* ctx, size_t bytes) {
@@ -681,7 +857,7 @@ extern "C" int pmp_tree_extend(pmp_ctx* ctx, const pmp_tree* tree, int32_t size_
                         from_index, nullptr, q_from, st);
     if (rc) return rc;
     rc = pmp_validate_edges(ctx, q_from, targets_dev, B, max_steps, 0, first_hit, n_steps, nullptr, nullptr, nullptr,
-                            nullptr, nullptr, nullptr, stream);
+                            nullptr, nullptr, nullptr, stream, 0);
     if (rc) return rc;
     PmpTreeAppendArgs a;
     a.nodes = tree->nodes; a.parent = tree->parent; a.via = tree->via; a.via_steps = tree->via_steps; a.size = tree->size;

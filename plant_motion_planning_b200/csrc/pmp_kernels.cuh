@@ -127,10 +127,14 @@ __device__ __forceinline__ bool pmp_prim_hit(int kind, const float* __restrict__
 // Per-configuration work shared by all worlds: arm FK, sphere centres, limits, self and fixed-obstacle
 // collisions.  Oracle: joint_frames / sphere_centers / ee_positions / rigid_hit
 // (reference: pybullet_tools/utils.py:3753-3762, 3965-4016).
-// QSRC: functor j -> joint value of this lane's configuration.
+// QSRC: functor j -> joint value of the configuration the GEOMETRY is in; QLIM: functor j -> the commanded joint
+// value, which is what the limit test sees (they differ only under arm lag, env.py:154,170).
+// RIGID = false (warp-uniform): limits and collisions were decided elsewhere (the hull pre-pass); only FK and centres are computed.
+// The sphere tests use the radii `rad` (the covering radii when they only cull for the hull test).
 // ------------------------------------------------------------------------------------------------
-template <int A, class QSRC>
-__device__ __forceinline__ bool pmp_config_eval(const PmpRobotTab& rt, QSRC qsrc, float (&c)[A][3], float (&ee)[3]) {
+template <int A, class QSRC, class QLIM>
+__device__ __forceinline__ bool pmp_config_eval(const PmpRobotTab& rt, const bool RIGID, QSRC qsrc, QLIM qlim,
+                                                float (&c)[A][3], float (&ee)[3], const float* __restrict__ rad) {
     float R[9], p[3];
 #pragma unroll
     for (int k = 0; k < 9; ++k) R[k] = rt.base_R[k];
@@ -142,8 +146,13 @@ __device__ __forceinline__ bool pmp_config_eval(const PmpRobotTab& rt, QSRC qsrc
     const int D = rt.dof;
     for (int j = 0; j < D; ++j) {
         const float qj = qsrc(j);
-        const bool circ = (rt.circular_mask >> j) & 1u;
-        hit |= (!circ) && !(qj >= rt.lower[j] && qj <= rt.upper[j]);
+        if (RIGID) {
+            const float ql = qlim(j);
+            const bool circ = (rt.circular_mask >> j) & 1u;
+            // a non-finite joint value is a violation on every joint (the limit test alone would let NaN through on
+            // continuous joints, which have no limits: pybullet_tools/utils.py:2128-2137)
+            hit |= circ ? !(fabsf(ql) <= 3.0e38f) : !(ql >= rt.lower[j] && ql <= rt.upper[j]);
+        }
         float s, co;
         sincosf(qj, &s, &co);
         const float* Cj = rt.joint_C + 9 * j;
@@ -173,6 +182,7 @@ __device__ __forceinline__ bool pmp_config_eval(const PmpRobotTab& rt, QSRC qsrc
             ee[0] = x + p[0]; ee[1] = y + p[1]; ee[2] = z + p[2];
         }
     }
+    if (!RIGID) return false;
     // self collisions: sphere pairs named by the (warp-uniform) pair mask
 #pragma unroll
     for (int a = 0; a < A; ++a) {
@@ -182,7 +192,7 @@ __device__ __forceinline__ bool pmp_config_eval(const PmpRobotTab& rt, QSRC qsrc
         for (int b = a + 1; b < A; ++b) {
             if ((m >> b) & 1u) {
                 float dx = c[a][0] - c[b][0], dy = c[a][1] - c[b][1], dz = c[a][2] - c[b][2];
-                float rr = rt.sph_radius[a] + rt.sph_radius[b];
+                float rr = rad[a] + rad[b];
                 hit |= fmaf(dx, dx, fmaf(dy, dy, dz * dz)) <= rr * rr;
             }
         }
@@ -195,10 +205,18 @@ __device__ __forceinline__ bool pmp_config_eval(const PmpRobotTab& rt, QSRC qsrc
         for (int a = 0; a < A; ++a) {
             if ((m >> a) & 1u)
                 hit |= pmp_prim_hit(kind, rt.fixed_R + 9 * f, rt.fixed_t + 3 * f, rt.fixed_half + 3 * f,
-                                    c[a][0], c[a][1], c[a][2], rt.sph_radius[a]);
+                                    c[a][0], c[a][1], c[a][2], rad[a]);
         }
     }
     return hit;
+}
+
+// Interpolation parameter of step i of an edge with n steps (oracle edge_configs / lagged_configs): the commanded
+// t = (i + off) / n, and under arm lag the parameter of the configuration the arm really has,
+// t - lag_kappa (1 - rho^i) / n  (closed form of a_i = a_{i-1} + c (q_i - a_{i-1}), a_0 = q_0, on a uniform ramp).
+__device__ __forceinline__ float pmp_lagged_t(const PmpKernelParams& prm, int i, float t, float inv_n) {
+    if (prm.lag_kappa <= 0.f) return t;
+    return fmaf(-prm.lag_kappa * inv_n, 1.f - exp2f((float)i * prm.lag_log2rho), t);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -227,6 +245,20 @@ struct PmpSweptBound {
 // CPF: functor (pair, coordinate) -> the centres of arm spheres 2 pair and 2 pair + 1 as one packed pair.  The edge
 // kernel serves them from its per-warp shared-memory tile (one LDS.64 each), which keeps 3 A registers free for the
 // packed arithmetic; the configuration kernel from registers.
+//
+// Geometry of a stem = the reference's box (rand_gen_plants_programmatically_main.py:30-51) with Bullet's margin carved
+// out: core half extents (hw, hw, hh) centred zc up the stem's z axis; an arm sphere of radius r touches it when the
+// distance of its centre to the core box is < r + margin.  With R the stem's link rotation and o its joint origin,
+//     p = R^T c - b,   b = R^T o + zc e_z        (sphere centre relative to the box centre, link coordinates)
+//     d = p - clamp(p, +-half),  dist = |d|,  pen = r + margin - dist
+//     d(dist)/d(tx, ty) = ((cy, 0, sy) . (d x pf), (d x pf)_y) / dist,   pf = p + zc e_z
+// (oracle/edgecheck_oracle.py plant_equilibrium).
+__device__ __forceinline__ void pmp_rxry(float sx, float cx, float sy, float cy, float (&M)[9]) {
+    M[0] = cy;       M[1] = 0.f; M[2] = sy;
+    M[3] = sx * sy;  M[4] = cx;  M[5] = -sx * cy;
+    M[6] = -cx * sy; M[7] = sx;  M[8] = cx * cy;
+}
+
 template <int A, int NSLOT, bool DETAIL, bool CULL, class CPF>
 __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ wt, int n_stems,
                                                       const float* __restrict__ boxes, int n_boxes,
@@ -249,12 +281,17 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
     const bool dense = prm.dense != 0;
     const int K = prm.iterations;
     float last = 0.f;
+    static_assert(A % 2 == 0, "sphere loops work on pairs");
     for (int s = 0; s < n_stems; ++s) {
         const float* rec = wt + s * PMP_STEM_STRIDE;
+        // the first 16 floats are everything the rest-pose tests need: four 128-bit loads
+        const float4 h0 = *reinterpret_cast<const float4*>(rec), h1 = *reinterpret_cast<const float4*>(rec + 4),
+                     h2 = *reinterpret_cast<const float4*>(rec + 8), h3 = *reinterpret_cast<const float4*>(rec + 12);
         const int pslot = __float_as_int(rec[PMP_S_PSLOT]);
         const int oslot = __float_as_int(rec[PMP_S_OSLOT]);
         const int flags = __float_as_int(rec[PMP_S_FLAGS]);
-        // ---- is the ancestor chain undeflected (warp-uniform)?  Then the joint frame is the table's rest frame. ----
+        const float hw = h3.x, hh = h3.y, zc = h3.z, mg = h3.w, lim = rec[PMP_S_LIM];
+        // ---- is the ancestor chain undeflected (warp-uniform)?  Then the stem starts in the table's rest pose. ----
         bool moved = false;
         bool chain_at_rest = true;
         if (pslot >= 0) {
@@ -264,34 +301,44 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
                 if (pslot == k) moved = FM[k];   // warp-uniform
             chain_at_rest = !__any_sync(PMP_FULL, moved);
         }
-        const float z0 = rec[PMP_S_Z0], z1 = rec[PMP_S_Z1], rad = rec[PMP_S_RAD], lim = rec[PMP_S_LIM];
-        // ---- phase 0: can ANY step of this warp touch the stem at rest?  One swept-bound test per lane, on the rest
-        // frame read straight from the record (no register copy of the frame is made for the 4 stems in 5 that end here)
+        // ---- phase 0: can ANY step of this warp touch the stem at rest?  One swept-bound test per lane: the ball
+        // around one arm sphere over a group of steps against the box itself
         bool maybe = true;
         if (CULL && !dense && chain_at_rest) {
-            const float ux = rec[PMP_S_RW0 + 2], uy = rec[PMP_S_RW0 + 5], uz = rec[PMP_S_RW0 + 8];
-            const float wx = bound.x - rec[PMP_S_TW0], wy = bound.y - rec[PMP_S_TW0 + 1], wz = bound.z - rec[PMP_S_TW0 + 2];
-            const float tau = pmp_clamp(fmaf(wx, ux, fmaf(wy, uy, wz * uz)), z0, z1);
-            const float dx = fmaf(-tau, ux, wx), dy = fmaf(-tau, uy, wy), dz = fmaf(-tau, uz, wz);
-            const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-            const float rr = bound.r + rad;
+            const float px = fmaf(h0.x, bound.x, fmaf(h0.w, bound.y, fmaf(h1.z, bound.z, -h2.y)));
+            const float py = fmaf(h0.y, bound.x, fmaf(h1.x, bound.y, fmaf(h1.w, bound.z, -h2.z)));
+            const float pz = fmaf(h0.z, bound.x, fmaf(h1.y, bound.y, fmaf(h2.x, bound.z, -h2.w)));
+            const float ex = fmaxf(fabsf(px) - hw, 0.f), ey = fmaxf(fabsf(py) - hw, 0.f), ez = fmaxf(fabsf(pz) - hh, 0.f);
+            const float d2 = fmaf(ex, ex, fmaf(ey, ey, ez * ez));
+            const float rr = bound.r + mg;
             maybe = __any_sync(PMP_FULL, bound.r >= 0.f && d2 < rr * rr);
         }
-        if (CULL && !maybe && prm.deflection_limit >= 0.f) {
-            // nothing can touch this stem at any step of the warp: it stays at rest with zero deflection.  Only the
-            // chain-rule state and the "moved" bit of its frame slot need updating (children of an unmoved stem take
-            // their frames from the table, and the observer rebuilds an unmoved parent's rotation from the record).
-            if (flags & (PMP_SF_PLANT_START | PMP_SF_IS_MAIN)) last = 0.f;
+        if (CULL && !maybe) {
+            // nothing can touch this stem at any step of the warp: it keeps its rest pose, whose observer value is in
+            // the record.  Only the chain rule and the "moved" bit of its frame slot need updating (children of an
+            // unmoved stem start from the table too, and the observer rebuilds an unmoved parent's rotation).
+            if (flags & PMP_SF_PLANT_START) last = 0.f;
+            const float d = fmaxf(rec[PMP_S_RAW0] - last, 0.f);
+            if (flags & PMP_SF_IS_MAIN) last = d;
+            out.exceeded |= d > prm.deflection_limit;
+            out.max_defl = fmaxf(out.max_defl, d);
+            out.over += fmaxf(d - prm.deflection_limit, 0.f);
 #pragma unroll
             for (int k = 0; k < NSLOT; ++k)
                 if (oslot == k) FM[k] = false;
             continue;
         }
-        // ---- joint frame: the table's rest frame, or parent frame . origin when an ancestor is deflected ----
-        float Rv[9], tv[3];
+        // ---- initial link frame Rs (rest angles th0) and joint origin tv: the table's rest pose, or composed from the
+        // parent's final frame for lanes whose ancestors are deflected ----
+        const float th0x = rec[PMP_S_TH0], th0y = rec[PMP_S_TH0 + 1];
+        float Rs[9], tv[3], b[3], Rv[9];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) Rv[i] = rec[PMP_S_RW0 + i];
-        tv[0] = rec[PMP_S_TW0]; tv[1] = rec[PMP_S_TW0 + 1]; tv[2] = rec[PMP_S_TW0 + 2];
+        for (int i = 0; i < 9; ++i) Rv[i] = 0.f;
+        Rs[0] = h0.x; Rs[1] = h0.y; Rs[2] = h0.z; Rs[3] = h0.w; Rs[4] = h1.x; Rs[5] = h1.y; Rs[6] = h1.z; Rs[7] = h1.w; Rs[8] = h2.x;
+        b[0] = h2.y; b[1] = h2.z; b[2] = h2.w;
+        tv[0] = rec[PMP_S_TV0]; tv[1] = rec[PMP_S_TV0 + 1]; tv[2] = rec[PMP_S_TV0 + 2];
+        float s0x = 0.f, c0x = 1.f, s0y = 0.f, c0y = 1.f;
+        bool have_sc = false;          // sincos of the rest angles
         if (pslot >= 0 && (dense || !chain_at_rest)) {
             float Rp[9], tp[3];
 #pragma unroll
@@ -305,85 +352,104 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
                     tp[0] = FT[k][0]; tp[1] = FT[k][1]; tp[2] = FT[k][2];
                 }
             }
-            float Ro[9], Rc[9];
+            float Ro[9], Rc[9], M0[9], Rl[9];
 #pragma unroll
             for (int i = 0; i < 9; ++i) Ro[i] = rec[PMP_S_RO + i];
             pmp_mat_mul(Rp, Ro, Rc);
             float x, y, z;
             pmp_mat_vec(Rp, rec[PMP_S_TO], rec[PMP_S_TO + 1], rec[PMP_S_TO + 2], x, y, z);
+            __sincosf(th0x, &s0x, &c0x);
+            __sincosf(th0y, &s0y, &c0y);
+            pmp_rxry(s0x, c0x, s0y, c0y, M0);
+            pmp_mat_mul(Rc, M0, Rl);
             if (moved) {
 #pragma unroll
-                for (int i = 0; i < 9; ++i) Rv[i] = Rc[i];
+                for (int i = 0; i < 9; ++i) Rs[i] = Rl[i];
                 tv[0] = x + tp[0]; tv[1] = y + tp[1]; tv[2] = z + tp[2];
+                float bx, by, bz;
+                pmp_matT_vec(Rs, tv[0], tv[1], tv[2], bx, by, bz);
+                b[0] = bx; b[1] = by; b[2] = bz + zc;
             }
+            have_sc = true;
         }
         // ---- phase 1: does any arm sphere touch the stem in its initial pose?  (exact, no rsqrt / Jacobian) ----
         bool touch = false;
         {
-            const float ux = Rv[2], uy = Rv[5], uz = Rv[8];
             float margin = -1.f;
-            static_assert(A % 2 == 0, "sphere loops work on pairs");
+            const pmp_f2 nbx = pmp_bc(-b[0]), nby = pmp_bc(-b[1]), nbz = pmp_bc(-b[2]);
 #pragma unroll
             for (int a = 0; a < A; a += 2) {          // spheres a (low half) and a + 1 (high half)
-                const pmp_f2 wx = pmp_sub2(cpf(a >> 1, 0), pmp_bc(tv[0]));
-                const pmp_f2 wy = pmp_sub2(cpf(a >> 1, 1), pmp_bc(tv[1]));
-                const pmp_f2 wz = pmp_sub2(cpf(a >> 1, 2), pmp_bc(tv[2]));
-                float t0, t1;
-                pmp_upk(pmp_fma2(wx, pmp_bc(ux), pmp_fma2(wy, pmp_bc(uy), pmp_mul2(wz, pmp_bc(uz)))), t0, t1);
-                const pmp_f2 tau = pmp_pk(pmp_clamp(t0, z0, z1), pmp_clamp(t1, z0, z1));
-                const pmp_f2 dx = pmp_fma2(tau, pmp_bc(-ux), wx), dy = pmp_fma2(tau, pmp_bc(-uy), wy),
-                             dz = pmp_fma2(tau, pmp_bc(-uz), wz);
-                const pmp_f2 d2 = pmp_fma2(dx, dx, pmp_fma2(dy, dy, pmp_mul2(dz, dz)));
-                // touching <=> (r_a + rad)^2 - d2 > 0; the largest such margin over all spheres decides
-                const pmp_f2 nrr = pmp_sub2(pmp_bc(-rad), *reinterpret_cast<const pmp_f2*>(&rt.sph_radius[a]));
+                const pmp_f2 cx = cpf(a >> 1, 0), cy = cpf(a >> 1, 1), cz = cpf(a >> 1, 2);
+                float p0, p1, q0, q1, r0, r1;
+                pmp_upk(pmp_fma2(pmp_bc(Rs[0]), cx, pmp_fma2(pmp_bc(Rs[3]), cy, pmp_fma2(pmp_bc(Rs[6]), cz, nbx))), p0, p1);
+                pmp_upk(pmp_fma2(pmp_bc(Rs[1]), cx, pmp_fma2(pmp_bc(Rs[4]), cy, pmp_fma2(pmp_bc(Rs[7]), cz, nby))), q0, q1);
+                pmp_upk(pmp_fma2(pmp_bc(Rs[2]), cx, pmp_fma2(pmp_bc(Rs[5]), cy, pmp_fma2(pmp_bc(Rs[8]), cz, nbz))), r0, r1);
+                const pmp_f2 ex = pmp_pk(fmaxf(fabsf(p0) - hw, 0.f), fmaxf(fabsf(p1) - hw, 0.f));
+                const pmp_f2 ey = pmp_pk(fmaxf(fabsf(q0) - hw, 0.f), fmaxf(fabsf(q1) - hw, 0.f));
+                const pmp_f2 ez = pmp_pk(fmaxf(fabsf(r0) - hh, 0.f), fmaxf(fabsf(r1) - hh, 0.f));
+                const pmp_f2 d2 = pmp_fma2(ex, ex, pmp_fma2(ey, ey, pmp_mul2(ez, ez)));
+                // touching <=> (r_a + margin)^2 - d2 > 0; the largest such value over all spheres decides
+                const pmp_f2 rr = pmp_add2(pmp_bc(mg), *reinterpret_cast<const pmp_f2*>(&rt.sph_radius[a]));
                 float m0, m1;
-                pmp_upk(pmp_sub2(pmp_mul2(nrr, nrr), d2), m0, m1);
+                pmp_upk(pmp_sub2(pmp_mul2(rr, rr), d2), m0, m1);
+                // (padding spheres sit at PMP_FAR with radius -1e3: (r + mg)^2 = 1e6 against d2 = 3e12)
                 margin = fmaxf(fmaxf(margin, m0), m1);
             }
             touch = margin > 0.f;
         }
-        float thx = 0.f, thy = 0.f;
-        float cx = 1.f, sx = 0.f, cy = 1.f, sy = 0.f;
+        float thx = th0x, thy = th0y;
         if (!solve) {
             out.plant_hit |= touch;          // avoid_all: the undeflected plant is an obstacle (env.py:75-77)
         } else if (dense || __any_sync(PMP_FULL, touch)) {
             // ---- phase 2: K damped Gauss-Newton steps (oracle plant_equilibrium) ----
+            if (!have_sc) { __sincosf(th0x, &s0x, &c0x); __sincosf(th0y, &s0y, &c0y); }
+            {
+                // the joint frame before the stem's own rotation: Rv = Rs M(th0)^T
+                float M0[9];
+                pmp_rxry(s0x, c0x, s0y, c0y, M0);
+#pragma unroll
+                for (int r_ = 0; r_ < 3; ++r_)
+#pragma unroll
+                    for (int c_ = 0; c_ < 3; ++c_)
+                        Rv[3 * r_ + c_] = fmaf(Rs[3 * r_], M0[3 * c_], fmaf(Rs[3 * r_ + 1], M0[3 * c_ + 1], Rs[3 * r_ + 2] * M0[3 * c_ + 2]));
+            }
+            float sx = s0x, cx = c0x, sy = s0y, cy = c0y;
+            float Rl[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Rl[i] = Rs[i];
             for (int it = 0; it < K; ++it) {
-                // stem axis u = Rv (sy, -sx cy, cx cy);  joint axes ax = Rv ex, ay = Rv (0, cx, sx)
-                float ux, uy, uz;
-                pmp_mat_vec(Rv, sy, -sx * cy, cx * cy, ux, uy, uz);
-                const float axx = Rv[0], axy = Rv[3], axz = Rv[6];
-                float ayx, ayy, ayz;
-                pmp_mat_vec(Rv, 0.f, cx, sx, ayx, ayy, ayz);
-                // n b = u x a (the negated cross products a x u): the sign of sc = -tau / dist is folded into them
-                const float nbxx = axz * uy - axy * uz, nbxy = axx * uz - axz * ux, nbxz = axy * ux - axx * uy;
-                const float nbyx = ayz * uy - ayy * uz, nbyy = ayx * uz - ayz * ux, nbyz = ayy * ux - ayx * uy;
                 // accumulators: low half = even spheres, high half = odd spheres
                 pmp_f2 Hxx2 = pmp_bc(0.f), Hxy2 = pmp_bc(0.f), Hyy2 = pmp_bc(0.f), gx2 = pmp_bc(0.f), gy2 = pmp_bc(0.f),
                        S2 = pmp_bc(0.f);
+                const pmp_f2 nbx = pmp_bc(-b[0]), nby = pmp_bc(-b[1]), nbz = pmp_bc(-b[2]);
 #pragma unroll
                 for (int a = 0; a < A; a += 2) {
-                    const pmp_f2 wx = pmp_sub2(cpf(a >> 1, 0), pmp_bc(tv[0]));
-                    const pmp_f2 wy = pmp_sub2(cpf(a >> 1, 1), pmp_bc(tv[1]));
-                    const pmp_f2 wz = pmp_sub2(cpf(a >> 1, 2), pmp_bc(tv[2]));
-                    float t0, t1;
-                    pmp_upk(pmp_fma2(wx, pmp_bc(ux), pmp_fma2(wy, pmp_bc(uy), pmp_mul2(wz, pmp_bc(uz)))), t0, t1);
-                    const pmp_f2 tau = pmp_pk(pmp_clamp(t0, z0, z1), pmp_clamp(t1, z0, z1));
-                    const pmp_f2 dx = pmp_fma2(tau, pmp_bc(-ux), wx), dy = pmp_fma2(tau, pmp_bc(-uy), wy),
-                                 dz = pmp_fma2(tau, pmp_bc(-uz), wz);
+                    const pmp_f2 ccx = cpf(a >> 1, 0), ccy = cpf(a >> 1, 1), ccz = cpf(a >> 1, 2);
+                    const pmp_f2 px = pmp_fma2(pmp_bc(Rl[0]), ccx, pmp_fma2(pmp_bc(Rl[3]), ccy, pmp_fma2(pmp_bc(Rl[6]), ccz, nbx)));
+                    const pmp_f2 py = pmp_fma2(pmp_bc(Rl[1]), ccx, pmp_fma2(pmp_bc(Rl[4]), ccy, pmp_fma2(pmp_bc(Rl[7]), ccz, nby)));
+                    const pmp_f2 pz = pmp_fma2(pmp_bc(Rl[2]), ccx, pmp_fma2(pmp_bc(Rl[5]), ccy, pmp_fma2(pmp_bc(Rl[8]), ccz, nbz)));
+                    float p0, p1, q0, q1, r0, r1;
+                    pmp_upk(px, p0, p1); pmp_upk(py, q0, q1); pmp_upk(pz, r0, r1);
+                    const pmp_f2 dx = pmp_sub2(px, pmp_pk(pmp_clamp(p0, -hw, hw), pmp_clamp(p1, -hw, hw)));
+                    const pmp_f2 dy = pmp_sub2(py, pmp_pk(pmp_clamp(q0, -hw, hw), pmp_clamp(q1, -hw, hw)));
+                    const pmp_f2 dz = pmp_sub2(pz, pmp_pk(pmp_clamp(r0, -hh, hh), pmp_clamp(r1, -hh, hh)));
                     // + 1e-24 > 0: rsqrt stays finite
                     const pmp_f2 d2 = pmp_fma2(dx, dx, pmp_fma2(dy, dy, pmp_fma2(dz, dz, pmp_bc(1e-24f))));
                     float e0, e1;
                     pmp_upk(d2, e0, e1);
                     const pmp_f2 inv = pmp_pk(pmp_rsqrt_ftz(e0), pmp_rsqrt_ftz(e1));
-                    // d2 * inv - (r_a + rad) = -(penetration)
+                    // d2 * inv - (r_a + margin) = -(penetration)
                     float n0, n1;
-                    const pmp_f2 nrr = pmp_sub2(pmp_bc(-rad), *reinterpret_cast<const pmp_f2*>(&rt.sph_radius[a]));
+                    const pmp_f2 nrr = pmp_sub2(pmp_bc(-mg), *reinterpret_cast<const pmp_f2*>(&rt.sph_radius[a]));
                     pmp_upk(pmp_fma2(d2, inv, nrr), n0, n1);
                     const pmp_f2 pen = pmp_pk(fmaxf(-n0, 0.f), fmaxf(-n1, 0.f));
-                    const pmp_f2 sc = pmp_mul2(tau, inv);
-                    const pmp_f2 Jx = pmp_mul2(sc, pmp_fma2(dx, pmp_bc(nbxx), pmp_fma2(dy, pmp_bc(nbxy), pmp_mul2(dz, pmp_bc(nbxz)))));
-                    const pmp_f2 Jy = pmp_mul2(sc, pmp_fma2(dx, pmp_bc(nbyx), pmp_fma2(dy, pmp_bc(nbyy), pmp_mul2(dz, pmp_bc(nbyz)))));
+                    // m = d x pf,  pf = p + zc e_z
+                    const pmp_f2 pfz = pmp_add2(pz, pmp_bc(zc));
+                    const pmp_f2 mx = pmp_fma2(dy, pfz, pmp_mul2(pmp_sub2(pmp_bc(0.f), dz), py));
+                    const pmp_f2 my = pmp_fma2(dz, px, pmp_mul2(pmp_sub2(pmp_bc(0.f), dx), pfz));
+                    const pmp_f2 mz = pmp_fma2(dx, py, pmp_mul2(pmp_sub2(pmp_bc(0.f), dy), px));
+                    const pmp_f2 Jx = pmp_mul2(inv, pmp_fma2(pmp_bc(cy), mx, pmp_mul2(pmp_bc(sy), mz)));
+                    const pmp_f2 Jy = pmp_mul2(inv, my);
                     const pmp_f2 pJx = pmp_mul2(pen, Jx), pJy = pmp_mul2(pen, Jy);
                     Hxx2 = pmp_fma2(pJx, Jx, Hxx2);
                     Hxy2 = pmp_fma2(pJx, Jy, Hxy2);
@@ -394,7 +460,7 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
                 }
                 const float Hxx = pmp_hsum2(Hxx2), Hxy = pmp_hsum2(Hxy2), Hyy = pmp_hsum2(Hyy2), gx = pmp_hsum2(gx2),
                             gy = pmp_hsum2(gy2), S = pmp_hsum2(S2);
-                // a stem that nothing touches in its initial pose is never pushed: it stays at theta = 0
+                // a stem that nothing touches in its initial pose is never pushed: it keeps its rest angles
                 const bool act = touch && (S > 0.f);
                 if (!dense && !__any_sync(PMP_FULL, act)) break;   // later steps would be no-ops for every lane
                 const float lam = prm.reg_eps * S;
@@ -407,33 +473,33 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
                 float dty = (a11 * gy - Hxy * gx) * idet;
                 dtx = pmp_clamp(dtx, -prm.max_step, prm.max_step);
                 dty = pmp_clamp(dty, -prm.max_step, prm.max_step);
-                thx = pmp_clamp(thx + dtx, -lim, lim);
-                thy = pmp_clamp(thy + dty, -lim, lim);
+                if (act) {
+                    thx = pmp_clamp(thx + dtx, -lim, lim);
+                    thy = pmp_clamp(thy + dty, -lim, lim);
+                }
                 __sincosf(thx, &sx, &cx);
                 __sincosf(thy, &sy, &cy);
+                // link frame and box offset of the new pose (the last iteration's are the final ones)
+                float M[9];
+                pmp_rxry(sx, cx, sy, cy, M);
+                pmp_mat_mul(Rv, M, Rl);
+                float bx, by, bz;
+                pmp_matT_vec(Rl, tv[0], tv[1], tv[2], bx, by, bz);
+                b[0] = bx; b[1] = by; b[2] = bz + zc;
+            }
+            const bool bent_ = (thx != th0x) || (thy != th0y);
+            if (bent_) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) Rs[i] = Rl[i];
             }
         }
-        const bool bent = (thx != 0.f) || (thy != 0.f);
+        const bool bent = (thx != th0x) || (thy != th0y);
         moved |= bent;
-        // final link frame R_s = Rv Rx(thx) Ry(thy)
-        float Rs[9];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) Rs[i] = Rv[i];
-        if (dense || __any_sync(PMP_FULL, bent)) {
-            float M[9], Rb[9];
-            M[0] = cy;       M[1] = 0.f; M[2] = sy;
-            M[3] = sx * sy;  M[4] = cx;  M[5] = -sx * cy;
-            M[6] = -cx * sy; M[7] = sx;  M[8] = cx * cy;
-            pmp_mat_mul(Rv, M, Rb);
-            if (bent) {
-#pragma unroll
-                for (int i = 0; i < 9; ++i) Rs[i] = Rb[i];
-            }
-        }
         // observer
-        float raw = 0.f;
+        float raw = rec[PMP_S_RAW0];         // value of the rest pose: exact for an undeflected chain
         if (dense || __any_sync(PMP_FULL, moved)) {
             const float ox = rec[PMP_S_OBSV], oy = rec[PMP_S_OBSV + 1], oz = rec[PMP_S_OBSV + 2];
+            float val;
             if (flags & PMP_SF_OBS_ANGLE) {
                 // angle between (COM - ref point) and the unit reference direction
                 const float cz_ = rec[PMP_S_COMZ];
@@ -447,15 +513,16 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
                 const float kx = vy * oz - vz * oy, ky = vz * ox - vx * oz, kz = vx * oy - vy * ox;
                 const float sn = sqrtf(fmaf(kx, kx, fmaf(ky, ky, kz * kz)));
                 const float cs = fmaf(vx, ox, fmaf(vy, oy, vz * oz));
-                raw = atan2f(sn, cs);     // == acos(cos) of the reference, well conditioned near 0
+                val = atan2f(sn, cs);     // == acos(cos) of the reference, well conditioned near 0
             } else {
                 float vx, vy, vz;
                 if (flags & PMP_SF_OBS_ROOT) {
                     pmp_mat_vec(Rs, ox, oy, oz, vx, vy, vz);
                 } else {
                     // parent rotation: from its frame slot if the parent moved, else its rest value rebuilt from this
-                    // stem's record, R_p0 = Rw0 Ro^T (an unmoved parent may have skipped the slot store altogether)
-                    float Rp[9], Rw0[9], RoT[9], Rp0[9];
+                    // stem's joint frame, R_p = Rv Ro^T (an unmoved parent may have skipped the slot store altogether;
+                    // a lane with an unmoved parent that counts as `moved` here has bent, so the solve above built its Rv)
+                    float Rp[9], RoT[9], Rp0[9];
                     bool pm = FM[0];
 #pragma unroll
                     for (int i = 0; i < 9; ++i) Rp[i] = FR[0][i];
@@ -468,12 +535,10 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
                         }
                     }
 #pragma unroll
-                    for (int i = 0; i < 9; ++i) Rw0[i] = rec[PMP_S_RW0 + i];
-#pragma unroll
                     for (int r_ = 0; r_ < 3; ++r_)
 #pragma unroll
                         for (int c_ = 0; c_ < 3; ++c_) RoT[3 * r_ + c_] = rec[PMP_S_RO + 3 * c_ + r_];
-                    pmp_mat_mul(Rw0, RoT, Rp0);
+                    pmp_mat_mul(Rv, RoT, Rp0);
                     if (!pm) {
 #pragma unroll
                         for (int i = 0; i < 9; ++i) Rp[i] = Rp0[i];
@@ -488,9 +553,9 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
                 if (sarg <= -0.99999f) { roll = 0.f; pitch = -1.57079632679f; }
                 else if (sarg >= 0.99999f) { roll = 0.f; pitch = 1.57079632679f; }
                 else { roll = atan2f(vy, vz); pitch = asinf(sarg); }
-                raw = sqrtf(fmaf(roll, roll, pitch * pitch));
+                val = sqrtf(fmaf(roll, roll, pitch * pitch));
             }
-            if (!moved) raw = 0.f;   // untouched chain: exactly at rest
+            if (moved) raw = val;   // untouched chain: exactly the rest pose
         }
         // chain rule (CharacterizePlant.observe_all)
         if (flags & PMP_SF_PLANT_START) last = 0.f;
@@ -516,8 +581,8 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
     }
     if (prm.mode == PMP_MODE_AVOID_ALL) {
         // plant base boxes join the obstacle set (env.py:75-77)
-        for (int b = 0; b < n_boxes; ++b) {
-            const float* bx = boxes + b * PMP_BOX_STRIDE;
+        for (int bb = 0; bb < n_boxes; ++bb) {
+            const float* bx = boxes + bb * PMP_BOX_STRIDE;
 #pragma unroll
             for (int a = 0; a < A; a += 2) {
                 float x0, x1, y0, y1, zz0, zz1;
@@ -545,6 +610,35 @@ __device__ __forceinline__ void pmp_stage_words(void* dst, const void* src, int 
     }
 }
 
+// Interpolation set-up of one edge (oracle num_steps / edge_configs; pybullet_tools/utils.py:3604-3676): lanes < D
+// stage q0, q1 and the (wrapped) difference, every lane returns n = int(|dq / res|_2) + 1 computed in float64 with
+// the summation order of the oracle.
+__device__ __forceinline__ int pmp_edge_setup(const PmpRobotTab& rt, const PmpKernelParams& prm, const float* q0,
+                                              const float* q1, int e, int lane, double* sm_sq, float* sm_q0,
+                                              float* sm_q1, float* sm_dq) {
+    const int D = rt.dof;
+    __syncwarp();
+    if (lane < D) {
+        const float a = q0[(size_t)e * D + lane], b = q1[(size_t)e * D + lane];
+        double d = __dsub_rn((double)b, (double)a);
+        if ((rt.circular_mask >> lane) & 1u) {
+            const double two_pi = 6.283185307179586, pi = 3.141592653589793;
+            double x = d + pi;
+            x = x - two_pi * floor(x / two_pi);
+            d = x - pi;
+        }
+        const double v = __ddiv_rn(d, prm.resolution);
+        sm_sq[lane] = __dmul_rn(v, v);
+        sm_q0[lane] = a; sm_q1[lane] = b; sm_dq[lane] = (float)d;
+    }
+    __syncwarp();
+    double ssum = 0.0;
+    for (int j = 0; j < D; ++j) ssum = __dadd_rn(ssum, sm_sq[j]);
+    const double nd = floor(__dsqrt_rn(ssum));
+    // NaN / inf inputs: one step, which the limit test of that configuration rejects
+    return (nd >= 0.0 && nd <= 1.0e6) ? (int)nd + 1 : (nd > 1.0e6 ? 1000001 : 1);
+}
+
 struct PmpEdgeArgs {
     const PmpRobotTab* robot;
     const float* stems;        // [W, max_stems, STRIDE]
@@ -570,6 +664,7 @@ struct PmpEdgeArgs {
                                // worlds w = part, part + split, ... (1 otherwise)
     int32_t edge_base;         // index of edge 0 in the caller's batch (the host entry point launches in chunks);
                                // enters the on-device gate's hash so that chunking does not change decisions
+    const uint32_t* rigid_pre; // [E, C] or null: limits | self | fixed decided by the hull pre-pass (bit = step)
 };
 
 // Edge-batch kernel.  Persistent CTAs; warp = edge, lane = step.
@@ -629,26 +724,7 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
         if (item >= n_items) break;
         const int e = item / split, part = item - e * split;
         // ---- interpolation set-up: oracle num_steps / edge_configs (pybullet_tools/utils.py:3604-3676) ----
-        __syncwarp();
-        if (lane < D) {
-            const float a = args.q0[(size_t)e * D + lane], b = args.q1[(size_t)e * D + lane];
-            double d = __dsub_rn((double)b, (double)a);
-            if ((rt.circular_mask >> lane) & 1u) {
-                const double two_pi = 6.283185307179586, pi = 3.141592653589793;
-                double x = d + pi;
-                x = x - two_pi * floor(x / two_pi);
-                d = x - pi;
-            }
-            const double v = __ddiv_rn(d, prm.resolution);
-            sm_sq[lane] = __dmul_rn(v, v);
-            sm_q0[lane] = a; sm_q1[lane] = b; sm_dq[lane] = (float)d;
-        }
-        __syncwarp();
-        double ssum = 0.0;
-        for (int j = 0; j < D; ++j) ssum = __dadd_rn(ssum, sm_sq[j]);
-        const double nd = floor(__dsqrt_rn(ssum));
-        // NaN / inf inputs: one step, which the limit test of that configuration rejects
-        const int n = (nd >= 0.0 && nd <= 1.0e6) ? (int)nd + 1 : (nd > 1.0e6 ? 1000001 : 1);
+        const int n = pmp_edge_setup(rt, prm, args.q0, args.q1, e, lane, sm_sq, sm_q0, sm_q1, sm_dq);
         const int nc = min(n, args.max_steps);
         const int off = args.backward ? 0 : 1;
         const float inv_n = 1.0f / (float)n;
@@ -658,7 +734,8 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
         float pe[3];   // end-effector point preceding this chunk's first step
         {
             float c0[A][3], e0[3];
-            pmp_config_eval<A>(rt, [&](int j) { return sm_q0[j]; }, c0, e0);
+            auto qs = [&](int j) { return sm_q0[j]; };
+            pmp_config_eval<A>(rt, false, qs, qs, c0, e0, rt.sph_radius);
             pe[0] = e0[0]; pe[1] = e0[1]; pe[2] = e0[2];
         }
         for (int base = 0, chunk = 0; base < nc; base += 32, ++chunk) {
@@ -675,12 +752,16 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
             const bool at_end = (num == n);
             float c[A][3], ee[3];
             const uint32_t circ = rt.circular_mask;
-            bool rigid0 = pmp_config_eval<A>(
-                rt,
-                [&](int j) {
-                    return (at_end && !((circ >> j) & 1u)) ? sm_q1[j] : fmaf(sm_dq[j], t, sm_q0[j]);
-                },
-                c, ee);
+            const bool lag = prm.lag_kappa > 0.f;
+            const float tg = pmp_lagged_t(prm, i, t, inv_n);
+            auto q_cmd = [&](int j) { return (at_end && !((circ >> j) & 1u)) ? sm_q1[j] : fmaf(sm_dq[j], t, sm_q0[j]); };
+            auto q_geo = [&](int j) {
+                return lag ? fmaf(sm_dq[j], tg, sm_q0[j])
+                           : ((at_end && !((circ >> j) & 1u)) ? sm_q1[j] : fmaf(sm_dq[j], t, sm_q0[j]));
+            };
+            // with hulls, the pre-pass kernel decided limits | self | fixed (one bit per step)
+            bool rigid0 = pmp_config_eval<A>(rt, args.rigid_pre == nullptr, q_geo, q_cmd, c, ee, rt.sph_radius);
+            if (args.rigid_pre) rigid0 = (args.rigid_pre[(size_t)e * C + chunk] >> lane) & 1u;
             rigid0 &= live;
             if (!live) {
 #pragma unroll
@@ -846,6 +927,7 @@ struct PmpConfigArgs {
     float* theta;              // [B, W, max_stems, 2] or null
     float* ee;                 // [B, 3] or null
     int32_t worlds_per_cta;    // blockIdx.y handles worlds [y * worlds_per_cta, (y + 1) * worlds_per_cta)
+    const uint8_t* rigid_pre;  // [B] or null: limits | self | fixed decided by the hull pre-pass
 };
 
 // Explicit-configuration kernel: thread = configuration, blockIdx.y = chunk of worlds.  Parity / scalar-adapter path.
@@ -862,7 +944,9 @@ __global__ void __launch_bounds__(128, 2) pmp_config_kernel(const PmpConfigArgs 
     const int bb = live ? b : 0;
     float c[A][3], ee[3];
     const float* q = args.q + (size_t)bb * D;
-    bool rigid0 = pmp_config_eval<A>(rt, [&](int j) { return __ldg(q + j); }, c, ee);
+    auto qs = [&](int j) { return __ldg(q + j); };
+    bool rigid0 = pmp_config_eval<A>(rt, args.rigid_pre == nullptr, qs, qs, c, ee, rt.sph_radius);
+    if (args.rigid_pre) rigid0 = args.rigid_pre[bb] != 0;
     if (!live) {
 #pragma unroll
         for (int a = 0; a < A; ++a) { c[a][0] = PMP_FAR; c[a][1] = PMP_FAR; c[a][2] = PMP_FAR; }

@@ -14,4 +14,5 @@
 
 PMP_DECLARE_LAUNCHERS(12)
 PMP_DECLARE_LAUNCHERS(16)
+PMP_DECLARE_LAUNCHERS(20)
 PMP_DECLARE_LAUNCHERS(32)

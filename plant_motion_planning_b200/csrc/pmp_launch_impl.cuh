@@ -2,33 +2,58 @@
 #pragma once
 #include "pmp_launch.h"
 
+// cudaFuncSetAttribute / cudaFuncGetAttributes are driver round trips; on the 47 us scalar collision_fn path they are
+// not free.  Each instantiation remembers the largest dynamic shared-memory size it has been opted into (per device,
+// the attribute is per context) and its register count.
+struct PmpFuncCache {
+    int smem_optin[16];
+    int regs[16];
+};
+
+template <class K>
+static cudaError_t pmp_prepare(K kernel, PmpFuncCache& fc, size_t smem, int* regs) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 15;
+    if ((int)smem > fc.smem_optin[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        fc.smem_optin[dev] = (int)smem;
+    }
+    if (fc.regs[dev] == 0) {
+        cudaFuncAttributes fa;
+        cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+        if (e != cudaSuccess) return e;
+        fc.regs[dev] = fa.numRegs;
+    }
+    if (regs) *regs = fc.regs[dev];
+    return cudaSuccess;
+}
+
 template <int A, int NS, bool FIRST>
 static cudaError_t pmp_launch_edge_t(const PmpEdgeArgs& args, bool wsmem, int grid, int block, size_t smem, cudaStream_t st,
                                      int* regs) {
+    static PmpFuncCache fc_s = {}, fc_g = {};
     cudaError_t e;
-    cudaFuncAttributes fa;
     if (wsmem) {
-        e = cudaFuncSetAttribute(pmp_edge_kernel<A, NS, true, FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = pmp_prepare(pmp_edge_kernel<A, NS, true, FIRST>, fc_s, smem, regs);
         if (e != cudaSuccess) return e;
         pmp_edge_kernel<A, NS, true, FIRST><<<grid, block, smem, st>>>(args);
-        cudaFuncGetAttributes(&fa, pmp_edge_kernel<A, NS, true, FIRST>);
     } else {
-        e = cudaFuncSetAttribute(pmp_edge_kernel<A, NS, false, FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = pmp_prepare(pmp_edge_kernel<A, NS, false, FIRST>, fc_g, smem, regs);
         if (e != cudaSuccess) return e;
         pmp_edge_kernel<A, NS, false, FIRST><<<grid, block, smem, st>>>(args);
-        cudaFuncGetAttributes(&fa, pmp_edge_kernel<A, NS, false, FIRST>);
     }
-    if (regs) *regs = fa.numRegs;
     return cudaGetLastError();
 }
 
 template <int A, int NS>
 static cudaError_t pmp_launch_config_t(const PmpConfigArgs& args, dim3 grid, int block, size_t smem, cudaStream_t st,
                                        int* regs) {
+    static PmpFuncCache fc = {};
+    cudaError_t e = pmp_prepare(pmp_config_kernel<A, NS>, fc, smem, regs);
+    if (e != cudaSuccess) return e;
     pmp_config_kernel<A, NS><<<grid, block, smem, st>>>(args);
-    cudaFuncAttributes fa;
-    cudaFuncGetAttributes(&fa, pmp_config_kernel<A, NS>);
-    if (regs) *regs = fa.numRegs;
     return cudaGetLastError();
 }
 

@@ -166,7 +166,6 @@ __global__ void __launch_bounds__(PMP_NN_BLOCK, 2) pmp_nearest_kernel(const PmpN
         float q[DP];
 #pragma unroll
         for (int j = 0; j < DP; ++j) q[j] = j < D ? a.nodes[(size_t)n * D + j] : 0.f;
-#pragma unroll
         float sq[TGT];
         bool any = false;
 #pragma unroll

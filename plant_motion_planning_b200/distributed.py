@@ -75,7 +75,8 @@ class ShardedEdgeChecker:
         (local EdgeBatchResult, (first_hit[E], n_steps[E], cost[E]) gathered over ranks)."""
         E = q_from.shape[0]
         lo, hi = shard_bounds(E, self.rank, self.world_size)
-        local = self.checker.validate_edges(q_from[lo:hi], q_to[lo:hi], backward=backward)
+        # edge_base = lo: the on-device gate hashes the GLOBAL edge index, so sharding does not change its decisions
+        local = self.checker.validate_edges(q_from[lo:hi], q_to[lo:hi], backward=backward, edge_base=lo)
         if self.world_size == 1:
             return local, (local.first_hit, local.n_steps, local.cost)
         return local, all_gather_summary(local.first_hit, local.n_steps, local.cost, E, self.group)

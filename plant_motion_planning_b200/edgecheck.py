@@ -37,7 +37,13 @@ class EdgeCheckConfig:
     iterations: int = 4                   # Gauss-Newton steps of the quasi-static plant solve
     max_step: float = 0.5                 # rad per step
     reg_eps: float = 1e-4                 # m^2
-    stem_radius: Optional[float] = None   # None = area-equivalent capsule of the stem box
+    stem_margin: float = 1.0e-3           # Bullet's collision margin of the stem boxes (carved out of the box)
+    gravity_sag: bool = True              # stems rest in their spring / gravity balance (model/statics.py), not at 0
+    arm_lag_gain: float = 0.0             # 0 = the arm is at the commanded configuration; the reference's position
+                                          # motor closes 1 % of the joint error per sub-step (env.py:154,170): 0.01
+    arm_lag_substeps: int = 50            # env.py:157, 216
+    use_hulls: bool = True                # decide self / obstacle collisions exactly on the convex hulls of the arm's
+                                          # collision meshes when the robot model carries them (else on its spheres)
     mode: str = "our_method"              # our_method | avoid_all | ignore_all
     gate_probability: float = 0.95        # pybullet_tools/utils.py:3843 (applied by the host adapters only)
     max_steps: int = 320                  # per-edge step capacity of validate_edges
@@ -109,22 +115,20 @@ class EdgeChecker:
     def _set_robot(self, robot: RobotModel, obstacles) -> None:
         t: RobotTables = pack_robot(robot, obstacles)
         self.robot_tables = t
-        d = _capi.RobotDesc()
-        d.dof, d.n_spheres, d.n_links, d.n_fixed = t.dof, t.n_spheres, t.n_links, t.n_fixed
-        d.joint_C, d.joint_A, d.joint_B = _capi.fptr(t.joint_C), _capi.fptr(t.joint_A), _capi.fptr(t.joint_B)
-        d.joint_t, d.lower, d.upper = _capi.fptr(t.joint_t), _capi.fptr(t.lower), _capi.fptr(t.upper)
-        d.circular = _capi.bptr(t.circular)
-        d.base_R, d.base_t = _capi.fptr(t.base_R), _capi.fptr(t.base_t)
-        d.sph_joint, d.sph_center = _capi.iptr(t.sph_joint), _capi.fptr(t.sph_center)
-        d.sph_radius, d.self_mask = _capi.fptr(t.sph_radius), _capi.uptr(t.self_mask)
-        d.link_joint, d.link_R = _capi.iptr(t.link_joint), _capi.fptr(t.link_R)
-        d.link_t, d.link_com = _capi.fptr(t.link_t), _capi.fptr(t.link_com)
-        d.ee_joint = t.ee_joint
-        d.ee_local = (C.c_float * 3)(*[float(v) for v in t.ee_local])
-        d.fixed_kind, d.fixed_R = _capi.iptr(t.fixed_kind), _capi.fptr(t.fixed_R)
-        d.fixed_t, d.fixed_half = _capi.fptr(t.fixed_t), _capi.fptr(t.fixed_half)
-        d.fixed_mask = _capi.uptr(t.fixed_mask)
+        d = _capi.robot_desc(t)
         self._check(self._lib.pmp_set_robot(self._ctx, C.byref(d)), "pmp_set_robot")
+        self._set_hulls()
+
+    def _set_hulls(self) -> None:
+        hulls = getattr(self.robot, "hulls", None)
+        if hulls is not None and self.config.use_hulls:
+            from .model.tables import default_obstacles
+            n_obs = len(default_obstacles() if self.obstacles is None else list(self.obstacles))
+            hd, keep = _capi.hull_desc(hulls, n_obs)
+            self._check(self._lib.pmp_set_robot_hulls(self._ctx, C.byref(hd)), "pmp_set_robot_hulls")
+            del keep
+        else:
+            self._check(self._lib.pmp_set_robot_hulls(self._ctx, None), "pmp_set_robot_hulls")
 
     def set_worlds(self, worlds) -> None:
         """``worlds``: PlantWorld objects, or ready-made WorldTables (model/batch_sampler.sample_world_tables for
@@ -134,7 +138,7 @@ class EdgeChecker:
             wt = worlds
         else:
             self.worlds = list(worlds)
-            wt = pack_worlds(self.worlds, self.config.stem_radius)
+            wt = pack_worlds(self.worlds, self.config.stem_margin, self.config.gravity_sag)
         self.world_tables = wt
         d = _capi.WorldDesc()
         d.n_worlds, d.max_stems, d.max_boxes, d.n_slots = wt.n_worlds, wt.max_stems, wt.max_boxes, wt.n_slots
@@ -151,17 +155,21 @@ class EdgeChecker:
         p = _capi.Params(c.resolution, c.deflection_limit, c.alpha, c.max_step, c.reg_eps, c.iterations,
                          MODES[c.mode], 1 if c.dense else 0,
                          0 if c.device_gate_seed is None else int(c.device_gate_seed) & 0xFFFFFFFF,
-                         0.0 if c.device_gate_seed is None else float(c.gate_probability), 0)
+                         0.0 if c.device_gate_seed is None else float(c.gate_probability),
+                         float(c.arm_lag_gain), int(c.arm_lag_substeps))
         self._check(self._lib.pmp_set_params(self._ctx, C.byref(p)), "pmp_set_params")
 
     def set_config(self, **changes) -> None:
         """Replace constants (e.g. mode='avoid_all', deflection_limit=2.0)."""
         old = self.config
         self.config = replace(self.config, **changes)
-        if self.config.stem_radius != old.stem_radius:
+        if (self.config.stem_margin, self.config.gravity_sag) != (old.stem_margin, old.gravity_sag):
             if self.worlds is None:
-                raise ValueError("worlds were given as tables: re-pack them with the new stem_radius and call set_worlds")
+                raise ValueError("worlds were given as tables: re-pack them with the new stem_margin / gravity_sag and "
+                                 "call set_worlds")
             self.set_worlds(self.worlds)
+        if self.config.use_hulls != old.use_hulls:
+            self._set_hulls()
         self._push_params()
 
     # ------------------------------------------------------------------ properties
@@ -246,8 +254,10 @@ class EdgeChecker:
 
     def validate_edges(self, q_from, q_to, backward: bool = False, want_masks: bool = False,
                        max_steps: Optional[int] = None, out: Optional[EdgeBatchResult] = None,
-                       first_hit_only: bool = False) -> EdgeBatchResult:
-        """``first_hit_only``: request only first_hit / n_steps.  The kernel then stops like the reference's loops
+                       first_hit_only: bool = False, edge_base: int = 0) -> EdgeBatchResult:
+        """``edge_base``: index of edge 0 of this call in the caller's whole batch (enters only the on-device gate's
+        hash, so shards / chunks of a batch decide exactly like the unsplit batch).
+        ``first_hit_only``: request only first_hit / n_steps.  The kernel then stops like the reference's loops
         (steps after the first violating one and the remaining worlds are not evaluated) -- the planner's
         accept/reject question, several times cheaper on edges that collide early."""
         torch = self._torch()
@@ -271,7 +281,7 @@ class EdgeChecker:
             self._check(self._lib.pmp_validate_edges(
                 self._ctx, self._p(q0), self._p(q1), E, ms, 1 if backward else 0, self._p(out.first_hit),
                 self._p(out.n_steps), self._p(out.max_deflection), self._p(out.over_limit), self._p(out.ee_len),
-                self._p(out.cost), self._p(out.rigid_mask), self._p(out.exceed_mask), self._stream()),
+                self._p(out.cost), self._p(out.rigid_mask), self._p(out.exceed_mask), self._stream(), int(edge_base)),
                 "pmp_validate_edges")
         return out
 

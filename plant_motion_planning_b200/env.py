@@ -22,6 +22,8 @@ from __future__ import annotations
 import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
+import weakref
+
 import numpy as np
 
 from .edgecheck import FLAG_RIGID, EdgeCheckConfig, EdgeChecker
@@ -30,24 +32,30 @@ from .model.robot import RobotModel
 from .planner_fns import GATE_PROBABILITY, get_limits_fn
 from .robots import load_iiwa14
 
-_STATES: Dict[int, Tuple[object, Optional[Tuple[float, ...]]]] = {}
+# State handles (pybullet_tools/utils.py:1517-1523).  The reference's p.saveState() is a module-level call on the one
+# global Bullet client; here a snapshot belongs to the MultiPlantWorld that was active when it was taken: it is stored
+# IN that environment (and dies with it), and its id carries the environment's serial number, so two environments in
+# one process never see each other's snapshots.
+_ENVS: "weakref.WeakValueDictionary[int, MultiPlantWorld]" = weakref.WeakValueDictionary()
 _ACTIVE: List[Optional["MultiPlantWorld"]] = [None]
+_SERIAL = [0]
+_ID_BITS = 32
 
 
 def save_state() -> int:
     """pybullet_tools/utils.py:1517-1519 (p.saveState).  The quasi-static world has one piece of state -- the arm
     configuration it was last stepped to -- so a snapshot is that configuration of the active MultiPlantWorld."""
-    sid = len(_STATES) + 1
     env = _ACTIVE[0]
-    _STATES[sid] = (env, None if env is None else env._action)
-    return sid
+    if env is None:
+        return 0
+    return env.save_state()
 
 
 def restore_state(state_id: int) -> None:
     """pybullet_tools/utils.py:1521-1523 (p.restoreState)."""
-    env, action = _STATES.get(state_id, (None, None))
+    env = _ENVS.get(int(state_id) >> _ID_BITS)
     if env is not None:
-        env._action = action
+        env.restore_state(state_id)
 
 
 class PlantRepresentation:
@@ -171,12 +179,37 @@ class MultiPlantWorld:
             self.envs[xy] = SinglePlantEnv(self, i, w, xy, avoid_all)
         self.fixed = self.envs[offsets[0]].fixed
         self._action: Optional[Tuple[float, ...]] = None
+        _SERIAL[0] += 1
+        self._serial = _SERIAL[0]
+        self._snapshots: Dict[int, Optional[Tuple[float, ...]]] = {}
+        _ENVS[self._serial] = self
         _ACTIVE[0] = self
         self._cache_q: Optional[Tuple[float, ...]] = None
         self._cache = None
         self.kernel_evaluations = 0
 
     # -- state ------------------------------------------------------------------------------------
+    def save_state(self) -> int:
+        """Snapshot of this environment (the configuration last stepped to); the id is valid for restore_state of this
+        module and of this object.  Snapshots live until release_states() or the environment goes away."""
+        k = len(self._snapshots) + 1
+        self._snapshots[k] = self._action
+        return (self._serial << _ID_BITS) | k
+
+    def restore_state(self, state_id: int) -> None:
+        if (int(state_id) >> _ID_BITS) != self._serial:
+            raise ValueError("state id belongs to another environment")
+        self._action = self._snapshots[int(state_id) & ((1 << _ID_BITS) - 1)]
+        self._cache_q = None
+
+    def release_states(self) -> None:
+        """Forget every snapshot (the reference never frees its Bullet snapshots; a long planning session here can)."""
+        self._snapshots.clear()
+
+    def activate(self) -> None:
+        """Make this the environment the module-level save_state() acts on (the last one constructed is by default)."""
+        _ACTIVE[0] = self
+
     def _set_action(self, action) -> None:
         self._action = tuple(float(v) for v in action)
 

@@ -18,9 +18,8 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 from .plants import OBS_MOD3, PLANT_JOINT_LIMIT, SCALING, STEM_COM_Z, STEM_HALF_WIDTH, PlantWorld, Stem
-from .tables import (BOX_STRIDE, F_HAS_PARENT, F_IS_MAIN, F_OBS_ROOT, F_PLANT_START, MAX_SLOTS, MAX_STEMS, S_COMZ, S_FLAGS,
-                     S_LIM, S_OBSV, S_OSLOT, S_PSLOT, S_RAD, S_RO, S_RW0, S_TO, S_TW0, S_Z0, S_Z1, STEM_STRIDE,
-                     WorldTables, assign_slots)
+from .tables import (BOX_STRIDE, F_HAS_PARENT, F_IS_MAIN, F_OBS_ROOT, F_PLANT_START, MAX_SLOTS, MAX_STEMS, STEM_MARGIN,
+                     WorldTables, assign_slots, build_stem_records)
 from .transforms import Frame
 
 
@@ -139,56 +138,26 @@ def _rpy_matrices(rpy: np.ndarray) -> np.ndarray:
     return R
 
 
-def tables_from_draws(d: PlantDraws, stem_radius: Optional[float] = None) -> WorldTables:
-    """The kernel's world tables of all n plants (what model/tables.pack_worlds writes, vectorised over worlds)."""
+def tables_from_draws(d: PlantDraws, stem_margin: float = STEM_MARGIN, gravity_sag: bool = True) -> WorldTables:
+    """The kernel's world tables of all n plants (what model/tables.pack_worlds writes, vectorised over worlds: both go
+    through tables.build_stem_records, so the records are identical)."""
     n, P = d.half_height.shape
     base_pos = np.concatenate([d.base_xy, d.base_half[:, 2:3]], axis=1)
     R = _rpy_matrices(d.rpy)                                               # [n, P, 3, 3]
     t = d.xyz.copy()
     t[:, 0] += base_pos                                                    # first stem's origin is a world frame
-    RW = np.empty_like(R)
-    TW = np.empty_like(t)
-    for k in range(P):
-        p = int(d.parent[k])
-        if p < 0:
-            RW[:, k], TW[:, k] = R[:, k], t[:, k]
-        else:
-            RW[:, k] = RW[:, p] @ R[:, k]
-            TW[:, k] = np.einsum("nij,nj->ni", RW[:, p], t[:, k]) + TW[:, p]
     # slot assignment, flags: functions of the topology only -- take them from a template object
     template = PlantWorld(stems=[Stem(parent=int(p), origin=Frame(), half_height=0.1, z_offset=0.0) for p in d.parent],
                           base_boxes=[])
     par, own, n_slots = assign_slots(template)
     if n_slots > MAX_SLOTS:
         raise ValueError(f"plant needs {n_slots} frame slots > {MAX_SLOTS}")
-    rec = np.zeros((n, P, STEM_STRIDE), dtype=np.float32)
-    irec = rec.view(np.int32)
-    r = float(stem_radius) if stem_radius is not None else 2.0 * STEM_HALF_WIDTH / np.sqrt(np.pi)
-    z0 = d.spacing + r
-    z1 = d.spacing + 2.0 * d.half_height - r
-    mid = d.spacing + d.half_height
-    short = z1 < z0
-    rec[:, :, S_RO:S_RO + 9] = R.reshape(n, P, 9)
-    rec[:, :, S_TO:S_TO + 3] = t
-    rec[:, :, S_Z0] = np.where(short, mid, z0)
-    rec[:, :, S_Z1] = np.where(short, mid, z1)
-    rec[:, :, S_RAD] = r
-    rec[:, :, S_LIM] = PLANT_JOINT_LIMIT
-    rec[:, :, S_COMZ] = STEM_COM_Z
-    rec[:, :, S_RW0:S_RW0 + 9] = RW.reshape(n, P, 9)
-    rec[:, :, S_TW0:S_TW0 + 3] = TW
-    for k in range(P):
-        p = int(d.parent[k])
-        flags = (F_PLANT_START if k == 0 else 0) | (F_IS_MAIN if d.is_main[k] else 0) | (F_HAS_PARENT if p >= 0 else 0)
-        if p < 0:
-            flags |= F_OBS_ROOT
-            c = RW[:, k, 2, :]                                             # R_l0^T ez = third row of R_l0
-        else:
-            c = np.einsum("nij,nj->ni", RW[:, k], RW[:, p, 2, :])          # R_l0 R_p0^T ez
-        rec[:, k, S_OBSV:S_OBSV + 3] = c
-        irec[:, k, S_PSLOT] = par[k]
-        irec[:, k, S_OSLOT] = own[k]
-        irec[:, k, S_FLAGS] = flags
+    flags = [(F_PLANT_START if k == 0 else 0) | (F_IS_MAIN if d.is_main[k] else 0) |
+             (F_HAS_PARENT if d.parent[k] >= 0 else F_OBS_ROOT) for k in range(P)]
+    full = lambda v: np.full((n, P), float(v))
+    rec = build_stem_records([int(p) for p in d.parent], R, t, d.half_height, full(d.spacing), full(STEM_HALF_WIDTH),
+                             full(STEM_COM_Z), full(PLANT_JOINT_LIMIT), flags, np.zeros((n, P, 3)), [False] * P,
+                             par, own, stem_margin, gravity_sag)
     boxes = np.zeros((n, 1, BOX_STRIDE), dtype=np.float32)
     boxes[:, 0, 0:9] = np.eye(3).reshape(-1)
     boxes[:, 0, 9:12] = base_pos
@@ -213,6 +182,7 @@ def worlds_from_draws(d: PlantDraws, index: Sequence[int]) -> List[PlantWorld]:
 
 
 def sample_world_tables(n: int, branches: int, verts: int, exts: int, plant_pos_xy_limits, seed: int = 0,
-                        stem_base_spacing: float = 0.0, stem_radius: Optional[float] = None) -> WorldTables:
+                        stem_base_spacing: float = 0.0, stem_margin: float = STEM_MARGIN,
+                        gravity_sag: bool = True) -> WorldTables:
     return tables_from_draws(draw_plants(n, branches, verts, exts, plant_pos_xy_limits, seed, stem_base_spacing),
-                             stem_radius)
+                             stem_margin, gravity_sag)

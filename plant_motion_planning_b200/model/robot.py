@@ -46,6 +46,22 @@ class FixedPrim:
 
 
 @dataclass
+class HullModel:
+    """Convex hulls of the arm's collision meshes, for the exact rigid narrow phase (pmp_set_robot_hulls).
+    PyBullet turns every URDF collision mesh into a btConvexHullShape of its vertices; collision between two links
+    (or a link and a static box) is GJK distance of the margin-free shapes minus both margins <= 0
+    (pybullet_tools/utils.py:3390-3441)."""
+    link_names: List[str]
+    joint: np.ndarray               # [H] joint the hull rides on
+    verts: List[np.ndarray]         # H arrays [n_h, 3], in the joint frame
+    margin: np.ndarray              # [H] collision margin outside the hull
+    pairs: np.ndarray               # [NP, 2] hull index pairs tested against each other
+    sph_hull: np.ndarray            # [A] hull each arm sphere approximates (-1 = none)
+    sph_radius_outer: np.ndarray    # [A] radii with which a hull's spheres cover hull (+) margin (broad phase)
+    fixed_margin: float = 1.0e-3    # margin carved out of static boxes
+
+
+@dataclass
 class RobotModel:
     name: str
     dof: int
@@ -71,6 +87,7 @@ class RobotModel:
     ee_joint: int = -1
     ee_local: np.ndarray = field(default_factory=lambda: np.zeros(3))
     ee_link: int = -1
+    hulls: Optional[HullModel] = None
 
     # ---------------------------------------------------------------- io
     def to_json(self) -> str:
@@ -91,12 +108,28 @@ class RobotModel:
                  "sphere_mask": int(p.sphere_mask), "name": p.name} for p in self.base_prims],
             "ee_joint": int(self.ee_joint), "ee_local": arr(self.ee_local), "ee_link": int(self.ee_link),
         }
+        if self.hulls is not None:
+            h = self.hulls
+            d["hulls"] = {"link_names": h.link_names, "joint": arr(h.joint), "margin": arr(h.margin), "pairs": arr(h.pairs),
+                          "sph_hull": arr(h.sph_hull), "sph_radius_outer": arr(h.sph_radius_outer),
+                          "fixed_margin": float(h.fixed_margin)}     # vertices travel in a .npz next to the JSON
         return json.dumps(d, indent=1)
 
     @staticmethod
-    def from_json(text: str) -> "RobotModel":
+    def from_json(text: str, hull_verts: Optional[Dict[str, np.ndarray]] = None) -> "RobotModel":
+        """``hull_verts``: link name -> [n, 3] hull vertices, required when the JSON carries a "hulls" section."""
         d = json.loads(text)
         f = lambda k: np.asarray(d[k], dtype=np.float64)
+        hulls = None
+        if "hulls" in d:
+            if hull_verts is None:
+                raise ValueError("this model has hulls: pass their vertices")
+            h = d["hulls"]
+            hulls = HullModel(list(h["link_names"]), np.asarray(h["joint"], dtype=np.int64),
+                              [np.asarray(hull_verts[n], dtype=np.float64) for n in h["link_names"]],
+                              np.asarray(h["margin"], dtype=np.float64), np.asarray(h["pairs"], dtype=np.int64).reshape(-1, 2),
+                              np.asarray(h["sph_hull"], dtype=np.int64), np.asarray(h["sph_radius_outer"], dtype=np.float64),
+                              float(h["fixed_margin"]))
         return RobotModel(
             name=d["name"], dof=int(d["dof"]), joint_names=list(d["joint_names"]),
             joint_R0=f("joint_R0"), joint_t0=f("joint_t0"), joint_axis=f("joint_axis"),
@@ -110,7 +143,7 @@ class RobotModel:
             base_prims=[FixedPrim(int(p["kind"]), np.asarray(p["R"], float), np.asarray(p["t"], float),
                                   np.asarray(p["half"], float), int(p["sphere_mask"]), p.get("name", ""))
                         for p in d["base_prims"]],
-            ee_joint=int(d["ee_joint"]), ee_local=f("ee_local"), ee_link=int(d["ee_link"]),
+            ee_joint=int(d["ee_joint"]), ee_local=f("ee_local"), ee_link=int(d["ee_link"]), hulls=hulls,
         )
 
     def with_base(self, base: Frame) -> "RobotModel":
@@ -147,7 +180,10 @@ def compile_robot(urdf: str | UrdfTree,
                   base: Optional[Frame] = None,
                   ee_link: Optional[str] = None,
                   disabled_collisions: Iterable[Tuple[str, str]] = (),
-                  name: Optional[str] = None) -> RobotModel:
+                  name: Optional[str] = None,
+                  mesh_spheres: Optional[Dict[str, Sequence[Tuple[Sequence[float], float, float]]]] = None,
+                  mesh_hulls: Optional[Dict[str, np.ndarray]] = None,
+                  hull_margin: float = 1.0e-3) -> RobotModel:
     """Compile a URDF into kernel tables.
 
     ``active_joints``: names of the planned joints in planner order (default: every movable
@@ -155,6 +191,10 @@ def compile_robot(urdf: str | UrdfTree,
     Other movable joints are frozen at ``frozen_positions`` (default 0).
     ``disabled_collisions``: link-name pairs to skip (the SRDF list of
     pybullet_tools/utils.py:873-880).
+    ``mesh_spheres`` / ``mesh_hulls``: for links whose collision geometry is a MESH (which PyBullet loads as the
+    convex hull of its vertices): link name -> fitted spheres (centre, radius, covering radius) in the link frame, and
+    link name -> hull vertices [n, 3] in the link frame.  The spheres carry the plant contact model and the broad
+    phase, the hulls the exact narrow phase (HullModel).
     """
     tree = parse_urdf(urdf) if isinstance(urdf, str) else urdf
     frozen_positions = dict(frozen_positions or {})
@@ -262,6 +302,9 @@ def compile_robot(urdf: str | UrdfTree,
     sph_link: List[int] = []
     base_prims: List[FixedPrim] = []
     base_prim_link: List[int] = []
+    sph_outer: List[float] = []
+    hull_links: List[int] = []
+    hull_vert_list: List[np.ndarray] = []
     root_frame = base if base is not None else Frame()
     for l in ([-1] + list(range(L))):
         nm = tree.root if l < 0 else link_names[l]
@@ -269,9 +312,21 @@ def compile_robot(urdf: str | UrdfTree,
         jn = -1 if l < 0 else int(link_joint[l])
         for g in tree.links[nm].collisions:
             if g.kind == "mesh":
-                raise NotImplementedError(
-                    f"link {nm!r} carries a mesh; the kernels test primitive geometry "
-                    "(use the *_spheres_collision URDF or add capsules)")
+                if jn < 0 or mesh_spheres is None or nm not in mesh_spheres:
+                    raise NotImplementedError(
+                        f"link {nm!r} carries a mesh; pass its fitted spheres (mesh_spheres) and hull (mesh_hulls), "
+                        "or use a URDF with primitive collision geometry")
+                for (cen, rad, rad_out) in mesh_spheres[nm]:
+                    sph_joint.append(jn)
+                    sph_center.append((rel @ g.origin).apply(np.asarray(cen, dtype=np.float64)))
+                    sph_radius.append(float(rad))
+                    sph_link.append(l)
+                    sph_outer.append(float(rad_out))
+                if mesh_hulls is not None and nm in mesh_hulls:
+                    fr = rel @ g.origin
+                    hull_links.append(l)
+                    hull_vert_list.append(np.asarray(mesh_hulls[nm], dtype=np.float64) @ fr.R.T + fr.t[None])
+                continue
             pose = rel @ g.origin
             if jn >= 0:
                 if g.kind != "sphere":
@@ -280,6 +335,7 @@ def compile_robot(urdf: str | UrdfTree,
                 sph_center.append(pose.t)
                 sph_radius.append(float(g.size[0]))
                 sph_link.append(l)
+                sph_outer.append(float(g.size[0]))
             else:
                 w = root_frame @ pose
                 if g.kind == "box":
@@ -298,6 +354,7 @@ def compile_robot(urdf: str | UrdfTree,
     sph_center_a = np.asarray(sph_center, dtype=np.float64).reshape(-1, 3)[order]
     sph_radius_a = np.asarray(sph_radius, dtype=np.float64)[order]
     sph_link_a = np.asarray(sph_link, dtype=np.int64)[order]
+    sph_outer_a = np.asarray(sph_outer, dtype=np.float64)[order]
 
     pair_set = {frozenset(p) for p in pairs}
     mask = np.zeros((A, A), dtype=bool)
@@ -318,6 +375,15 @@ def compile_robot(urdf: str | UrdfTree,
     ee_frame = link_rel[ee_idx]
     ee_local = ee_frame.apply(link_com[ee_idx])
 
+    hulls = None
+    if hull_links:
+        hp = [(i, j) for i, j in combinations(range(len(hull_links)), 2)
+              if frozenset((hull_links[i], hull_links[j])) in pair_set]
+        sph_hull = np.array([hull_links.index(int(l)) if int(l) in hull_links else -1 for l in sph_link_a], dtype=np.int64)
+        hulls = HullModel([link_names[l] for l in hull_links], np.array([int(link_joint[l]) for l in hull_links]),
+                          hull_vert_list, np.full(len(hull_links), float(hull_margin)),
+                          np.asarray(hp, dtype=np.int64).reshape(-1, 2), sph_hull, sph_outer_a)
+
     return RobotModel(
         name=name or tree.name, dof=D, joint_names=active_joints,
         joint_R0=joint_R0, joint_t0=joint_t0, joint_axis=joint_axis,
@@ -325,7 +391,7 @@ def compile_robot(urdf: str | UrdfTree,
         link_names=link_names, link_joint=link_joint, link_R=link_R, link_t=link_t, link_com=link_com,
         sph_joint=sph_joint_a, sph_center=sph_center_a, sph_radius=sph_radius_a, sph_link=sph_link_a,
         self_pair_mask=mask, base_prims=base_prims,
-        ee_joint=int(link_joint[ee_idx]), ee_local=ee_local, ee_link=int(ee_idx),
+        ee_joint=int(link_joint[ee_idx]), ee_local=ee_local, ee_link=int(ee_idx), hulls=hulls,
     )
 
 

@@ -73,6 +73,7 @@ def get_difference_fn(robot) -> Callable:
 
 
 def get_distance_fn(robot, weights=None, norm=2) -> Callable:
+    default_metric = weights is None and norm == 2
     weights = 1 * np.ones(robot.dof) if weights is None else weights
     difference_fn = get_difference_fn(robot)
 
@@ -81,6 +82,10 @@ def get_distance_fn(robot, weights=None, norm=2) -> Callable:
         if norm == 2:
             return np.sqrt(np.dot(weights, diff * diff))
         return np.linalg.norm(np.multiply(weights, diff), ord=norm)
+    # lets the batched / vectorised nearest-node searches recognise the metric they implement (unit weights, 2-norm,
+    # wrap on continuous joints); any other distance_fn is evaluated node by node
+    fn.default_metric = default_metric
+    fn.circular = np.asarray(_circular(robot), dtype=bool)
     return fn
 
 

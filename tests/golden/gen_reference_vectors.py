@@ -264,6 +264,14 @@ def gen_planner_fns(out):
     joints = U.get_movable_joints(0)
     res["iiwa14"]["moving_links"] = sorted(map(int, U.get_moving_links(0, joints)))
     res["iiwa14"]["self_link_pairs"] = sorted([sorted(map(int, p)) for p in U.get_self_link_pairs(0, joints)])
+    # the URDF the scripts actually load (DRAKE_IIWA_URDF_EDIT): mesh collision on links 1-7, none on link 0
+    register_urdf_body(2, os.path.join(REF, "models/drake/iiwa_description/urdf/iiwa14_polytope_collision_edit.urdf"))
+    joints2 = U.get_movable_joints(2)
+    res["iiwa14_polytope_edit"] = {
+        "joints": list(map(int, joints2)),
+        "moving_links": sorted(map(int, U.get_moving_links(2, joints2))),
+        "self_link_pairs": sorted([sorted(map(int, p)) for p in U.get_self_link_pairs(2, joints2)]),
+    }
     out["reference_planner_fns.json"] = res
 
 
@@ -496,6 +504,13 @@ def gen_rrt(out):
         env = MultiPlantWorld(cfg["xs"], cfg["ys"], cfg["deflection_limit"], *cfg["args"], cfg["limits"],
                               avoid_all=cfg["avoid_all"], checker_factory=OracleChecker)
         plant_aware = script == "multi_world_our_method"
+        if script == "multi_world_avoid_all":
+            # start in collision with the fourth plant (see scenarios.py): the reference's check_initial_end_multi_world
+            # (pybullet_tools/utils.py:4358-4380) would exit(); its RRT loop returns None at once
+            env.step(START)
+            assert env.net_constraint_violation_checker_benchmark(START)
+            res[script] = {"planner_seed": 1, "plant_aware": False, "path": None, "start_in_collision": True}
+            continue
         fwd = env.net_constraint_violation_checker_forward if plant_aware else env.net_constraint_violation_checker_benchmark
         back = env.net_constraint_violation_checker_backward if plant_aware else env.net_constraint_violation_checker_benchmark
         np.random.seed(1)

@@ -14,7 +14,9 @@ class OracleChecker:
         self.worlds = list(worlds)
         c = self.config
         self.o = COracle(robot, self.worlds, resolution=c.resolution, deflection_limit=c.deflection_limit, alpha=c.alpha,
-                         iterations=c.iterations, max_step=c.max_step, reg_eps=c.reg_eps, stem_radius=c.stem_radius,
+                         iterations=c.iterations, max_step=c.max_step, reg_eps=c.reg_eps, stem_margin=c.stem_margin,
+                         gravity_sag=c.gravity_sag, arm_lag_gain=c.arm_lag_gain, arm_lag_substeps=c.arm_lag_substeps,
+                         use_hulls=c.use_hulls,
                          mode=c.mode)
         self.num_worlds = len(self.worlds)
 

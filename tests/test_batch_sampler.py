@@ -20,6 +20,8 @@ def test_tables_equal_the_scalar_packer_on_the_same_draws(args, spacing):
     ref = pack_worlds(B.worlds_from_draws(d, range(40)))
     assert wt.stems.shape == ref.stems.shape and wt.n_slots == ref.n_slots
     assert np.array_equal(wt.stems[..., :24], ref.stems[..., :24]) and np.array_equal(wt.stems[..., 27:], ref.stems[..., 27:])
+    if args[0] > 0:
+        assert np.abs(wt.stems[..., 28:30]).max() > 0.01, "the rest pose of a branched plant must carry gravity sag"
     assert np.array_equal(wt.stems.view(np.int32)[..., 24:27], ref.stems.view(np.int32)[..., 24:27])   # slots, flags
     assert np.array_equal(wt.boxes, ref.boxes) and np.array_equal(wt.n_stems, ref.n_stems)
     # same topology as the sequential restatement of create_plant_params
@@ -54,11 +56,13 @@ def test_distributions_match_the_sequential_sampler():
         worlds.append(sample_world(2, 3, 2, LIMITS, stem_base_spacing=0.05))
     seq = pack_worlds(worlds).stems
     vec = B.sample_world_tables(1500, 2, 3, 2, LIMITS, seed=9, stem_base_spacing=0.05).stems
-    for col in (0, 4, 8, 9, 10, 11, 13, 16, 17, 18, 32, 40, 41, 42, 43):     # frames, capsule, observer, rest frames
+    for col in (0, 4, 8, 9, 10, 11, 13, 14, 16, 17, 18, 23, 28, 29, 32, 40, 41, 42, 43, 44, 46):   # rest frames, box, observer, sag, origins
         a, b = seq[..., col].astype(np.float64), vec[..., col].astype(np.float64)
         scale = max(a.std(), 1e-3)
-        assert abs(a.mean() - b.mean()) <= 0.03 * scale + 1e-6, col         # 31 500 samples per column
-        assert abs(a.std() - b.std()) <= 0.05 * scale + 1e-6, col
+        # 31 500 samples per column; the sag-derived columns are correlated within a plant (1500 independent plants)
+        k = 4.0 if col in (23, 28, 29) else 1.0
+        assert abs(a.mean() - b.mean()) <= k * 0.03 * scale + 1e-6, col
+        assert abs(a.std() - b.std()) <= k * 0.05 * scale + 1e-6, col
 
 
 def test_capacity_and_bad_arguments():
@@ -88,4 +92,4 @@ def test_gpu_accepts_tables_directly():
     sub = EdgeChecker(robot, B.tables_from_draws(B.draw_plants(4096, 1, 2, 1, LIMITS, seed=1)), EdgeCheckConfig())
     assert torch.equal(out.first_hit, sub.validate_edges(Q[:64], Q[64:128]).first_hit)
     with pytest.raises(ValueError):
-        a.set_config(stem_radius=0.03)
+        a.set_config(stem_margin=0.002)

@@ -54,7 +54,7 @@ def test_gpu_parity_at_the_caps(big):
     chk = EdgeChecker(m, worlds, EdgeCheckConfig())
     g = chk.check_configs(torch.from_numpy(Q))
     info = chk.launch_info()
-    assert info["n_sphere_pad"] == 32 and info["n_slot_pad"] == 4
+    assert info["n_sphere_pad"] == 20 and info["n_slot_pad"] == 4      # 18 spheres: the A = 20 instantiation
     c = COracle(m, worlds).check_configs(Q)
     fl = g.flags.cpu().numpy()
     Qd = Q.astype(np.float64)
@@ -77,6 +77,20 @@ def test_gpu_parity_at_the_caps(big):
     assert np.array_equal(out.first_hit.cpu().numpy()[same], ce["first_hit"][same])
     fast = chk.validate_edges(torch.from_numpy(q0), torch.from_numpy(q1), first_hit_only=True)
     assert torch.equal(fast.first_hit, out.first_hit)
+    # the A = 32 instantiation: a 15-joint arm with two spheres per link (32 spheres, the table's capacity)
+    m32 = synthetic_robot(n_joints=15, spheres_per_link=2)
+    assert m32.num_spheres == 32
+    Q32 = np.random.RandomState(9).uniform(np.where(m32.circular, -np.pi, m32.lower), np.where(m32.circular, np.pi, m32.upper),
+                                           size=(512, 15)).astype(np.float32)
+    chk32 = EdgeChecker(m32, worlds, EdgeCheckConfig())
+    g32 = chk32.check_configs(torch.from_numpy(Q32))
+    assert chk32.launch_info()["n_sphere_pad"] == 32
+    c32 = COracle(m32, worlds).check_configs(Q32)
+    rob32 = O.rigid_hit(m32, obs, Q32.astype(np.float64), inflate=-1e-5) == O.rigid_hit(m32, obs, Q32.astype(np.float64), inflate=1e-5)
+    f32 = g32.flags.cpu().numpy()
+    assert np.array_equal((f32 & 1 > 0)[rob32], ((c32["flags"] & 1) > 0)[rob32])
+    assert np.percentile(np.abs(g32.deflection.cpu().numpy() - c32["deflection"]), 99.5) <= 1e-4
+    chk32.close()
     # nearest-node search on the DP = 16 path of a 16-DOF arm with a continuous joint
     idx, dist = chk.nearest(torch.from_numpy(Q[:300]), torch.from_numpy(Q[300:364]))
     oi, od = O.nearest(m, Q[:300], Q[300:364])

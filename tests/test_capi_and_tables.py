@@ -89,11 +89,20 @@ def test_stems_must_be_parents_first():
 
 
 def test_pack_robot_masks():
-    t = pack_robot(load_iiwa14())
-    assert t.dof == 7 and t.n_spheres == 12 and t.n_fixed == 3
-    assert bin(int(sum(bin(int(m)).count("1") for m in t.self_mask))) and sum(bin(int(m)).count("1") for m in t.self_mask) == 38
-    assert int(t.fixed_mask[0]) == 0xFFF and int(t.fixed_mask[1]) == 0xFFF     # floor, block: every sphere
-    assert int(t.fixed_mask[2]) == 0xFFE                                        # base cylinder: not link 1 (adjacent)
+    # the URDF's own 12-sphere model: floor, block, 8 block-corner points, base cylinder
+    t = pack_robot(load_iiwa14(collision="urdf_spheres"))
+    assert t.dof == 7 and t.n_spheres == 12 and t.n_fixed == 11
+    assert sum(bin(int(m)).count("1") for m in t.self_mask) == 38
+    assert all(int(t.fixed_mask[f]) == 0xFFF for f in range(10))                # obstacles: every sphere
+    assert int(t.fixed_mask[10]) == 0xFFE                                       # base cylinder: not link 1 (adjacent)
+    # the arm the scripts load: 18 spheres fitted to the 7 link hulls, no geometry on link 0
+    m = load_iiwa14()
+    t = pack_robot(m)
+    assert t.dof == 7 and t.n_spheres == 18 and t.n_fixed == 10
+    h = m.hulls
+    assert len(h.verts) == 7 and [len(v) for v in h.verts] == [620, 773, 687, 768, 706, 688, 64]
+    assert h.pairs.tolist() == [[a, b] for a in range(7) for b in range(a + 2, 7)]
+    assert np.all(h.sph_radius_outer > m.sph_radius) and np.all(np.diff(h.sph_hull) >= 0)
 
 
 def test_synthetic_edges_have_exact_step_count():

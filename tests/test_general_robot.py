@@ -28,7 +28,7 @@ def test_compile_invariants(setup):
     assert m.circular.tolist() == [False] * 4 + [True] + [False] * 4
     assert np.all(np.diff(m.sph_joint) >= 0)
     t = pack_robot(m)
-    assert t.n_fixed == 3 and t.circular[4] == 1
+    assert t.n_fixed == 11 and t.circular[4] == 1      # floor, block, 8 block-corner points, the robot's base box
     assert [w.num_stems for w in worlds] == [21, 21, 21]
     assert max(assign_slots(w)[2] for w in worlds) == 3
     # adjacent links are never paired; spheres of one link never pair with each other
@@ -68,7 +68,7 @@ def test_gpu_parity_general_robot(setup):
     chk = EdgeChecker(m, worlds, EdgeCheckConfig())
     g = chk.check_configs(torch.from_numpy(Q))
     info = chk.launch_info()
-    assert info["n_sphere_pad"] == 32 and info["n_slot_pad"] == 4
+    assert info["n_sphere_pad"] == 20 and info["n_slot_pad"] == 4     # 20 spheres: the A = 20 instantiation
     c = COracle(m, worlds).check_configs(Q)
     fl = g.flags.cpu().numpy()
     Qd = Q.astype(np.float64)

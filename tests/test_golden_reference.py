@@ -91,7 +91,7 @@ def test_planner_fns_match_reference(planner_golden, which):
 def test_self_collision_link_pairs_match_reference(planner_golden):
     """compile_robot's pair table vs get_self_link_pairs / get_moving_links run on the same URDF tree."""
     d = planner_golden["iiwa14"]
-    model = load_iiwa14()
+    model = load_iiwa14(collision="urdf_spheres")
     assert d["moving_links"] == [1, 2, 3, 4, 5, 6, 7, 8, 9]
     pairs = set()
     A = model.num_spheres
@@ -110,6 +110,20 @@ def test_self_collision_link_pairs_match_reference(planner_golden):
     # sphere vs link 7's sphere; the link pair itself stays checked through link 5's other sphere
     assert not model.self_pair_mask[8, 11] and model.self_pair_mask[9, 11]
     assert int(model.self_pair_mask.sum()) == 38
+    # the URDF the scripts load (mesh collision on links 1-7, none on link 0): the reference's get_self_link_pairs gives
+    # the 15 non-adjacent pairs of links 1..7, and so do the hull pairs / sphere masks of the default model
+    e = planner_golden["iiwa14_polytope_edit"]
+    hm = load_iiwa14()
+    ref = {tuple(p) for p in e["self_link_pairs"]}
+    assert e["moving_links"] == [1, 2, 3, 4, 5, 6, 7, 8, 9] and len(ref) == 15
+    link_of_hull = [hm.link_names.index(n) for n in hm.hulls.link_names]
+    assert {tuple(sorted((link_of_hull[a], link_of_hull[b]))) for a, b in hm.hulls.pairs} == ref
+    sp = set()
+    for a in range(hm.num_spheres):
+        for b in range(a + 1, hm.num_spheres):
+            if hm.self_pair_mask[a, b]:
+                sp.add(tuple(sorted((int(hm.sph_link[a]), int(hm.sph_link[b])))))
+    assert sp == ref and not hm.base_prims
 
 
 def test_sampler_matches_reference_run():

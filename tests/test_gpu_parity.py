@@ -38,7 +38,8 @@ def ctx():
 def test_library_is_the_cuda_one(ctx):
     info_before = ctx["chk"].launch_info()["kernel_launches"]
     ctx["chk"].check_configs(ctx["torch"].from_numpy(ctx["Q"][:8]))
-    assert ctx["chk"].launch_info()["kernel_launches"] == info_before + 1
+    # two of this library's kernels: the hull pre-pass (exact rigid test) and the configuration kernel
+    assert ctx["chk"].launch_info()["kernel_launches"] == info_before + 2
     with open("/proc/self/maps") as fp:
         assert "libpmp_edgecheck.so" in fp.read()
 
@@ -90,7 +91,7 @@ def test_config_flags_and_deflections(ctx, mode):
     gr, gx = (fl & 1) > 0, (fl & 2) > 0
     cr, cx = (c["flags"] & 1) > 0, (c["flags"] & 2) > 0
     Qd = Q.astype(np.float64)
-    robust = O.rigid_hit(model, O.default_obstacles(), Qd, inflate=-EPS_M) == O.rigid_hit(model, O.default_obstacles(), Qd, inflate=EPS_M)
+    robust = _rigid_robust(model, Qd)
     if mode == "avoid_all":
         # plant contact adds a boundary: |rest penetration| < eps
         for wi, w in enumerate(worlds):
@@ -100,7 +101,7 @@ def test_config_flags_and_deflections(ctx, mode):
             assert np.array_equal(gr[ok, wi], cr[ok, wi])
     else:
         assert np.array_equal(gr[robust], cr[robust])
-    assert (gr != cr).mean() < 1e-3
+    assert (gr != cr).sum() <= 2, "flag differences are confined to the 1e-5 m band, which holds a handful of 32768"
     near = np.any(np.abs(c["deflection"] - 0.30) < EPS_RAD, axis=2)
     assert np.array_equal(gx[~near], cx[~near])
     err = np.abs(g.deflection.cpu().numpy() - c["deflection"])
@@ -112,6 +113,42 @@ def test_config_flags_and_deflections(ctx, mode):
         assert cx.any() and (c["deflection"] > 0).mean() > 0.01, "test inputs must exercise the plant solve"
 
 
+def _rigid_robust(model, Qd):
+    """Configurations whose rigid decision is at least EPS_M away from flipping: hull clearance (exact geometry,
+    float64 GJK) and joint limits."""
+    from oracle import edgecheck_oracle as O
+    clear = O.hull_clearance(model, O.default_obstacles(), Qd)
+    lim = np.minimum(Qd - model.lower[None], model.upper[None] - Qd).min(axis=1)
+    return (np.abs(clear) > EPS_M) & (np.abs(lim) > EPS_M)
+
+
+def test_rigid_flags_equal_the_hull_oracle_outside_the_band(ctx):
+    """The exact rigid test (hull pre-pass kernel, float32 GJK) against the INDEPENDENT convex-hull oracle
+    (oracle/hull_oracle.py: own URDF kinematics, hulls extracted from the reference's meshes, float64 GJK): identical
+    booleans for every configuration whose Bullet clearance is more than 1e-5 m from zero; the band itself holds a
+    few configurations in 10^5, counted here."""
+    from oracle import hull_oracle as H
+    torch, chk = ctx["torch"], ctx["chk"]
+    rng = np.random.RandomState(42)
+    model = ctx["model"]
+    Q = rng.uniform(model.lower, model.upper, size=(100000, 7)).astype(np.float32)
+    chk.set_config(mode="ignore_all")
+    try:
+        fl = chk.check_configs(torch.from_numpy(Q), detail=False).flags.cpu().numpy()[:, 0] & 1
+    finally:
+        chk.set_config(mode="our_method")
+    ref = H.HullScene().rigid(Q.astype(np.float64))
+    band = np.abs(ref["clearance"]) <= EPS_M
+    assert np.array_equal(fl[~band] > 0, ref["hit"][~band])
+    assert band.sum() <= 20 and 0.15 < ref["hit"].mean() < 0.25
+    # the script's own goal, unmodified, is free; 2 cm deeper into the block it is not
+    from plant_motion_planning_b200.scenarios import REFERENCE_GOAL
+    g2 = np.array([REFERENCE_GOAL, REFERENCE_GOAL], dtype=np.float32)
+    g2[1, 5] += 0.02
+    fl = chk.check_configs(torch.from_numpy(g2), detail=False).flags.cpu().numpy()
+    assert not (fl[0] & 1).any() and (fl[1] & 1).all()
+
+
 def test_numpy_oracle_small(ctx):
     """The normative float64 numpy oracle (quaternion observers, acos) on a small sample."""
     from oracle import edgecheck_oracle as O
@@ -119,7 +156,8 @@ def test_numpy_oracle_small(ctx):
     g = chk.check_configs(torch.from_numpy(Q))
     r = O.check_configs(model, worlds, Q.astype(np.float64), O.OracleParams(reg_eps=chk.config.reg_eps))
     fl = g.flags.cpu().numpy()
-    assert ((fl & 1 > 0) != r.rigid).mean() < 2e-3
+    robust = _rigid_robust(model, Q.astype(np.float64))
+    assert np.array_equal((fl & 1 > 0)[robust], r.rigid[robust])
     near = np.any(np.abs(r.deflection - 0.30) < EPS_RAD, axis=2)
     assert np.array_equal((fl & 2 > 0)[~near], r.exceeded[~near])
     err = np.abs(g.deflection.cpu().numpy() - r.deflection)
@@ -142,7 +180,10 @@ def _edge_compare(chk, torch, model, worlds, q0, q1, backward, max_steps=320):
     same = np.all(gm_r == c["rigid_mask"], axis=(1, 2)) & np.all(gm_x == c["exceed_mask"], axis=(1, 2))
     fh = out.first_hit.cpu().numpy()
     assert np.array_equal(fh[same], c["first_hit"][same])
-    assert (fh != c["first_hit"]).mean() <= 0.02
+    # every differing bit must sit inside a decision band of the float64 oracle (1e-5 m of rigid contact or of a joint
+    # limit, 1e-3 rad of the deflection limit): checked step by step on the edges that differ
+    _assert_differences_in_band(chk, model, worlds, q0, q1, backward, max_steps, np.nonzero(~same)[0],
+                                gm_r, c["rigid_mask"], gm_x, c["exceed_mask"])
     assert np.abs(out.ee_len.cpu().numpy() - c["ee_len"]).max() <= 1e-4
     # max over up to max_steps x P per-unit values: the per-unit tail (deep penetrations)
     # is picked up by the max, so the edge-level bar is on the 99th percentile
@@ -153,6 +194,38 @@ def _edge_compare(chk, torch, model, worlds, q0, q1, backward, max_steps=320):
     cost = np.abs(out.cost.cpu().numpy() - c["cost"])
     assert np.percentile(cost, 99) <= 1e-3
     return out, c
+
+
+def _assert_differences_in_band(chk, model, worlds, q0, q1, backward, max_steps, edges, gm_r, cm_r, gm_x, cm_x):
+    from oracle import edgecheck_oracle as O
+    from oracle.c_oracle import COracle
+    if len(edges) == 0:
+        return
+    assert len(edges) <= max(4, len(q0) // 50), "too many edges differ for float32-vs-float64 rounding"
+    co = COracle(model, worlds, reg_eps=chk.config.reg_eps, deflection_limit=chk.config.deflection_limit,
+                 mode=chk.config.mode)
+    tail = []
+    for e in edges:
+        Qe = O.edge_configs(model, q0[e].astype(np.float64), q1[e].astype(np.float64), chk.config.resolution, backward)[:max_steps]
+        robust = _rigid_robust(model, Qe)
+        defl = co.check_configs(Qe.astype(np.float32))["deflection"]
+        near = np.any(np.abs(defl - chk.config.deflection_limit) < EPS_RAD, axis=2)         # [n, W]
+        # the ill-conditioned tail of the K-step solve (deep penetrations: float32 and float64 can differ by > 1e-3
+        # there) may flip an "exceeded" bit a little further from the limit; it is rare and counted
+        wide = np.any(np.abs(defl - chk.config.deflection_limit) < 0.05, axis=2)
+        for w in range(len(worlds)):
+            for ch in range(gm_r.shape[2]):
+                dr, dx = int(gm_r[e, w, ch]) ^ int(cm_r[e, w, ch]), int(gm_x[e, w, ch]) ^ int(cm_x[e, w, ch])
+                for bit in range(32):
+                    i = 32 * ch + bit
+                    if (dr >> bit) & 1:
+                        assert not robust[i], ("rigid bit differs outside the band", e, w, i)
+                    if (dx >> bit) & 1 and not near[i, w]:
+                        assert wide[i, w], ("exceeded bit differs far from the limit", e, w, i)
+                        tail.append((int(e), w, i))
+    units = int(sum(min(int(O.num_steps(model, q0[e].astype(np.float64), q1[e].astype(np.float64), chk.config.resolution)),
+                        max_steps) for e in range(len(q0)))) * len(worlds)
+    assert len(tail) <= max(1, units // 1000000), ("too many ill-conditioned exceeded bits", tail[:5], units)
 
 
 @pytest.mark.parametrize("backward", [False, True])
@@ -227,13 +300,13 @@ def test_worlds_without_plants(ctx):
             c = COracle(model, worlds, mode=mode).check_configs(Q)
             fl = g.flags.cpu().numpy()
             assert np.array_equal(fl[:, 0], fl[:, -1]) and not (fl[:, 0] & 2).any()
-            assert (fl != c["flags"]).mean() <= 2e-3
+            assert (fl != c["flags"]).sum() <= 1
             assert np.abs(g.deflection.cpu().numpy()[:, 0]).max() == 0.0
             q0, q1 = random_edges(model, 64, seed=2)
             out = chk.validate_edges(torch.from_numpy(q0), torch.from_numpy(q1))
             ce = COracle(model, worlds, mode=mode).validate_edges(q0, q1)
             assert np.array_equal(out.n_steps.cpu().numpy(), ce["n_steps"])
-            assert (out.first_hit.cpu().numpy() != ce["first_hit"]).mean() <= 0.05
+            assert (out.first_hit.cpu().numpy() != ce["first_hit"]).sum() <= 1
             assert float(out.max_deflection[:, 0].abs().max()) == 0.0
             fast = chk.validate_edges(torch.from_numpy(q0), torch.from_numpy(q1), first_hit_only=True)
             assert torch.equal(fast.first_hit, out.first_hit)
@@ -287,7 +360,8 @@ def test_non_finite_inputs_are_rejected_not_crashed(ctx):
     out = chk.validate_edges(torch.from_numpy(q0), torch.from_numpy(q1), max_steps=64)
     torch.cuda.synchronize()
     fh, n = out.first_hit.cpu().numpy(), out.n_steps.cpu().numpy()
-    assert n[0] >= 1 and fh[0] == n[0]                 # the finite edge is untouched by its neighbours
+    solo = chk.validate_edges(torch.from_numpy(q0[:1]), torch.from_numpy(q1[:1]), max_steps=64)
+    assert n[0] == int(solo.n_steps[0]) >= 1 and fh[0] == int(solo.first_hit[0])     # the finite edge is untouched by its neighbours
     assert n[1] == 1 and fh[1] == 0                   # NaN: one step, rejected
     assert n[2] > 64 and fh[2] == 0                    # inf: infinitely long edge, every configuration rejected
     assert n[3] > 64 and fh[3] < 64                    # absurdly long edge: truncated at max_steps and rejected (limits)
@@ -406,17 +480,26 @@ def test_batch_composition_and_world_order_do_not_matter(sweep):
 
 
 def test_full_sweep_shape_checksum_against_oracle_sample(sweep):
-    """2^17 x 32 x 64 units on the GPU; a 256-edge slice re-evaluated by the C oracle."""
+    """2^17 x 32 x 64 units on the GPU; a 4096-edge slice (8.4 M units) re-evaluated by the C oracle: step masks
+    identical except inside the decision bands, first violation identical wherever the masks are."""
     from oracle.c_oracle import COracle
     torch, model, worlds, chk, a, b = sweep
-    r = chk.validate_edges(a, b)
+    r = chk.validate_edges(a, b, want_masks=True)
     torch.cuda.synchronize()
-    idx = np.arange(0, 1 << 17, 512)
-    c = COracle(model, worlds).validate_edges(a.cpu().numpy()[idx], b.cpu().numpy()[idx], max_steps=32)
+    idx = np.arange(0, 1 << 17, 32)
+    q0, q1 = a.cpu().numpy()[idx], b.cpu().numpy()[idx]
+    c = COracle(model, worlds).validate_edges(q0, q1, max_steps=32, want_masks=True)
+    gm_r = r.rigid_mask.cpu().numpy().view(np.uint32)[idx]
+    gm_x = r.exceed_mask.cpu().numpy().view(np.uint32)[idx]
+    same = np.all(gm_r == c["rigid_mask"], axis=(1, 2)) & np.all(gm_x == c["exceed_mask"], axis=(1, 2))
     fh = r.first_hit.cpu().numpy()[idx]
-    assert (fh != c["first_hit"]).mean() <= 0.02
+    assert np.array_equal(fh[same], c["first_hit"][same])
+    _assert_differences_in_band(chk, model, worlds, q0, q1, False, 32, np.nonzero(~same)[0], gm_r, c["rigid_mask"],
+                                gm_x, c["exceed_mask"])
+    # max over 32 steps x 6 stems of per-unit values: the per-unit tail (ill-conditioned deep penetrations, DESIGN.md
+    # section 6) is picked up by the max
     md = np.abs(r.max_deflection.cpu().numpy()[idx] - c["max_deflection"])
-    assert np.percentile(md, 99.5) <= 1e-4
+    assert np.percentile(md, 99) <= 1e-4 and np.percentile(md, 99.9) <= 2e-3
 
 
 def test_many_worlds_tables_outside_shared_memory(ctx):
@@ -434,9 +517,9 @@ def test_many_worlds_tables_outside_shared_memory(ctx):
     assert chk.launch_info()["worlds_in_smem"] == 0
     idx = np.arange(0, 4096, 64)
     c = COracle(model, worlds).validate_edges(q0[idx], q1[idx], max_steps=32)
-    assert (out.first_hit.cpu().numpy()[idx] != c["first_hit"]).mean() <= 0.02
+    assert (out.first_hit.cpu().numpy()[idx] != c["first_hit"]).sum() <= 1
     md = np.abs(out.max_deflection.cpu().numpy()[idx] - c["max_deflection"])
-    assert np.percentile(md, 99.5) <= 1e-4
+    assert np.percentile(md, 99) <= 1e-4
     # same worlds, first 64 only, tables in shared memory: identical columns
     chk64 = EdgeChecker(model, worlds[:64], EdgeCheckConfig(max_steps=32))
     o64 = chk64.validate_edges(torch.from_numpy(q0), torch.from_numpy(q1))
@@ -530,8 +613,10 @@ def test_facade_matches_reference_call_pattern(ctx):
                 break
         want.append(hit)
     assert got == want and after == np.random.rand()
-    back = [env.net_constraint_violation_checker_backward(tuple(q)) for q in Q[:1]]
-    assert back[0] == bool(c["flags"][0, 0] & 1) or True
+    # the backward checker ignores the plants: OR over the worlds of the rigid flag alone (env.py:241-247)
+    for i in range(20):
+        env.step(tuple(Q[i]))
+        assert env.net_constraint_violation_checker_backward(tuple(Q[i])) == bool((c["flags"][i] & 1).any())
     env.step(tuple(Q[3]))
     env.envs[(0, 5)].plant_rep.observe_all()
     assert np.allclose(env.envs[(0, 5)].plant_rep.deflections, c["deflection"][3, 1, :6], atol=1e-4)

@@ -43,8 +43,12 @@ def _plan(script, checker_cls):
     np.random.seed(gold["planner_seed"])
     random.seed(gold["planner_seed"])
     backend = _Backend(chk, gold["plant_aware"])
-    path, _ = birrt.rrt_connect_multi_world(START, GOAL, F.get_distance_fn(robot), F.get_sample_fn(robot),
-                                            F.get_extend_fn(robot), backend)
+    res = birrt.rrt_connect_multi_world(START, GOAL, F.get_distance_fn(robot), F.get_sample_fn(robot),
+                                        F.get_extend_fn(robot), backend)
+    if gold["path"] is None:            # the script's own seed: the start touches a plant (scenarios.py)
+        assert res is None or res[0] is None
+        return None, None, gold
+    path, _ = res
     nxt = float(np.random.rand())
     np.random.seed(gold["smoothing_seed"])
     random.seed(gold["smoothing_seed"])
@@ -56,6 +60,8 @@ def _plan(script, checker_cls):
 @pytest.mark.parametrize("script", sorted(SCRIPTS))
 def test_restated_driver_equals_reference_rrt_on_oracle_flags(script):
     path, nxt, gold = _plan(script, OracleChecker)
+    if gold["path"] is None:
+        return
     assert path is not None and len(path) == gold["path_len"]
     assert [list(q) for q in path] == gold["path"]
     assert nxt == gold["next_np_rand"]
@@ -68,6 +74,8 @@ def test_restated_driver_equals_reference_rrt_on_oracle_flags(script):
 def test_gpu_plans_equal_reference_rrt(script):
     from plant_motion_planning_b200 import EdgeChecker
     path, nxt, gold = _plan(script, EdgeChecker)
+    if gold["path"] is None:
+        return
     assert path is not None and [list(q) for q in path] == gold["path"]
     assert nxt == gold["next_np_rand"]
     sm, np_next, py_next = gold["_smoothed"]
@@ -97,7 +105,10 @@ def _cost(script, factory):
     return ee_len, over, total, gold["execute"]
 
 
-@pytest.mark.parametrize("script", sorted(SCRIPTS))
+PLANNED = sorted(s for s in SCRIPTS if s != "multi_world_avoid_all")      # seed 19: the start touches a plant
+
+
+@pytest.mark.parametrize("script", PLANNED)
 def test_path_cost_equals_reference_execute_report(script):
     """env.path_cost vs the totals printed by the reference's unchanged Command.execute_multi_world
     (pybullet_tools/kuka_primitives.py:467-521) on the same smoothed path (oracle-backed facade)."""
@@ -109,7 +120,7 @@ def test_path_cost_equals_reference_execute_report(script):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("script", sorted(SCRIPTS))
+@pytest.mark.parametrize("script", PLANNED)
 def test_gpu_path_cost_equals_reference_execute_report(script):
     ee_len, over, total, ex = _cost(script, None)
     assert abs(ee_len - ex["ee_len"]) < 1e-4
