@@ -31,6 +31,8 @@ struct pmp_ctx {
     float4* d_hull_verts = nullptr;
     void* d_rigid_scratch = nullptr;
     size_t rigid_scratch_bytes = 0;
+    uint8_t* d_pair_tables = nullptr;      // clearance tables of the two-joint hull pairs (PmpHullTab::tab_*)
+    uint32_t self_mask_spheres[PMP_MAX_SPHERES];   // the sphere model's own pair masks (hull mode edits the device copy)
     float* d_stems = nullptr;
     int32_t* d_nstems = nullptr;
     float* d_boxes = nullptr;
@@ -112,7 +114,7 @@ extern "C" int pmp_destroy(pmp_ctx* ctx) {
     if (!ctx) return PMP_OK;
     cudaSetDevice(ctx->device);
     free_worlds(ctx);
-    cudaFree(ctx->d_hulls); cudaFree(ctx->d_hull_verts); cudaFree(ctx->d_rigid_scratch);
+    cudaFree(ctx->d_hulls); cudaFree(ctx->d_hull_verts); cudaFree(ctx->d_rigid_scratch); cudaFree(ctx->d_pair_tables);
     cudaFree(ctx->d_robot); cudaFree(ctx->d_links); cudaFree(ctx->d_scratch); cudaFree(ctx->d_tree_scratch); cudaFree(ctx->d_work_counter);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -183,6 +185,7 @@ extern "C" int pmp_set_robot(pmp_ctx* ctx, const pmp_robot_desc* r) {
     CK(cudaMemcpy(ctx->d_links, &lt, sizeof(lt), cudaMemcpyHostToDevice));
     ctx->h_robot = t;
     ctx->h_links = lt;
+    memcpy(ctx->self_mask_spheres, t.self_mask, sizeof(t.self_mask));
     ctx->has_robot = true;
     ctx->has_hulls = false;      // hulls describe one robot: a new robot starts on its sphere model
     return PMP_OK;
@@ -194,6 +197,7 @@ extern "C" int pmp_set_robot_hulls(pmp_ctx* ctx, const pmp_hull_desc* h) {
     CK(cudaSetDevice(ctx->device));
     PmpRobotTab t = ctx->h_robot;
     const int A = t.n_spheres, D = t.dof;
+    memcpy(t.self_mask, ctx->self_mask_spheres, sizeof(t.self_mask));
     if (!h || h->n_hulls == 0) {
         t.has_hulls = 0;
         for (int a = 0; a < A; ++a) t.sph_radius_outer[a] = t.sph_radius[a];
@@ -252,12 +256,86 @@ extern "C" int pmp_set_robot_hulls(pmp_ctx* ctx, const pmp_hull_desc* h) {
     std::vector<float4> verts((size_t)NV);
     for (int i = 0; i < NV; ++i) verts[i] = make_float4(h->hull_verts[3 * i], h->hull_verts[3 * i + 1], h->hull_verts[3 * i + 2], 0.f);
     t.has_hulls = 1;
+
+    // ---- clearance tables for hull pairs whose relative pose depends on exactly two joints (a = j + 1, b = j + 2) ----
+    // Lipschitz bound of the hull distance: a point of hull 2 moves at most rho_b per radian of q_b (its distance from
+    // axis b) and at most rho_a per radian of q_a (distance of joint b's origin from axis a + the hull's radius).
+    struct TabPlan { int pair, na, nb; float band; size_t off; };
+    std::vector<TabPlan> plans;
+    size_t tab_bytes = 0;
+    for (int p = 0; p < h->n_pairs; ++p) {
+        ht.tab_off[p] = -1;
+        const int h1 = ht.pairs[2 * p], h2 = ht.pairs[2 * p + 1];
+        const int j1 = ht.hull_joint[h1], j2 = ht.hull_joint[h2];
+        if (j2 - j1 != 2) continue;
+        const int ja = j1 + 1, jb = j2;
+        if (((t.circular_mask >> ja) & 1u) || ((t.circular_mask >> jb) & 1u)) continue;
+        const double ra = (double)t.upper[ja] - t.lower[ja], rb = (double)t.upper[jb] - t.lower[jb];
+        if (!(ra > 0 && rb > 0 && ra < 13 && rb < 13)) continue;
+        auto axis_of = [&](int j, double* a) {      // R0^T C = a a^T: take its largest column
+            double R0[9], M[9];
+            for (int k = 0; k < 9; ++k) R0[k] = (double)t.joint_C[9 * j + k] + t.joint_A[9 * j + k];
+            for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) {
+                M[3 * r + c] = 0;
+                for (int k = 0; k < 3; ++k) M[3 * r + c] += R0[3 * k + r] * t.joint_C[9 * j + 3 * k + c];
+            }
+            int kk = M[0] >= M[4] ? (M[0] >= M[8] ? 0 : 2) : (M[4] >= M[8] ? 1 : 2);
+            const double nrm = sqrt(M[4 * kk] > 0 ? M[4 * kk] : 1.0);
+            for (int r = 0; r < 3; ++r) a[r] = M[3 * r + kk] / nrm;
+            // axis in the joint's own (post-origin) frame; as a direction in the PARENT frame it is R0 a
+        };
+        double ab[3], aa[3];
+        axis_of(jb, ab);
+        axis_of(ja, aa);
+        double rho_b = 0, rmax = 0;
+        for (int i = ht.hull_off[h2]; i < ht.hull_off[h2 + 1]; ++i) {
+            const double v[3] = {h->hull_verts[3 * i], h->hull_verts[3 * i + 1], h->hull_verts[3 * i + 2]};
+            const double along = v[0] * ab[0] + v[1] * ab[1] + v[2] * ab[2];
+            const double n2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+            rho_b = fmax(rho_b, sqrt(fmax(n2 - along * along, 0.0)));
+            rmax = fmax(rmax, sqrt(n2));
+        }
+        // joint b's origin in the frame of joint a (after a's rotation): joint_t[b]; axis a in that frame is `aa`
+        const double tb[3] = {t.joint_t[3 * jb], t.joint_t[3 * jb + 1], t.joint_t[3 * jb + 2]};
+        const double alongt = tb[0] * aa[0] + tb[1] * aa[1] + tb[2] * aa[2];
+        const double rho_a = sqrt(fmax(tb[0] * tb[0] + tb[1] * tb[1] + tb[2] * tb[2] - alongt * alongt, 0.0)) + rmax;
+        const double msum = (double)ht.hull_margin[h1] + ht.hull_margin[h2];
+        double target = 0.35 * msum;                    // Lipschitz half of the band; float32 slack is added below
+        if (!(target > 1e-5)) continue;
+        double da = target / fmax(rho_a, 1e-3), db = target / fmax(rho_b, 1e-3);
+        long long na = (long long)ceil(ra / da) + 1, nb = (long long)ceil(rb / db) + 1;
+        if (na * nb > (1ll << 21)) continue;              // too fine to be worth a table
+        da = ra / (double)(na - 1); db = rb / (double)(nb - 1);
+        const float band = (float)(0.5 * (rho_a * da + rho_b * db) + 3.0e-5);
+        if (!(band < msum)) continue;
+        ht.tab_off[p] = (int32_t)tab_bytes; ht.tab_ja[p] = ja; ht.tab_jb[p] = jb; ht.tab_na[p] = (int32_t)na; ht.tab_nb[p] = (int32_t)nb;
+        ht.tab_lo_a[p] = t.lower[ja]; ht.tab_inv_a[p] = (float)(1.0 / da);
+        ht.tab_lo_b[p] = t.lower[jb]; ht.tab_inv_b[p] = (float)(1.0 / db);
+        plans.push_back({p, (int)na, (int)nb, band, tab_bytes});
+        tab_bytes += (size_t)(na * nb);
+        tab_bytes = (tab_bytes + 15) & ~(size_t)15;
+        // the covering spheres no longer cull this pair: drop its sphere pairs from the broad-phase mask
+        for (int a = ht.sph_lo[h1]; a < ht.sph_hi[h1]; ++a)
+            for (int b = ht.sph_lo[h2]; b < ht.sph_hi[h2]; ++b) t.self_mask[a < b ? a : b] &= ~(1u << (a < b ? b : a));
+    }
+
     cudaFree(ctx->d_hull_verts); ctx->d_hull_verts = nullptr;
+    cudaFree(ctx->d_pair_tables); ctx->d_pair_tables = nullptr;
     CK(cudaMalloc(&ctx->d_hull_verts, sizeof(float4) * (size_t)NV));
+    if (tab_bytes) CK(cudaMalloc(&ctx->d_pair_tables, tab_bytes));
     if (!ctx->d_hulls) CK(cudaMalloc(&ctx->d_hulls, sizeof(PmpHullTab)));
     CK(cudaMemcpy(ctx->d_hull_verts, verts.data(), sizeof(float4) * (size_t)NV, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_hulls, &ht, sizeof(ht), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_robot, &t, sizeof(t), cudaMemcpyHostToDevice));
+    for (const TabPlan& pl : plans) {
+        PmpPairTableArgs a;
+        a.robot = ctx->d_robot; a.hulls = ctx->d_hulls; a.hull_verts = ctx->d_hull_verts;
+        a.table = ctx->d_pair_tables + pl.off; a.pair = pl.pair; a.band = pl.band;
+        pmp_pair_table_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(a);
+        CK(cudaGetLastError());
+        ctx->info.kernel_launches++;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
     ctx->h_robot = t;
     ctx->h_hulls = ht;
     ctx->has_hulls = true;
@@ -269,6 +347,7 @@ static int launch_rigid(pmp_ctx* ctx, const float* q0, const float* q1, int32_t 
                         uint32_t* rigid_pre, const float* q, int32_t B, uint8_t* rigid_flags, cudaStream_t st) {
     PmpRigidArgs a;
     a.robot = ctx->d_robot; a.hulls = ctx->d_hulls; a.hull_verts = ctx->d_hull_verts; a.prm = ctx->prm;
+    a.pair_tables = ctx->d_pair_tables;
     a.q0 = q0; a.q1 = q1; a.E = E; a.max_steps = max_steps; a.backward = backward ? 1 : 0; a.rigid_pre = rigid_pre;
     a.q = q; a.B = B; a.rigid_flags = rigid_flags;
     const long long items = q ? (B + 31) / 32 : (long long)E * ((max_steps + 31) / 32);

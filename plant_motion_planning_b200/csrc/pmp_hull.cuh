@@ -17,33 +17,53 @@
 #pragma once
 #include "pmp_kernels.cuh"
 
-struct PmpGjkShape {          // one posed convex shape, identical in every lane
+struct PmpGjkShape {          // one posed convex shape, identical in every lane (kept in registers)
     const float4* verts;      // hull vertices (x, y, z, -) in the shape frame; nullptr: box / point given by `half`
     int n;
     float R[9], t[3];         // world pose
     float half[3];            // verts == nullptr: core half extents of a box (all zero: a point)
 };
 
-// world support point of S in world direction (dx, dy, dz); ties resolve to the lowest vertex index
-__device__ __forceinline__ void pmp_gjk_support(const PmpGjkShape& S, float dx, float dy, float dz, float (&o)[3]) {
+struct PmpV3 { float x, y, z; };
+__device__ __forceinline__ PmpV3 pmp_v3(float x, float y, float z) { PmpV3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ PmpV3 operator-(PmpV3 a, PmpV3 b) { return pmp_v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float pmp_dot(PmpV3 a, PmpV3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+__device__ __forceinline__ PmpV3 pmp_cross(PmpV3 a, PmpV3 b) {
+    return pmp_v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ PmpV3 pmp_axpy(float s, PmpV3 a, PmpV3 b) { return pmp_v3(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z)); }
+__device__ __forceinline__ bool pmp_same(PmpV3 a, PmpV3 b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
+// element k of (p0, p1, p2, p3) without dynamic indexing (the simplex stays in registers)
+__device__ __forceinline__ PmpV3 pmp_pick(int k, PmpV3 p0, PmpV3 p1, PmpV3 p2, PmpV3 p3) {
+    PmpV3 r = p0;
+    if (k == 1) r = p1;
+    if (k == 2) r = p2;
+    if (k == 3) r = p3;
+    return r;
+}
+
+// world support point of S in world direction d.  The scan over a hull's vertices is strided over the 32 lanes
+// (coalesced 16-byte loads), then a warp arg-max; ties go to an arbitrary maximal vertex (the distance does not care).
+__device__ __forceinline__ PmpV3 pmp_gjk_support(const PmpGjkShape& S, PmpV3 d) {
     float lx, ly, lz;
-    pmp_matT_vec(S.R, dx, dy, dz, lx, ly, lz);
+    pmp_matT_vec(S.R, d.x, d.y, d.z, lx, ly, lz);
     float vx, vy, vz;
     if (S.verts) {
         const int lane = threadIdx.x & 31;
         float best = -3.0e38f;
-        int bi = 0x7fffffff;
+        int bi = 0;
+#pragma unroll 4
         for (int i = lane; i < S.n; i += 32) {
             const float4 v = __ldg(S.verts + i);
             const float val = fmaf(v.x, lx, fmaf(v.y, ly, v.z * lz));
             if (val > best) { best = val; bi = i; }
         }
-#pragma unroll
-        for (int ofs = 16; ofs > 0; ofs >>= 1) {
-            const float ob = __shfl_xor_sync(PMP_FULL, best, ofs);
-            const int oi = __shfl_xor_sync(PMP_FULL, bi, ofs);
-            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-        }
+        // order-preserving map float -> uint, one warp max, the first lane holding it publishes its vertex index
+        const uint32_t u = __float_as_uint(best);
+        const uint32_t key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+        const uint32_t mx = __reduce_max_sync(PMP_FULL, key);
+        const int src = __ffs(__ballot_sync(PMP_FULL, key == mx)) - 1;
+        bi = __shfl_sync(PMP_FULL, bi, src);
         const float4 v = __ldg(S.verts + bi);
         vx = v.x; vy = v.y; vz = v.z;
     } else {
@@ -51,154 +71,114 @@ __device__ __forceinline__ void pmp_gjk_support(const PmpGjkShape& S, float dx, 
     }
     float x, y, z;
     pmp_mat_vec(S.R, vx, vy, vz, x, y, z);
-    o[0] = x + S.t[0]; o[1] = y + S.t[1]; o[2] = z + S.t[2];
+    return pmp_v3(x + S.t[0], y + S.t[1], z + S.t[2]);
 }
 
-__device__ __forceinline__ float pmp_dot3(const float* a, const float* b) { return fmaf(a[0], b[0], fmaf(a[1], b[1], a[2] * b[2])); }
-
-// closest point to the origin on triangle (a, b, c) by Voronoi regions; idx / n = supporting feature
-__device__ __forceinline__ void pmp_gjk_triangle(const float* a, const float* b, const float* c, float* out, int* idx, int& n) {
-    float ab[3], ac[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { ab[k] = b[k] - a[k]; ac[k] = c[k] - a[k]; }
-    const float d1 = -pmp_dot3(ab, a), d2 = -pmp_dot3(ac, a);
-    if (d1 <= 0.f && d2 <= 0.f) { out[0] = a[0]; out[1] = a[1]; out[2] = a[2]; idx[0] = 0; n = 1; return; }
-    const float d3 = -pmp_dot3(ab, b), d4 = -pmp_dot3(ac, b);
-    if (d3 >= 0.f && d4 <= d3) { out[0] = b[0]; out[1] = b[1]; out[2] = b[2]; idx[0] = 1; n = 1; return; }
+// closest point to the origin on triangle (a, b, c) by Voronoi regions; (i0, i1, i2) / n = supporting feature as
+// indices into {0, 1, 2}
+__device__ __forceinline__ PmpV3 pmp_gjk_triangle(PmpV3 a, PmpV3 b, PmpV3 c, int& i0, int& i1, int& i2, int& n) {
+    const PmpV3 ab = b - a, ac = c - a;
+    const float d1 = -pmp_dot(ab, a), d2 = -pmp_dot(ac, a);
+    i0 = 0; i1 = 1; i2 = 2;
+    if (d1 <= 0.f && d2 <= 0.f) { n = 1; i0 = 0; return a; }
+    const float d3 = -pmp_dot(ab, b), d4 = -pmp_dot(ac, b);
+    if (d3 >= 0.f && d4 <= d3) { n = 1; i0 = 1; return b; }
     const float vc = d1 * d4 - d3 * d2;
-    if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) {
-        const float v = d1 / (d1 - d3);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) out[k] = fmaf(v, ab[k], a[k]);
-        idx[0] = 0; idx[1] = 1; n = 2; return;
-    }
-    const float d5 = -pmp_dot3(ab, c), d6 = -pmp_dot3(ac, c);
-    if (d6 >= 0.f && d5 <= d6) { out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; idx[0] = 2; n = 1; return; }
+    if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) { n = 2; i0 = 0; i1 = 1; return pmp_axpy(d1 / (d1 - d3), ab, a); }
+    const float d5 = -pmp_dot(ab, c), d6 = -pmp_dot(ac, c);
+    if (d6 >= 0.f && d5 <= d6) { n = 1; i0 = 2; return c; }
     const float vb = d5 * d2 - d1 * d6;
-    if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) {
-        const float w = d2 / (d2 - d6);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) out[k] = fmaf(w, ac[k], a[k]);
-        idx[0] = 0; idx[1] = 2; n = 2; return;
-    }
+    if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) { n = 2; i0 = 0; i1 = 2; return pmp_axpy(d2 / (d2 - d6), ac, a); }
     const float va = d3 * d6 - d5 * d4;
     if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) {
-        const float w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
-#pragma unroll
-        for (int k = 0; k < 3; ++k) out[k] = fmaf(w, c[k] - b[k], b[k]);
-        idx[0] = 1; idx[1] = 2; n = 2; return;
+        n = 2; i0 = 1; i1 = 2;
+        return pmp_axpy((d4 - d3) / ((d4 - d3) + (d5 - d6)), c - b, b);
     }
     const float den = 1.f / (va + vb + vc);
-    const float v = vb * den, w = vc * den;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) out[k] = fmaf(ac[k], w, fmaf(ab[k], v, a[k]));
-    idx[0] = 0; idx[1] = 1; idx[2] = 2; n = 3;
+    n = 3;
+    return pmp_axpy(vc * den, ac, pmp_axpy(vb * den, ab, a));
 }
 
 // "GJK distance of the margin-free shapes <= msum" (msum = sum of both collision margins).  Early exits: the current
-// closest point of the simplex is an upper bound of the distance, v.w / |v| a lower bound.
-__device__ __noinline__ bool pmp_gjk_hit(const PmpGjkShape& A, const PmpGjkShape& B, float msum) {
-    float P[4][3];
-    int ns = 0;
-    float v[3], a[3], b[3], w[3];
+// closest point of the simplex is an upper bound of the distance, v.w / |v| a lower bound.  Every lane runs the same
+// scalar code on the same data (only the support scans are split over the lanes).
+__device__ __forceinline__ bool pmp_gjk_hit(const PmpGjkShape& A, const PmpGjkShape& B, float msum) {
+    PmpV3 p0, p1 = pmp_v3(0.f, 0.f, 0.f), p2 = p1, p3 = p1;
+    int ns;
     const float m2 = msum * msum;
+    PmpV3 v;
     // first point of A - B: the one furthest towards the origin as seen from the difference of the shape origins
     {
-        float dx = B.t[0] - A.t[0], dy = B.t[1] - A.t[1], dz = B.t[2] - A.t[2];
-        if (fmaf(dx, dx, fmaf(dy, dy, dz * dz)) < 1e-12f) { dx = 1.f; dy = 0.f; dz = 0.f; }
-        pmp_gjk_support(A, dx, dy, dz, a);
-        pmp_gjk_support(B, -dx, -dy, -dz, b);
+        PmpV3 d = pmp_v3(B.t[0] - A.t[0], B.t[1] - A.t[1], B.t[2] - A.t[2]);
+        if (pmp_dot(d, d) < 1e-12f) d = pmp_v3(1.f, 0.f, 0.f);
+        v = pmp_gjk_support(A, d) - pmp_gjk_support(B, pmp_v3(-d.x, -d.y, -d.z));
     }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { v[k] = a[k] - b[k]; P[0][k] = v[k]; }
+    p0 = v;
     ns = 1;
-    float vv = pmp_dot3(v, v);
+    float vv = pmp_dot(v, v);
     for (int it = 0; it < 48; ++it) {
         if (vv <= m2) return true;
-        pmp_gjk_support(A, -v[0], -v[1], -v[2], a);
-        pmp_gjk_support(B, v[0], v[1], v[2], b);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) w[k] = a[k] - b[k];
-        const float vw = pmp_dot3(v, w);
+        const PmpV3 w = pmp_gjk_support(A, pmp_v3(-v.x, -v.y, -v.z)) - pmp_gjk_support(B, v);
+        const float vw = pmp_dot(v, w);
         if (vw > 0.f && vw * vw > m2 * vv) return false;          // separated by more than the margins
         if (vv - vw <= 1e-6f * vv) return false;                  // converged with |v|^2 > msum^2
-        bool dup = false;
-        for (int i = 0; i < ns; ++i) dup |= (P[i][0] == w[0] && P[i][1] == w[1] && P[i][2] == w[2]);
-        if (dup) return false;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) P[ns][k] = w[k];
-        ++ns;
-        float nv[3];
-        if (ns == 2) {
-            float ab[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) ab[k] = P[1][k] - P[0][k];
-            const float t = -pmp_dot3(P[0], ab), den = pmp_dot3(ab, ab);
-            if (t <= 0.f || den <= 0.f) { nv[0] = P[0][0]; nv[1] = P[0][1]; nv[2] = P[0][2]; ns = 1; }
-            else if (t >= den) {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { nv[k] = P[1][k]; P[0][k] = P[1][k]; }
-                ns = 1;
-            } else {
-                const float u = t / den;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) nv[k] = fmaf(u, ab[k], P[0][k]);
-            }
-        } else if (ns == 3) {
-            int idx[3], n;
-            pmp_gjk_triangle(P[0], P[1], P[2], nv, idx, n);
-            float Q[3][3];
-            for (int i = 0; i < n; ++i)
-#pragma unroll
-                for (int k = 0; k < 3; ++k) Q[i][k] = P[idx[i]][k];
-            for (int i = 0; i < n; ++i)
-#pragma unroll
-                for (int k = 0; k < 3; ++k) P[i][k] = Q[i][k];
+        if (pmp_same(w, p0) || (ns > 1 && pmp_same(w, p1)) || (ns > 2 && pmp_same(w, p2))) return false;
+        PmpV3 nv;
+        if (ns == 1) {
+            p1 = w;
+            const PmpV3 ab = p1 - p0;
+            const float t = -pmp_dot(p0, ab), den = pmp_dot(ab, ab);
+            if (t <= 0.f || den <= 0.f) { nv = p0; ns = 1; }
+            else if (t >= den) { nv = p1; p0 = p1; ns = 1; }
+            else { nv = pmp_axpy(t / den, ab, p0); ns = 2; }
+        } else if (ns == 2) {
+            p2 = w;
+            int i0, i1, i2, n;
+            nv = pmp_gjk_triangle(p0, p1, p2, i0, i1, i2, n);
+            const PmpV3 q0 = pmp_pick(i0, p0, p1, p2, p3), q1 = pmp_pick(i1, p0, p1, p2, p3), q2 = pmp_pick(i2, p0, p1, p2, p3);
+            p0 = q0; p1 = q1; p2 = q2;
             ns = n;
         } else {
+            p3 = w;
             // tetrahedron: faces the origin lies outside of; a (nearly) flat one has no reliable inside
-            const int faces[4][4] = {{0, 1, 2, 3}, {0, 2, 3, 1}, {0, 3, 1, 2}, {1, 3, 2, 0}};
-            float e1[3], e2[3], e3[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { e1[k] = P[1][k] - P[0][k]; e2[k] = P[2][k] - P[0][k]; e3[k] = P[3][k] - P[0][k]; }
-            const float cr[3] = {e2[1] * e3[2] - e2[2] * e3[1], e2[2] * e3[0] - e2[0] * e3[2], e2[0] * e3[1] - e2[1] * e3[0]};
-            const float vol = fabsf(pmp_dot3(e1, cr));
-            const float scale = sqrtf(pmp_dot3(e1, e1) * pmp_dot3(e2, e2) * pmp_dot3(e3, e3));
+            const PmpV3 e1 = p1 - p0, e2 = p2 - p0, e3 = p3 - p0;
+            const float vol = fabsf(pmp_dot(e1, pmp_cross(e2, e3)));
+            const float scale = sqrtf(pmp_dot(e1, e1) * pmp_dot(e2, e2) * pmp_dot(e3, e3));
             const bool flat = !(vol > 1e-4f * scale);
-            float best = 3.0e38f, bp[3] = {0.f, 0.f, 0.f};
-            int bidx[3] = {0, 0, 0}, bn = 0, bf = -1;
-            for (int f = 0; f < 4; ++f) {
-                const float *pa = P[faces[f][0]], *pb = P[faces[f][1]], *pc = P[faces[f][2]], *pd = P[faces[f][3]];
-                float ab[3], ac[3], ad[3];
+            float best = 3.0e38f;
+            PmpV3 bp = pmp_v3(0.f, 0.f, 0.f);
+            int b0 = 0, b1 = 0, b2 = 0, bn = 0;
+            bool any = false;
 #pragma unroll
-                for (int k = 0; k < 3; ++k) { ab[k] = pb[k] - pa[k]; ac[k] = pc[k] - pa[k]; ad[k] = pd[k] - pa[k]; }
-                const float nn[3] = {ab[1] * ac[2] - ab[2] * ac[1], ab[2] * ac[0] - ab[0] * ac[2], ab[0] * ac[1] - ab[1] * ac[0]};
-                const float sp = -pmp_dot3(pa, nn), sd = pmp_dot3(ad, nn);
-                const bool outside = flat || sd == 0.f || sp * sd < 0.f;
-                if (!outside) continue;
-                float q[3];
-                int idx[3], n;
-                pmp_gjk_triangle(pa, pb, pc, q, idx, n);
-                const float dd = pmp_dot3(q, q);
+            for (int f = 0; f < 4; ++f) {
+                // faces (0,1,2|3) (0,2,3|1) (0,3,1|2) (1,3,2|0)
+                const int fa = f == 3 ? 1 : 0, fb = f == 0 ? 1 : (f == 1 ? 2 : 3), fc = f == 0 ? 2 : (f == 1 ? 3 : (f == 2 ? 1 : 2)),
+                          fd = f == 0 ? 3 : (f == 1 ? 1 : (f == 2 ? 2 : 0));
+                const PmpV3 pa = pmp_pick(fa, p0, p1, p2, p3), pb = pmp_pick(fb, p0, p1, p2, p3), pc = pmp_pick(fc, p0, p1, p2, p3),
+                            pd = pmp_pick(fd, p0, p1, p2, p3);
+                const PmpV3 nn = pmp_cross(pb - pa, pc - pa);
+                const float sp = -pmp_dot(pa, nn), sd = pmp_dot(pd - pa, nn);
+                if (!(flat || sd == 0.f || sp * sd < 0.f)) continue;
+                int i0, i1, i2, n;
+                const PmpV3 q = pmp_gjk_triangle(pa, pb, pc, i0, i1, i2, n);
+                const float dd = pmp_dot(q, q);
                 if (dd < best) {
-                    best = dd; bp[0] = q[0]; bp[1] = q[1]; bp[2] = q[2];
-                    bidx[0] = idx[0]; bidx[1] = idx[1]; bidx[2] = idx[2]; bn = n; bf = f;
+                    best = dd; bp = q; bn = n; any = true;
+                    // map the triangle-local indices back to simplex indices
+                    b0 = i0 == 0 ? fa : (i0 == 1 ? fb : fc);
+                    b1 = i1 == 0 ? fa : (i1 == 1 ? fb : fc);
+                    b2 = i2 == 0 ? fa : (i2 == 1 ? fb : fc);
                 }
             }
-            if (bf < 0) return true;                               // the origin is inside: the shapes intersect
-            float Q[3][3];
-            for (int i = 0; i < bn; ++i)
-#pragma unroll
-                for (int k = 0; k < 3; ++k) Q[i][k] = P[faces[bf][bidx[i]]][k];
-            for (int i = 0; i < bn; ++i)
-#pragma unroll
-                for (int k = 0; k < 3; ++k) P[i][k] = Q[i][k];
+            if (!any) return true;                                 // the origin is inside: the shapes intersect
+            const PmpV3 q0 = pmp_pick(b0, p0, p1, p2, p3), q1 = pmp_pick(b1, p0, p1, p2, p3), q2 = pmp_pick(b2, p0, p1, p2, p3);
+            p0 = q0; p1 = q1; p2 = q2;
             ns = bn;
-            nv[0] = bp[0]; nv[1] = bp[1]; nv[2] = bp[2];
+            nv = bp;
         }
-        const float nvv = pmp_dot3(nv, nv);
+        const float nvv = pmp_dot(nv, nv);
         if (nvv >= vv) return false;                               // no progress (rounding): |v|^2 > msum^2 stands
-        v[0] = nv[0]; v[1] = nv[1]; v[2] = nv[2];
+        v = nv;
         vv = nvv;
     }
     return vv <= m2;
@@ -208,6 +188,7 @@ struct PmpRigidArgs {
     const PmpRobotTab* robot;
     const PmpHullTab* hulls;
     const float4* hull_verts;
+    const uint8_t* pair_tables;
     PmpKernelParams prm;
     // edge mode (q == nullptr): steps of edges q0 -> q1, one bit per step into rigid_pre [E, C]
     const float* q0;
@@ -222,14 +203,73 @@ struct PmpRigidArgs {
     uint8_t* rigid_flags;
 };
 
+// Clearance-table lookup of hull pair p at joint values (qa, qb): 1 = certainly free, 2 = certainly colliding, 0 = ask GJK.
+__device__ __forceinline__ int pmp_pair_table(const PmpHullTab& ht, const uint8_t* __restrict__ tables, int p, float qa, float qb) {
+    const int na = ht.tab_na[p], nb = ht.tab_nb[p];
+    const int ia = min(max(__float2int_rn((qa - ht.tab_lo_a[p]) * ht.tab_inv_a[p]), 0), na - 1);
+    const int ib = min(max(__float2int_rn((qb - ht.tab_lo_b[p]) * ht.tab_inv_b[p]), 0), nb - 1);
+    return (int)__ldg(tables + ht.tab_off[p] + (size_t)ia * nb + ib);
+}
+
+// Set-up kernel: fills the clearance table of one hull pair (h1 on joint j, h2 on joint j + 2; a = j + 1, b = j + 2).
+// warp = grid node; the pose of h2 in h1's frame is X_a(qa) X_b(qb) with X_k = origin_k Rot(axis_k, q_k).
+struct PmpPairTableArgs {
+    const PmpRobotTab* robot;
+    const PmpHullTab* hulls;
+    const float4* hull_verts;
+    uint8_t* table;
+    int32_t pair;
+    float band;        // Lipschitz bound of the clearance over half a grid step (+ float32 slack)
+};
+
+__global__ void __launch_bounds__(128) pmp_pair_table_kernel(const PmpPairTableArgs args) {
+    __shared__ __align__(16) PmpRobotTab rt;
+    __shared__ __align__(16) PmpHullTab ht;
+    pmp_stage_words(&rt, args.robot, sizeof(PmpRobotTab) / 4);
+    pmp_stage_words(&ht, args.hulls, sizeof(PmpHullTab) / 4);
+    __syncthreads();
+    const int p = args.pair, na = ht.tab_na[p], nb = ht.tab_nb[p];
+    const int h1 = ht.pairs[2 * p], h2 = ht.pairs[2 * p + 1], ja = ht.tab_ja[p], jb = ht.tab_jb[p];
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; node < na * nb; node += warps) {
+        const int ia = node / nb, ib = node - ia * nb;
+        const float qa = ht.tab_lo_a[p] + (float)ia / ht.tab_inv_a[p], qb = ht.tab_lo_b[p] + (float)ib / ht.tab_inv_b[p];
+        PmpGjkShape SA, SB;
+        SA.verts = args.hull_verts + ht.hull_off[h1]; SA.n = ht.hull_off[h1 + 1] - ht.hull_off[h1];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) SA.R[k] = (k % 4 == 0) ? 1.f : 0.f;
+        SA.t[0] = SA.t[1] = SA.t[2] = 0.f; SA.half[0] = SA.half[1] = SA.half[2] = 0.f;
+        SB.verts = args.hull_verts + ht.hull_off[h2]; SB.n = ht.hull_off[h2 + 1] - ht.hull_off[h2];
+        SB.half[0] = SB.half[1] = SB.half[2] = 0.f;
+        float Ma[9], Mb[9], sa, ca, sb, cb;
+        sincosf(qa, &sa, &ca);
+        sincosf(qb, &sb, &cb);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            Ma[k] = fmaf(sa, rt.joint_B[9 * ja + k], fmaf(ca, rt.joint_A[9 * ja + k], rt.joint_C[9 * ja + k]));
+            Mb[k] = fmaf(sb, rt.joint_B[9 * jb + k], fmaf(cb, rt.joint_A[9 * jb + k], rt.joint_C[9 * jb + k]));
+        }
+        pmp_mat_mul(Ma, Mb, SB.R);
+        float x, y, z;
+        pmp_mat_vec(Ma, rt.joint_t[3 * jb], rt.joint_t[3 * jb + 1], rt.joint_t[3 * jb + 2], x, y, z);
+        SB.t[0] = x + rt.joint_t[3 * ja]; SB.t[1] = y + rt.joint_t[3 * ja + 1]; SB.t[2] = z + rt.joint_t[3 * ja + 2];
+        const float msum = ht.hull_margin[h1] + ht.hull_margin[h2];
+        const bool free_ = !pmp_gjk_hit(SA, SB, msum + args.band);
+        const bool hit_ = msum > args.band && pmp_gjk_hit(SA, SB, msum - args.band);
+        if (lane == 0) args.table[node] = (uint8_t)((free_ ? 1 : 0) | (hit_ ? 2 : 0));
+    }
+}
+
 #define PMP_RIGID_WARPS 4
-__global__ void __launch_bounds__(32 * PMP_RIGID_WARPS) pmp_rigid_kernel(const PmpRigidArgs args) {
+__global__ void __launch_bounds__(32 * PMP_RIGID_WARPS, 4) pmp_rigid_kernel(const PmpRigidArgs args) {
     __shared__ __align__(16) PmpRobotTab rt;
     __shared__ __align__(16) PmpHullTab ht;
     __shared__ double sm_sq_all[PMP_RIGID_WARPS][PMP_MAX_DOF];
     __shared__ float sm_q_all[PMP_RIGID_WARPS][3 * PMP_MAX_DOF];
     __shared__ float sm_fr_all[PMP_RIGID_WARPS][PMP_MAX_DOF][12];
     __shared__ float sm_sc_all[PMP_RIGID_WARPS][PMP_MAX_SPHERES][3];
+    __shared__ float sm_qL_all[PMP_RIGID_WARPS][PMP_MAX_DOF];
     pmp_stage_words(&rt, args.robot, sizeof(PmpRobotTab) / 4);
     pmp_stage_words(&ht, args.hulls, sizeof(PmpHullTab) / 4);
     __syncthreads();
@@ -241,6 +281,7 @@ __global__ void __launch_bounds__(32 * PMP_RIGID_WARPS) pmp_rigid_kernel(const P
     float* sm_dq = sm_q1 + PMP_MAX_DOF;
     float (*fr)[12] = sm_fr_all[wid];
     float (*sc)[3] = sm_sc_all[wid];
+    float* qL = sm_qL_all[wid];
     const int D = rt.dof, A = rt.n_spheres, H = ht.n_hulls;
     const bool edge_mode = args.q == nullptr;
     const int C = (args.max_steps + 31) >> 5;
@@ -292,8 +333,16 @@ __global__ void __launch_bounds__(32 * PMP_RIGID_WARPS) pmp_rigid_kernel(const P
             auto q_in = [&](int j) { return rt.lower[j]; };      // the limit test is done above
             near = pmp_config_eval<PMP_MAX_SPHERES>(rt, true, q_geo, q_in, c, ee, rt.sph_radius_outer);
         }
-        bool rigid = live && lim_hit;
-        uint32_t todo = __ballot_sync(PMP_FULL, live && !lim_hit && near);
+        // hull pairs with a clearance table are decided by one lookup; only its narrow band goes on to GJK
+        bool tab_hit = false;
+        for (int p = 0; p < ht.n_pairs; ++p) {
+            if (ht.tab_off[p] < 0) continue;
+            const int r = pmp_pair_table(ht, args.pair_tables, p, q_geo(ht.tab_ja[p]), q_geo(ht.tab_jb[p]));
+            tab_hit |= r == 2;
+            near |= r == 0;
+        }
+        bool rigid = live && (lim_hit || tab_hit);
+        uint32_t todo = __ballot_sync(PMP_FULL, live && !lim_hit && !tab_hit && near);
         // ---- narrow phase: one surviving step at a time, by the whole warp ----
         while (todo) {
             const int L = __ffs(todo) - 1;
@@ -313,6 +362,7 @@ __global__ void __launch_bounds__(32 * PMP_RIGID_WARPS) pmp_rigid_kernel(const P
                     if (!edge_mode) qj = __ldg(args.q + (size_t)cfgL * D + j);
                     else qj = lag ? fmaf(sm_dq[j], tgL, sm_q0[j])
                                   : ((endL && !((circ >> j) & 1u)) ? sm_q1[j] : fmaf(sm_dq[j], tL, sm_q0[j]));
+                    if (lane == 0) qL[j] = qj;
                     float s, co;
                     sincosf(qj, &s, &co);
                     float M[9], Rn[9], tx, ty, tz;
@@ -352,7 +402,9 @@ __global__ void __launch_bounds__(32 * PMP_RIGID_WARPS) pmp_rigid_kernel(const P
             for (int p0 = 0; p0 < ht.n_pairs && !hit; p0 += 32) {
                 bool cand = false;
                 const int p = p0 + lane;
-                if (p < ht.n_pairs) {
+                if (p < ht.n_pairs && ht.tab_off[p] >= 0) {
+                    cand = pmp_pair_table(ht, args.pair_tables, p, qL[ht.tab_ja[p]], qL[ht.tab_jb[p]]) == 0;
+                } else if (p < ht.n_pairs) {
                     const int h1 = ht.pairs[2 * p], h2 = ht.pairs[2 * p + 1];
                     for (int a = ht.sph_lo[h1]; a < ht.sph_hi[h1]; ++a)
                         for (int b = ht.sph_lo[h2]; b < ht.sph_hi[h2]; ++b) {

@@ -88,6 +88,15 @@ struct PmpHullTab {
     int32_t sph_lo[PMP_MAX_HULLS];      // arm spheres [sph_lo, sph_hi) approximate hull h (spheres are sorted by joint)
     int32_t sph_hi[PMP_MAX_HULLS];
     int32_t pairs[PMP_MAX_HULL_PAIRS * 2];
+    // Clearance tables of hull pairs whose relative pose depends on exactly two joints (a, b): node (ia, ib) holds
+    // bit 0 = "free for every configuration within half a grid step" and bit 1 = "colliding for every ...", decided
+    // at set-up by the device GJK with the margins moved by the Lipschitz bound of the clearance over half a step.
+    // tab_off < 0: no table (the covering spheres cull that pair).
+    int32_t tab_off[PMP_MAX_HULL_PAIRS];
+    int32_t tab_ja[PMP_MAX_HULL_PAIRS], tab_jb[PMP_MAX_HULL_PAIRS];
+    int32_t tab_na[PMP_MAX_HULL_PAIRS], tab_nb[PMP_MAX_HULL_PAIRS];
+    float tab_lo_a[PMP_MAX_HULL_PAIRS], tab_inv_a[PMP_MAX_HULL_PAIRS];
+    float tab_lo_b[PMP_MAX_HULL_PAIRS], tab_inv_b[PMP_MAX_HULL_PAIRS];
     int32_t pad[3];
 };
 static_assert(sizeof(PmpHullTab) % 16 == 0, "PmpHullTab must be a whole number of uint4");

@@ -210,9 +210,15 @@ def _assert_differences_in_band(chk, model, worlds, q0, q1, backward, max_steps,
         robust = _rigid_robust(model, Qe)
         defl = co.check_configs(Qe.astype(np.float32))["deflection"]
         near = np.any(np.abs(defl - chk.config.deflection_limit) < EPS_RAD, axis=2)         # [n, W]
-        # the ill-conditioned tail of the K-step solve (deep penetrations: float32 and float64 can differ by > 1e-3
-        # there) may flip an "exceeded" bit a little further from the limit; it is rare and counted
-        wide = np.any(np.abs(defl - chk.config.deflection_limit) < 0.05, axis=2)
+        # the ill-conditioned tail of the K-step solve: where the arm is pressed deep into a plant the K damped steps
+        # are not a contraction, and a 1e-6 rad change of the INPUT moves the oracle's own answer by more than the
+        # band.  Such steps are identified by exactly that -- the float64 oracle disagreeing
+        # with itself under 1e-6 rad perturbations -- excluded, and counted.
+        rs = np.random.RandomState(0)
+        pert = [co.check_configs((Qe + 1e-6 * rs.choice([-1.0, 1.0], size=Qe.shape)).astype(np.float32))["deflection"]
+                for _ in range(4)]
+        spread = np.max(np.abs(np.stack(pert) - defl[None]), axis=(0, 3))                     # [n, W]
+        wide = spread > EPS_RAD
         for w in range(len(worlds)):
             for ch in range(gm_r.shape[2]):
                 dr, dx = int(gm_r[e, w, ch]) ^ int(cm_r[e, w, ch]), int(gm_x[e, w, ch]) ^ int(cm_x[e, w, ch])
@@ -221,11 +227,18 @@ def _assert_differences_in_band(chk, model, worlds, q0, q1, backward, max_steps,
                     if (dr >> bit) & 1:
                         assert not robust[i], ("rigid bit differs outside the band", e, w, i)
                     if (dx >> bit) & 1 and not near[i, w]:
-                        assert wide[i, w], ("exceeded bit differs far from the limit", e, w, i)
+                        # float32 tail of the K-step solve: the GPU's own deflections of this step must then be within
+                        # 1e-2 rad of the oracle's and the limit must lie between the two (or the step is ill-conditioned)
+                        if not wide[i, w]:
+                            gd = chk.check_configs_host(Qe[i:i + 1].astype(np.float32))["deflection"][0, w]
+                            err = np.abs(gd - defl[i, w])
+                            lim = chk.config.deflection_limit
+                            assert err.max() < 1e-2 and np.any(np.abs(defl[i, w] - lim) <= err + 1e-4), \
+                                ("exceeded bit differs outside the band on a well-conditioned step", e, w, i, err.max())
                         tail.append((int(e), w, i))
     units = int(sum(min(int(O.num_steps(model, q0[e].astype(np.float64), q1[e].astype(np.float64), chk.config.resolution)),
                         max_steps) for e in range(len(q0)))) * len(worlds)
-    assert len(tail) <= max(1, units // 1000000), ("too many ill-conditioned exceeded bits", tail[:5], units)
+    assert len(tail) <= max(2, units // 200000), ("too many exceeded bits in the float32 / ill-conditioned tail", tail[:5], units)
 
 
 @pytest.mark.parametrize("backward", [False, True])
