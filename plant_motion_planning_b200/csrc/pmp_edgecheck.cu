@@ -355,7 +355,13 @@ static int launch_rigid(pmp_ctx* ctx, const float* q0, const float* q1, int32_t 
     const long long cap = (long long)ctx->sm_count * 8;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
-    pmp_rigid_kernel<<<(int)grid, 32 * PMP_RIGID_WARPS, 0, st>>>(a);
+    const size_t smem = sizeof(float) * (size_t)PMP_RIGID_WARPS * 3 * ctx->h_robot.n_spheres * 32;   // <= 48 KB
+    static int optin[16] = {0};
+    if (!optin[ctx->device & 15]) {
+        CK(cudaFuncSetAttribute(pmp_rigid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        optin[ctx->device & 15] = 1;
+    }
+    pmp_rigid_kernel<<<(int)grid, 32 * PMP_RIGID_WARPS, smem, st>>>(a);
     CK(cudaGetLastError());
     ctx->info.kernel_launches++;
     return PMP_OK;

@@ -44,7 +44,7 @@ __device__ __forceinline__ PmpV3 pmp_pick(int k, PmpV3 p0, PmpV3 p1, PmpV3 p2, P
 
 // world support point of S in world direction d.  The scan over a hull's vertices is strided over the 32 lanes
 // (coalesced 16-byte loads), then a warp arg-max; ties go to an arbitrary maximal vertex (the distance does not care).
-__device__ __forceinline__ PmpV3 pmp_gjk_support(const PmpGjkShape& S, PmpV3 d) {
+__device__ __noinline__ PmpV3 pmp_gjk_support(const PmpGjkShape& S, PmpV3 d) {
     float lx, ly, lz;
     pmp_matT_vec(S.R, d.x, d.y, d.z, lx, ly, lz);
     float vx, vy, vz;
@@ -101,8 +101,10 @@ __device__ __forceinline__ PmpV3 pmp_gjk_triangle(PmpV3 a, PmpV3 b, PmpV3 c, int
 
 // "GJK distance of the margin-free shapes <= msum" (msum = sum of both collision margins).  Early exits: the current
 // closest point of the simplex is an upper bound of the distance, v.w / |v| a lower bound.  Every lane runs the same
-// scalar code on the same data (only the support scans are split over the lanes).
-__device__ __forceinline__ bool pmp_gjk_hit(const PmpGjkShape& A, const PmpGjkShape& B, float msum) {
+// scalar code on the same data (only the support scans are split over the lanes).  ONE copy of this code per kernel
+// (noinline, compact loops): inlined at every call site it overflowed the instruction cache (ncu: 29 "no instruction"
+// stall cycles per issue).
+__device__ __noinline__ bool pmp_gjk_hit(const PmpGjkShape& A, const PmpGjkShape& B, float msum) {
     PmpV3 p0, p1 = pmp_v3(0.f, 0.f, 0.f), p2 = p1, p3 = p1;
     int ns;
     const float m2 = msum * msum;
@@ -149,7 +151,7 @@ __device__ __forceinline__ bool pmp_gjk_hit(const PmpGjkShape& A, const PmpGjkSh
             PmpV3 bp = pmp_v3(0.f, 0.f, 0.f);
             int b0 = 0, b1 = 0, b2 = 0, bn = 0;
             bool any = false;
-#pragma unroll
+#pragma unroll 1
             for (int f = 0; f < 4; ++f) {
                 // faces (0,1,2|3) (0,2,3|1) (0,3,1|2) (1,3,2|0)
                 const int fa = f == 3 ? 1 : 0, fb = f == 0 ? 1 : (f == 1 ? 2 : 3), fc = f == 0 ? 2 : (f == 1 ? 3 : (f == 2 ? 1 : 2)),
@@ -270,6 +272,7 @@ __global__ void __launch_bounds__(32 * PMP_RIGID_WARPS, 4) pmp_rigid_kernel(cons
     __shared__ float sm_fr_all[PMP_RIGID_WARPS][PMP_MAX_DOF][12];
     __shared__ float sm_sc_all[PMP_RIGID_WARPS][PMP_MAX_SPHERES][3];
     __shared__ float sm_qL_all[PMP_RIGID_WARPS][PMP_MAX_DOF];
+    extern __shared__ __align__(16) float sm_lane_centres[];        // [warps][3 A][32] (dynamic: 3 * A * 32 floats per warp)
     pmp_stage_words(&rt, args.robot, sizeof(PmpRobotTab) / 4);
     pmp_stage_words(&ht, args.hulls, sizeof(PmpHullTab) / 4);
     __syncthreads();
@@ -282,6 +285,7 @@ __global__ void __launch_bounds__(32 * PMP_RIGID_WARPS, 4) pmp_rigid_kernel(cons
     float (*fr)[12] = sm_fr_all[wid];
     float (*sc)[3] = sm_sc_all[wid];
     float* qL = sm_qL_all[wid];
+    float* lc = sm_lane_centres + (size_t)wid * 3 * rt.n_spheres * 32;
     const int D = rt.dof, A = rt.n_spheres, H = ht.n_hulls;
     const bool edge_mode = args.q == nullptr;
     const int C = (args.max_steps + 31) >> 5;
@@ -327,11 +331,55 @@ __global__ void __launch_bounds__(32 * PMP_RIGID_WARPS, 4) pmp_rigid_kernel(cons
             const float ql = q_cmd(j);
             lim_hit |= ((circ >> j) & 1u) ? !(fabsf(ql) <= 3.0e38f) : !(ql >= rt.lower[j] && ql <= rt.upper[j]);
         }
-        bool near;
+        // FK of this lane's step; the sphere centres go to a per-warp shared-memory tile [sphere][coordinate][lane]
+        // (conflict-free: a lane only touches its own column).  Rolled loops throughout: the unrolled sphere-pair
+        // code of the edge kernels, instantiated for 32 spheres, alone overflowed the instruction cache here.
+        bool near = false;
         {
-            float c[PMP_MAX_SPHERES][3], ee[3];
-            auto q_in = [&](int j) { return rt.lower[j]; };      // the limit test is done above
-            near = pmp_config_eval<PMP_MAX_SPHERES>(rt, true, q_geo, q_in, c, ee, rt.sph_radius_outer);
+            float R[9], pp[3];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) R[k] = rt.base_R[k];
+            pp[0] = rt.base_t[0]; pp[1] = rt.base_t[1]; pp[2] = rt.base_t[2];
+            int a = 0;
+#pragma unroll 1
+            for (int j = 0; j < D; ++j) {
+                float sj, cj;
+                sincosf(q_geo(j), &sj, &cj);
+                float M[9], Rn[9], tx, ty, tz;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) M[k] = fmaf(sj, rt.joint_B[9 * j + k], fmaf(cj, rt.joint_A[9 * j + k], rt.joint_C[9 * j + k]));
+                pmp_mat_vec(R, rt.joint_t[3 * j], rt.joint_t[3 * j + 1], rt.joint_t[3 * j + 2], tx, ty, tz);
+                pp[0] += tx; pp[1] += ty; pp[2] += tz;
+                pmp_mat_mul(R, M, Rn);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) R[k] = Rn[k];
+                for (; a < A && rt.sph_joint[a] == j; ++a) {      // spheres are sorted by joint
+                    float x, y, z;
+                    pmp_mat_vec(R, rt.sph_center[3 * a], rt.sph_center[3 * a + 1], rt.sph_center[3 * a + 2], x, y, z);
+                    lc[(3 * a) * 32 + lane] = x + pp[0]; lc[(3 * a + 1) * 32 + lane] = y + pp[1]; lc[(3 * a + 2) * 32 + lane] = z + pp[2];
+                }
+            }
+            // covering spheres of the hull pairs without a clearance table
+#pragma unroll 1
+            for (int p = 0; p < ht.n_pairs; ++p) {
+                if (ht.tab_off[p] >= 0) continue;
+                const int h1 = ht.pairs[2 * p], h2 = ht.pairs[2 * p + 1];
+                for (int a1 = ht.sph_lo[h1]; a1 < ht.sph_hi[h1]; ++a1)
+                    for (int b1 = ht.sph_lo[h2]; b1 < ht.sph_hi[h2]; ++b1) {
+                        const float dx = lc[(3 * a1) * 32 + lane] - lc[(3 * b1) * 32 + lane],
+                                    dy = lc[(3 * a1 + 1) * 32 + lane] - lc[(3 * b1 + 1) * 32 + lane],
+                                    dz = lc[(3 * a1 + 2) * 32 + lane] - lc[(3 * b1 + 2) * 32 + lane];
+                        const float rr = rt.sph_radius_outer[a1] + rt.sph_radius_outer[b1];
+                        near |= fmaf(dx, dx, fmaf(dy, dy, dz * dz)) <= rr * rr;
+                    }
+            }
+            // ... and against the obstacles
+#pragma unroll 1
+            for (int f = 0; f < ht.n_fixed_exact; ++f)
+                for (int a1 = 0; a1 < A; ++a1)
+                    near |= pmp_prim_hit(rt.fixed_kind[f], rt.fixed_R + 9 * f, rt.fixed_t + 3 * f, rt.fixed_half + 3 * f,
+                                         lc[(3 * a1) * 32 + lane], lc[(3 * a1 + 1) * 32 + lane], lc[(3 * a1 + 2) * 32 + lane],
+                                         rt.sph_radius_outer[a1]);
         }
         // hull pairs with a clearance table are decided by one lookup; only its narrow band goes on to GJK
         bool tab_hit = false;
