@@ -229,6 +229,13 @@ typedef struct pmp_launch_info {
 } pmp_launch_info;
 int pmp_get_launch_info(pmp_ctx* ctx, pmp_launch_info* out);
 
+/* Per-kernel device timing of pmp_validate_edges (bench.py's roofline leg).  With `on` != 0 every
+ * pmp_validate_edges call records CUDA events on ITS stream around the hull pre-pass and around the edge kernel;
+ * pmp_get_kernel_times waits for the last timed call and returns both durations in milliseconds (0 for a kernel
+ * that did not run).  Off by default: four event records per call are not free on the scalar adapter path. */
+int pmp_set_kernel_timing(pmp_ctx* ctx, int32_t on);
+int pmp_get_kernel_times(pmp_ctx* ctx, float* rigid_ms, float* edge_ms);
+
 /* FP32 FMA-pipe micro-benchmark (dependent FMA chains, 8 independent chains per thread) used as the
  * measured roofline denominator: returns achieved TFLOP/s in *tflops and the kernel time in *ms. */
 int pmp_measure_fp32_peak(pmp_ctx* ctx, int32_t repeats, double* tflops, double* ms);

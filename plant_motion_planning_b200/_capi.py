@@ -69,6 +69,7 @@ EXPORTS = [
     "pmp_create", "pmp_destroy", "pmp_last_error", "pmp_set_robot", "pmp_set_robot_hulls", "pmp_set_worlds", "pmp_set_params",
     "pmp_num_worlds", "pmp_max_stems", "pmp_fk", "pmp_check_configs", "pmp_validate_edges",
     "pmp_validate_edges_host", "pmp_check_configs_host", "pmp_get_launch_info", "pmp_measure_fp32_peak",
+    "pmp_set_kernel_timing", "pmp_get_kernel_times",
     "pmp_nearest", "pmp_edge_points", "pmp_tree_extend",
 ]
 
@@ -118,6 +119,8 @@ def load() -> C.CDLL:
     lib.pmp_nearest.argtypes = [vp, vp, C.c_int32, vp, vp, C.c_int32, vp, vp, vp, vp]
     lib.pmp_edge_points.argtypes = [vp, vp, vp, C.c_int32, vp, C.c_int32, vp, vp]
     lib.pmp_tree_extend.argtypes = [vp, C.POINTER(Tree), C.c_int32, vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp]
+    lib.pmp_set_kernel_timing.argtypes = [vp, C.c_int32]
+    lib.pmp_get_kernel_times.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     for name in EXPORTS:
         if name != "pmp_last_error":
             getattr(lib, name).restype = C.c_int

@@ -53,6 +53,9 @@ struct pmp_ctx {
     unsigned work_slot = 0;
     void* d_tree_scratch = nullptr;
     size_t tree_scratch_bytes = 0;
+    // per-kernel timing (pmp_set_kernel_timing): events around the hull pre-pass [0, 1] and the edge kernel [2, 3]
+    bool timing = false, timed_rigid = false, timed_edge = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 static std::string g_create_err;
@@ -117,6 +120,7 @@ extern "C" int pmp_destroy(pmp_ctx* ctx) {
     cudaFree(ctx->d_hulls); cudaFree(ctx->d_hull_verts); cudaFree(ctx->d_rigid_scratch); cudaFree(ctx->d_pair_tables);
     cudaFree(ctx->d_robot); cudaFree(ctx->d_links); cudaFree(ctx->d_scratch); cudaFree(ctx->d_tree_scratch); cudaFree(ctx->d_work_counter);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     delete ctx;
@@ -473,7 +477,7 @@ extern "C" int pmp_fk(pmp_ctx* ctx, const float* q_dev, int32_t B, float* pos, f
 // ---- kernel selection (instantiations live in pmp_inst_a*.cu) ---------------------------------------
 static void pads(pmp_ctx* ctx, int& apad, int& nspad) {
     const int A = ctx->h_robot.n_spheres;
-    apad = A <= 12 ? 12 : (A <= 16 ? 16 : (A <= 20 ? 20 : 32));
+    apad = A <= 12 ? 12 : (A <= 16 ? 16 : (A <= 18 ? 18 : (A <= 20 ? 20 : 32)));
     nspad = ctx->n_slots <= 1 ? 1 : (ctx->n_slots <= 2 ? 2 : 4);
 }
 
@@ -511,9 +515,13 @@ static int validate_edges_impl(pmp_ctx* ctx, const float* q0, const float* q1, i
             if (rc) return rc;
             pre = (uint32_t*)ctx->d_rigid_scratch;
         }
+        if (ctx->timing) CK(cudaEventRecord(ctx->ev[0], (cudaStream_t)stream));
         rc = launch_rigid(ctx, q0, q1, E, max_steps, backward, pre, nullptr, 0, nullptr, (cudaStream_t)stream);
         if (rc) return rc;
+        if (ctx->timing) { CK(cudaEventRecord(ctx->ev[1], (cudaStream_t)stream)); ctx->timed_rigid = true; }
         a.rigid_pre = pre;
+    } else {
+        ctx->timed_rigid = false;
     }
     a.robot = ctx->d_robot; a.stems = ctx->d_stems; a.n_stems = ctx->d_nstems; a.boxes = ctx->d_boxes;
     a.n_boxes = ctx->d_nboxes; a.prm = ctx->prm; a.q0 = q0; a.q1 = q1; a.E = E; a.max_steps = max_steps;
@@ -572,19 +580,23 @@ static int validate_edges_impl(pmp_ctx* ctx, const float* q0, const float* q1, i
     cudaError_t err;
     int regs = 0;
     cudaStream_t st_ = (cudaStream_t)stream;
+    if (ctx->timing) CK(cudaEventRecord(ctx->ev[2], st_));
     if (first_only) {
         if (apad == 12) err = pmp_launch_edge_first_a12(nspad, a, wsmem, grid, block, smem, st_, &regs);
         else if (apad == 16) err = pmp_launch_edge_first_a16(nspad, a, wsmem, grid, block, smem, st_, &regs);
+        else if (apad == 18) err = pmp_launch_edge_first_a18(nspad, a, wsmem, grid, block, smem, st_, &regs);
         else if (apad == 20) err = pmp_launch_edge_first_a20(nspad, a, wsmem, grid, block, smem, st_, &regs);
         else err = pmp_launch_edge_first_a32(nspad, a, wsmem, grid, block, smem, st_, &regs);
     } else {
         if (apad == 12) err = pmp_launch_edge_a12(nspad, a, wsmem, grid, block, smem, st_, &regs);
         else if (apad == 16) err = pmp_launch_edge_a16(nspad, a, wsmem, grid, block, smem, st_, &regs);
+        else if (apad == 18) err = pmp_launch_edge_a18(nspad, a, wsmem, grid, block, smem, st_, &regs);
         else if (apad == 20) err = pmp_launch_edge_a20(nspad, a, wsmem, grid, block, smem, st_, &regs);
         else err = pmp_launch_edge_a32(nspad, a, wsmem, grid, block, smem, st_, &regs);
     }
     ctx->info.regs_per_thread = regs;
     if (err != cudaSuccess) return fail(ctx, PMP_E_CUDA, std::string("edge kernel launch: ") + cudaGetErrorString(err));
+    if (ctx->timing) { CK(cudaEventRecord(ctx->ev[3], st_)); ctx->timed_edge = true; }
     ctx->info.grid = grid; ctx->info.block = block; ctx->info.smem_bytes = (int)smem;
     ctx->info.worlds_in_smem = wsmem ? 1 : 0; ctx->info.n_sphere_pad = apad; ctx->info.n_slot_pad = nspad;
     ctx->info.kernel_launches++;
@@ -627,6 +639,7 @@ extern "C" int pmp_check_configs(pmp_ctx* ctx, const float* q, int32_t B, uint8_
     int regs = 0;
     if (apad == 12) err = pmp_launch_config_a12(nspad, a, grid, block, smem, (cudaStream_t)stream, &regs);
     else if (apad == 16) err = pmp_launch_config_a16(nspad, a, grid, block, smem, (cudaStream_t)stream, &regs);
+    else if (apad == 18) err = pmp_launch_config_a18(nspad, a, grid, block, smem, (cudaStream_t)stream, &regs);
     else if (apad == 20) err = pmp_launch_config_a20(nspad, a, grid, block, smem, (cudaStream_t)stream, &regs);
     else err = pmp_launch_config_a32(nspad, a, grid, block, smem, (cudaStream_t)stream, &regs);
     ctx->info.regs_per_thread = regs;
@@ -788,6 +801,28 @@ extern "C" int pmp_check_configs_host(pmp_ctx* ctx, const float* q, int32_t B, u
 extern "C" int pmp_get_launch_info(pmp_ctx* ctx, pmp_launch_info* out) {
     if (!ctx || !out) return PMP_E_INVALID;
     *out = ctx->info;
+    return PMP_OK;
+}
+
+extern "C" int pmp_set_kernel_timing(pmp_ctx* ctx, int32_t on) {
+    if (!ctx) return PMP_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (on)
+        for (int i = 0; i < 4; ++i)
+            if (!ctx->ev[i]) CK(cudaEventCreate(&ctx->ev[i]));
+    ctx->timing = on != 0;
+    ctx->timed_rigid = ctx->timed_edge = false;
+    return PMP_OK;
+}
+
+extern "C" int pmp_get_kernel_times(pmp_ctx* ctx, float* rigid_ms, float* edge_ms) {
+    if (!ctx || !rigid_ms || !edge_ms) return fail(ctx, PMP_E_INVALID, "null argument");
+    *rigid_ms = 0.f; *edge_ms = 0.f;
+    if (!ctx->timing || !ctx->timed_edge) return fail(ctx, PMP_E_STATE, "no timed pmp_validate_edges call yet");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(ctx->ev[3]));
+    CK(cudaEventElapsedTime(edge_ms, ctx->ev[2], ctx->ev[3]));
+    if (ctx->timed_rigid) CK(cudaEventElapsedTime(rigid_ms, ctx->ev[0], ctx->ev[1]));
     return PMP_OK;
 }
 

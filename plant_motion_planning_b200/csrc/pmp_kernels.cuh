@@ -88,10 +88,38 @@ __device__ __forceinline__ pmp_f2 pmp_sub2(pmp_f2 a, pmp_f2 b) {
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+// -v: scalar negations of the two halves, which ptxas folds into the consuming FFMA2 / FMUL2 / FADD2 as operand
+// modifiers (0 - v through sub.f32x2 is NOT folded: it is a different value for v = +0 and costs an FADD2).
+__device__ __forceinline__ pmp_f2 pmp_neg2(pmp_f2 v) {
+    float lo, hi;
+    pmp_upk(v, lo, hi);
+    return pmp_pk(-lo, -hi);
+}
 __device__ __forceinline__ float pmp_hsum2(pmp_f2 v) {
     float lo, hi;
     pmp_upk(v, lo, hi);
     return lo + hi;
+}
+
+// atan2 for the observers: octant reduction + odd minimax polynomial of degree 15 (|error| < 1.7e-7 rad evaluated in
+// float32, the accuracy of libdevice's atan2f, in a third of its instructions and without its divergent slow paths).
+__device__ __forceinline__ float pmp_atan2_fast(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float t = mn * pmp_rcp_ftz(fmaxf(mx, 1e-30f));
+    const float s = t * t;
+    float p = -0.0046687733f;
+    p = fmaf(p, s, 0.0241661895f);
+    p = fmaf(p, s, -0.0593671008f);
+    p = fmaf(p, s, 0.0990609690f);
+    p = fmaf(p, s, -0.1401658504f);
+    p = fmaf(p, s, 0.1996923539f);
+    p = fmaf(p, s, -0.3333195972f);
+    p = fmaf(p, s, 0.9999998978f);
+    float r = p * t;
+    if (ay > ax) r = 1.57079632679f - r;
+    if (x < 0.f) r = 3.14159265359f - r;
+    return copysignf(r, y);
 }
 
 // Sphere centres as pairs: cp[i][k] = (c[2i][k], c[2i+1][k]).
@@ -259,11 +287,55 @@ __device__ __forceinline__ void pmp_rxry(float sx, float cx, float sy, float cy,
     M[6] = -cx * sy; M[7] = sx;  M[8] = cx * cy;
 }
 
+// Register-resident centres (configuration kernel).
+template <int A>
+struct PmpCentresReg {
+    pmp_f2 cp[A / 2][3];
+    __device__ __forceinline__ pmp_f2 operator()(int pair, int k) const { return cp[pair][k]; }
+    __device__ __forceinline__ void prep(float, const PmpRobotTab&) {}
+    // -(r_a + margin) of the pair's two spheres
+    __device__ __forceinline__ pmp_f2 nrr(int pair, float mg, const PmpRobotTab& rt) const {
+        return pmp_sub2(pmp_bc(-mg), *reinterpret_cast<const pmp_f2*>(&rt.sph_radius[2 * pair]));
+    }
+};
+// Centres in the edge kernel's per-warp shared-memory tile (rows of 66 floats: 32 steps x 2 spheres + 2 spare floats).
+// The spare pair of row (pair, 0) holds -(r_a + margin) of the pair for the margin last seen (stems of one world set
+// share one margin in practice), which takes an FADD2 per pair out of the innermost loop.
+// (volatile loads: the compiler would otherwise hoist all 3 A / 2 loads out of the world loop and keep the centres in
+// registers after all, which is exactly the pressure this layout is meant to remove)
+struct PmpCentresTile {
+    uint32_t my_tile;      // shared-space address of this lane's column
+    uint32_t warp_tile;    // shared-space address of the warp's tile
+    int lane, n_pairs;
+    float cached_mg;
+    __device__ __forceinline__ pmp_f2 operator()(int pair, int k) const {
+        pmp_f2 v;
+        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(my_tile + (uint32_t)((pair * 3 + k) * 66 * 4)));
+        return v;
+    }
+    __device__ __forceinline__ void prep(float mg, const PmpRobotTab& rt) {
+        if (mg != cached_mg) {          // warp-uniform
+            __syncwarp();
+            if (lane < n_pairs) {
+                const pmp_f2 v = pmp_sub2(pmp_bc(-mg), *reinterpret_cast<const pmp_f2*>(&rt.sph_radius[2 * lane]));
+                asm volatile("st.shared.b64 [%0], %1;" :: "r"(warp_tile + (uint32_t)(lane * 3 * 66 * 4 + 256)), "l"(v) : "memory");
+            }
+            __syncwarp();
+            cached_mg = mg;
+        }
+    }
+    __device__ __forceinline__ pmp_f2 nrr(int pair, float, const PmpRobotTab&) const {
+        pmp_f2 v;
+        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(warp_tile + (uint32_t)(pair * 3 * 66 * 4 + 256)));
+        return v;
+    }
+};
+
 template <int A, int NSLOT, bool DETAIL, bool CULL, class CPF>
 __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ wt, int n_stems,
                                                       const float* __restrict__ boxes, int n_boxes,
                                                       const PmpRobotTab& rt, const PmpKernelParams& prm,
-                                                      CPF cpf, float* __restrict__ defl_out,
+                                                      CPF& cpf, float* __restrict__ defl_out,
                                                       float* __restrict__ theta_out,
                                                       const PmpSweptBound bound = PmpSweptBound{0.f, 0.f, 0.f, -1.f}) {
     PmpUnitOut out;
@@ -403,6 +475,7 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
         } else if (dense || __any_sync(PMP_FULL, touch)) {
             // ---- phase 2: K damped Gauss-Newton steps (oracle plant_equilibrium) ----
             if (!have_sc) { __sincosf(th0x, &s0x, &c0x); __sincosf(th0y, &s0y, &c0y); }
+            cpf.prep(mg, rt);
             {
                 // the joint frame before the stem's own rotation: Rv = Rs M(th0)^T
                 float M0[9];
@@ -440,14 +513,13 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
                     const pmp_f2 inv = pmp_pk(pmp_rsqrt_ftz(e0), pmp_rsqrt_ftz(e1));
                     // d2 * inv - (r_a + margin) = -(penetration)
                     float n0, n1;
-                    const pmp_f2 nrr = pmp_sub2(pmp_bc(-mg), *reinterpret_cast<const pmp_f2*>(&rt.sph_radius[a]));
-                    pmp_upk(pmp_fma2(d2, inv, nrr), n0, n1);
+                    pmp_upk(pmp_fma2(d2, inv, cpf.nrr(a >> 1, mg, rt)), n0, n1);
                     const pmp_f2 pen = pmp_pk(fmaxf(-n0, 0.f), fmaxf(-n1, 0.f));
                     // m = d x pf,  pf = p + zc e_z
                     const pmp_f2 pfz = pmp_add2(pz, pmp_bc(zc));
-                    const pmp_f2 mx = pmp_fma2(dy, pfz, pmp_mul2(pmp_sub2(pmp_bc(0.f), dz), py));
-                    const pmp_f2 my = pmp_fma2(dz, px, pmp_mul2(pmp_sub2(pmp_bc(0.f), dx), pfz));
-                    const pmp_f2 mz = pmp_fma2(dx, py, pmp_mul2(pmp_sub2(pmp_bc(0.f), dy), px));
+                    const pmp_f2 mx = pmp_fma2(dy, pfz, pmp_mul2(pmp_neg2(dz), py));
+                    const pmp_f2 my = pmp_fma2(dz, px, pmp_mul2(pmp_neg2(dx), pfz));
+                    const pmp_f2 mz = pmp_fma2(dx, py, pmp_mul2(pmp_neg2(dy), px));
                     const pmp_f2 Jx = pmp_mul2(inv, pmp_fma2(pmp_bc(cy), mx, pmp_mul2(pmp_bc(sy), mz)));
                     const pmp_f2 Jy = pmp_mul2(inv, my);
                     const pmp_f2 pJx = pmp_mul2(pen, Jx), pJy = pmp_mul2(pen, Jy);
@@ -513,7 +585,7 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
                 const float kx = vy * oz - vz * oy, ky = vz * ox - vx * oz, kz = vx * oy - vy * ox;
                 const float sn = sqrtf(fmaf(kx, kx, fmaf(ky, ky, kz * kz)));
                 const float cs = fmaf(vx, ox, fmaf(vy, oy, vz * oz));
-                val = atan2f(sn, cs);     // == acos(cos) of the reference, well conditioned near 0
+                val = pmp_atan2_fast(sn, cs);     // == acos(cos) of the reference, well conditioned near 0
             } else {
                 float vx, vy, vz;
                 if (flags & PMP_SF_OBS_ROOT) {
@@ -552,7 +624,11 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
                 float roll, pitch;
                 if (sarg <= -0.99999f) { roll = 0.f; pitch = -1.57079632679f; }
                 else if (sarg >= 0.99999f) { roll = 0.f; pitch = 1.57079632679f; }
-                else { roll = atan2f(vy, vz); pitch = asinf(sarg); }
+                else {
+                    // asin(sarg) = atan2(sarg, sqrt(1 - sarg^2)); (vx, vy, vz) is a row of a rotation matrix
+                    roll = pmp_atan2_fast(vy, vz);
+                    pitch = pmp_atan2_fast(sarg, sqrtf(fmaf(vy, vy, vz * vz)));
+                }
                 val = sqrtf(fmaf(roll, roll, pitch * pitch));
             }
             if (moved) raw = val;   // untouched chain: exactly the rest pose
@@ -772,7 +848,11 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
             // so that this once-per-chunk step costs no registers in the world loop below.
             PmpSweptBound bound{0.f, 0.f, 0.f, -1.f};
             {
-                constexpr int L = (A <= 16) ? 16 : 32;           // lanes per group (>= A)
+                // 32 lanes carry 32 (sphere, step group) balls.  A <= 16: every sphere gets two groups of 16 steps.
+                // 16 < A <= 32: the first N1 = 2A - 32 spheres (the ones nearest the base, which sweep the least)
+                // get one 32-step ball, the other 32 - A spheres two 16-step balls -- a 16-step ball is about half
+                // as wide, and what the cull lets through pays the full contact test.
+                constexpr int N1 = (A <= 16) ? 0 : 2 * A - 32, N2 = (A <= 16) ? 16 : 32 - A;
                 __syncwarp();
 #pragma unroll
                 for (int a = 0; a < A; ++a) {
@@ -781,11 +861,15 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
                     sm_tile[PMP_TILE_AT(a, 2, lane)] = c[a][2];
                 }
                 __syncwarp();
-                const int la = lane & (L - 1), g0 = lane & ~(L - 1);
+                int la, g0, span;
+                if (A <= 16) { la = lane & 15; g0 = lane & 16; span = 16; }
+                else if (lane < N1) { la = lane; g0 = 0; span = 32; }
+                else if (lane < N1 + N2) { la = lane; g0 = 0; span = 16; }
+                else { la = lane - N2; g0 = 16; span = 16; }
                 const int n_live = nc - base;                      // live lanes are the prefix [0, n_live)
                 if (la < rt.n_spheres && g0 < n_live) {
                     float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-                    const int jn = min(L, n_live - g0);
+                    const int jn = min(span, n_live - g0);
                     for (int j = 0; j < jn; ++j) {
 #pragma unroll
                         for (int k = 0; k < 3; ++k) {
@@ -822,14 +906,11 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
             // reference's loops do (primitives.py:225-241, env.py:230-238): steps after the first violating one are
             // retired, and the remaining worlds are skipped once step 0 of the chunk violates.
             // the world loop reads the centres back from the tile, two spheres per 64-bit load
-            // (volatile: the compiler would otherwise hoist all 3 A / 2 loads out of the world loop and keep the
-            // centres in registers after all, which is exactly the pressure this layout is meant to remove)
-            const uint32_t my_tile = (uint32_t)__cvta_generic_to_shared(sm_tile + 2 * lane);
-            auto cpf = [my_tile](int pair, int k) {
-                pmp_f2 v;
-                asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(my_tile + (uint32_t)((pair * 3 + k) * 66 * 4)));
-                return v;
-            };
+            PmpCentresTile cpf;
+            cpf.warp_tile = (uint32_t)__cvta_generic_to_shared(sm_tile);
+            cpf.my_tile = cpf.warp_tile + 8u * (uint32_t)lane;
+            cpf.lane = lane; cpf.n_pairs = A / 2;
+            cpf.cached_mg = __int_as_float(0x7fc00000);     // NaN: the first solved stem writes the -(r + margin) slots
             int retired_from = 32;
             auto retire = [&](uint32_t v) {
                 const int L = __ffs(v) - 1;
@@ -951,9 +1032,8 @@ __global__ void __launch_bounds__(128, 2) pmp_config_kernel(const PmpConfigArgs 
 #pragma unroll
         for (int a = 0; a < A; ++a) { c[a][0] = PMP_FAR; c[a][1] = PMP_FAR; c[a][2] = PMP_FAR; }
     }
-    pmp_f2 cp[A / 2][3];
-    pmp_pack_centres<A>(c, cp);
-    auto cpf = [&cp](int pair, int k) { return cp[pair][k]; };
+    PmpCentresReg<A> cpf;
+    pmp_pack_centres<A>(c, cpf.cp);
     if (live && args.ee && blockIdx.y == 0) { args.ee[3 * b] = ee[0]; args.ee[3 * b + 1] = ee[1]; args.ee[3 * b + 2] = ee[2]; }
     // worlds are spread over blockIdx.y so that small batches (the scalar collision_fn adapter: B = 1..50) use many
     // SMs instead of one thread walking all W worlds; the arm FK above is simply recomputed per world chunk

@@ -14,5 +14,6 @@
 
 PMP_DECLARE_LAUNCHERS(12)
 PMP_DECLARE_LAUNCHERS(16)
+PMP_DECLARE_LAUNCHERS(18)
 PMP_DECLARE_LAUNCHERS(20)
 PMP_DECLARE_LAUNCHERS(32)

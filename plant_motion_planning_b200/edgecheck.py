@@ -194,6 +194,16 @@ class EdgeChecker:
         self._check(self._lib.pmp_get_launch_info(self._ctx, C.byref(info)), "pmp_get_launch_info")
         return {k: int(getattr(info, k)) for k, _ in info._fields_}
 
+    def set_kernel_timing(self, on: bool) -> None:
+        """Record CUDA events around the kernels of every validate_edges call (bench.py's roofline leg)."""
+        self._check(self._lib.pmp_set_kernel_timing(self._ctx, 1 if on else 0), "pmp_set_kernel_timing")
+
+    def kernel_times(self):
+        """(hull pre-pass ms, edge kernel ms) of the last timed validate_edges call; waits for it."""
+        r, e = C.c_float(), C.c_float()
+        self._check(self._lib.pmp_get_kernel_times(self._ctx, C.byref(r), C.byref(e)), "pmp_get_kernel_times")
+        return r.value, e.value
+
     def measure_fp32_peak(self, repeats: int = 5):
         tf, ms = C.c_double(), C.c_double()
         self._check(self._lib.pmp_measure_fp32_peak(self._ctx, repeats, C.byref(tf), C.byref(ms)),

@@ -54,7 +54,7 @@ def test_gpu_parity_at_the_caps(big):
     chk = EdgeChecker(m, worlds, EdgeCheckConfig())
     g = chk.check_configs(torch.from_numpy(Q))
     info = chk.launch_info()
-    assert info["n_sphere_pad"] == 20 and info["n_slot_pad"] == 4      # 18 spheres: the A = 20 instantiation
+    assert info["n_sphere_pad"] == 18 and info["n_slot_pad"] == 4      # 18 spheres: the A = 18 instantiation
     c = COracle(m, worlds).check_configs(Q)
     fl = g.flags.cpu().numpy()
     Qd = Q.astype(np.float64)
