@@ -105,6 +105,10 @@ typedef struct pmp_hull_desc {
     float fixed_margin;            /* collision margin carved out of the static boxes (btBoxShape: 0.001) */
     int32_t n_fixed_exact;         /* the first n_fixed_exact static primitives (boxes / spheres) are obstacles
                                       tested against every hull (product(moving links, fixed), utils.py:4008-4014) */
+    const float* sph_radius_inner; /* [n_spheres] or NULL: radius of the ball around sphere a's centre that lies INSIDE
+                                      hull (+) margin (depth of the centre in the hull + margin; 0 = unknown).  Two
+                                      such balls overlapping, or one reaching an obstacle, decide "colliding" in the
+                                      broad phase without GJK -- exact, the balls are subsets of the shapes */
 } pmp_hull_desc;
 
 /* Sampled plant worlds (copied by pmp_set_worlds).  Replaces the per-world Bullet bodies created by

@@ -54,6 +54,7 @@ class HullDesc(C.Structure):
         ("n_hulls", C.c_int32), ("hull_joint", c_int32_p), ("hull_off", c_int32_p), ("hull_verts", c_float_p),
         ("hull_margin", c_float_p), ("n_pairs", C.c_int32), ("pairs", c_int32_p), ("sph_hull", c_int32_p),
         ("sph_radius_outer", c_float_p), ("fixed_margin", C.c_float), ("n_fixed_exact", C.c_int32),
+        ("sph_radius_inner", c_float_p),
     ]
 
 
@@ -183,6 +184,9 @@ def hull_desc(hulls, n_fixed_exact: int):
         "sph_hull": np.ascontiguousarray(hulls.sph_hull, dtype=np.int32),
         "outer": np.ascontiguousarray(hulls.sph_radius_outer, dtype=np.float32),
     }
+    inner = getattr(hulls, "sph_radius_inner", None)
+    if inner is not None:
+        keep["inner"] = np.ascontiguousarray(inner, dtype=np.float32)
     d = HullDesc()
     d.n_hulls = H
     d.hull_joint, d.hull_off, d.hull_verts = iptr(keep["joint"]), iptr(keep["off"]), fptr(keep["verts"])
@@ -191,4 +195,5 @@ def hull_desc(hulls, n_fixed_exact: int):
     d.pairs, d.sph_hull, d.sph_radius_outer = iptr(keep["pairs"]), iptr(keep["sph_hull"]), fptr(keep["outer"])
     d.fixed_margin = float(hulls.fixed_margin)
     d.n_fixed_exact = int(n_fixed_exact)
+    d.sph_radius_inner = fptr(keep["inner"]) if "inner" in keep else None
     return d, keep

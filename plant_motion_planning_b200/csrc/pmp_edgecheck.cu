@@ -204,7 +204,7 @@ extern "C" int pmp_set_robot_hulls(pmp_ctx* ctx, const pmp_hull_desc* h) {
     memcpy(t.self_mask, ctx->self_mask_spheres, sizeof(t.self_mask));
     if (!h || h->n_hulls == 0) {
         t.has_hulls = 0;
-        for (int a = 0; a < A; ++a) t.sph_radius_outer[a] = t.sph_radius[a];
+        for (int a = 0; a < A; ++a) { t.sph_radius_outer[a] = t.sph_radius[a]; t.sph_radius_inner[a] = 0.f; }
         CK(cudaMemcpy(ctx->d_robot, &t, sizeof(t), cudaMemcpyHostToDevice));
         ctx->h_robot = t;
         ctx->has_hulls = false;
@@ -256,6 +256,13 @@ extern "C" int pmp_set_robot_hulls(pmp_ctx* ctx, const pmp_hull_desc* h) {
         if (h->sph_hull[a] < -1 || h->sph_hull[a] >= H) return fail(ctx, PMP_E_INVALID, "sph_hull out of range");
         if (!(h->sph_radius_outer[a] >= t.sph_radius[a])) return fail(ctx, PMP_E_INVALID, "sph_radius_outer must be >= sph_radius");
         t.sph_radius_outer[a] = h->sph_radius_outer[a];
+        t.sph_radius_inner[a] = 0.f;
+        if (h->sph_radius_inner && h->sph_hull[a] >= 0) {
+            const float ri = h->sph_radius_inner[a];
+            if (!(ri >= 0.f) || ri > h->sph_radius_outer[a]) return fail(ctx, PMP_E_INVALID, "sph_radius_inner must be in [0, sph_radius_outer]");
+            // 2e-6 m inside the true ball: float32 rounding of the posed centres never turns a miss into a hit
+            t.sph_radius_inner[a] = ri > 2.0e-6f ? ri - 2.0e-6f : 0.f;
+        }
     }
     std::vector<float4> verts((size_t)NV);
     for (int i = 0; i < NV; ++i) verts[i] = make_float4(h->hull_verts[3 * i], h->hull_verts[3 * i + 1], h->hull_verts[3 * i + 2], 0.f);
@@ -803,6 +810,15 @@ extern "C" int pmp_get_launch_info(pmp_ctx* ctx, pmp_launch_info* out) {
     *out = ctx->info;
     return PMP_OK;
 }
+
+#ifdef PMP_RIGID_STATS
+// experiment builds only (not declared in the public header): read and clear the narrow-phase counters
+extern "C" int pmp_debug_rigid_stats(unsigned long long* out128) {
+    unsigned long long z[128] = {0};
+    if (cudaMemcpyFromSymbol(out128, pmp_rigid_stats, sizeof(z)) != cudaSuccess) return -1;
+    return cudaMemcpyToSymbol(pmp_rigid_stats, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 extern "C" int pmp_set_kernel_timing(pmp_ctx* ctx, int32_t on) {
     if (!ctx) return PMP_E_INVALID;

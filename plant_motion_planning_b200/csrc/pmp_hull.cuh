@@ -17,6 +17,17 @@
 #pragma once
 #include "pmp_kernels.cuh"
 
+// Experiment builds (-DPMP_RIGID_STATS): counters of the narrow phase, read back with cudaMemcpyFromSymbol.
+//  [0] warp items  [1] steps sent to the narrow phase  [2] GJK calls on hull pairs  [3] GJK calls hull x obstacle
+//  [4] GJK iterations  [5] steps decided by a table hit / limits  [6] narrow-phase steps that end in a hit
+//  [16 + p] GJK calls of self pair p   [48 + f * 8 + h] GJK calls of (obstacle f, hull h)
+#ifdef PMP_RIGID_STATS
+__device__ unsigned long long pmp_rigid_stats[128];
+#define PMP_STAT(i, v) do { const unsigned long long v_ = (unsigned long long)(v); if ((threadIdx.x & 31) == 0) atomicAdd(&pmp_rigid_stats[i], v_); } while (0)
+#else
+#define PMP_STAT(i, v) do { } while (0)
+#endif
+
 struct PmpGjkShape {          // one posed convex shape, identical in every lane (kept in registers)
     const float4* verts;      // hull vertices (x, y, z, -) in the shape frame; nullptr: box / point given by `half`
     int n;
@@ -119,6 +130,7 @@ __device__ __noinline__ bool pmp_gjk_hit(const PmpGjkShape& A, const PmpGjkShape
     ns = 1;
     float vv = pmp_dot(v, v);
     for (int it = 0; it < 48; ++it) {
+        PMP_STAT(4, 1);
         if (vv <= m2) return true;
         const PmpV3 w = pmp_gjk_support(A, pmp_v3(-v.x, -v.y, -v.z)) - pmp_gjk_support(B, v);
         const float vw = pmp_dot(v, w);
@@ -334,7 +346,7 @@ __global__ void __launch_bounds__(32 * PMP_RIGID_WARPS, 4) pmp_rigid_kernel(cons
         // FK of this lane's step; the sphere centres go to a per-warp shared-memory tile [sphere][coordinate][lane]
         // (conflict-free: a lane only touches its own column).  Rolled loops throughout: the unrolled sphere-pair
         // code of the edge kernels, instantiated for 32 spheres, alone overflowed the instruction cache here.
-        bool near = false;
+        bool near = false, sure = false;
         {
             float R[9], pp[3];
 #pragma unroll
@@ -359,7 +371,8 @@ __global__ void __launch_bounds__(32 * PMP_RIGID_WARPS, 4) pmp_rigid_kernel(cons
                     lc[(3 * a) * 32 + lane] = x + pp[0]; lc[(3 * a + 1) * 32 + lane] = y + pp[1]; lc[(3 * a + 2) * 32 + lane] = z + pp[2];
                 }
             }
-            // covering spheres of the hull pairs without a clearance table
+            // covering spheres of the hull pairs without a clearance table; the INSCRIBED balls of the same spheres
+            // (inside hull (+) margin) decide a certain hit right here when two of them overlap
 #pragma unroll 1
             for (int p = 0; p < ht.n_pairs; ++p) {
                 if (ht.tab_off[p] >= 0) continue;
@@ -369,17 +382,29 @@ __global__ void __launch_bounds__(32 * PMP_RIGID_WARPS, 4) pmp_rigid_kernel(cons
                         const float dx = lc[(3 * a1) * 32 + lane] - lc[(3 * b1) * 32 + lane],
                                     dy = lc[(3 * a1 + 1) * 32 + lane] - lc[(3 * b1 + 1) * 32 + lane],
                                     dz = lc[(3 * a1 + 2) * 32 + lane] - lc[(3 * b1 + 2) * 32 + lane];
+                        const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
                         const float rr = rt.sph_radius_outer[a1] + rt.sph_radius_outer[b1];
-                        near |= fmaf(dx, dx, fmaf(dy, dy, dz * dz)) <= rr * rr;
+                        near |= d2 <= rr * rr;
+                        const float ia = rt.sph_radius_inner[a1], ib = rt.sph_radius_inner[b1];
+                        sure |= ia > 0.f && ib > 0.f && d2 <= (ia + ib) * (ia + ib);
                     }
             }
-            // ... and against the obstacles
+            // ... and against the obstacles (Bullet's box = core box (half - margin) (+) margin; sphere = point (+) radius)
 #pragma unroll 1
-            for (int f = 0; f < ht.n_fixed_exact; ++f)
-                for (int a1 = 0; a1 < A; ++a1)
-                    near |= pmp_prim_hit(rt.fixed_kind[f], rt.fixed_R + 9 * f, rt.fixed_t + 3 * f, rt.fixed_half + 3 * f,
-                                         lc[(3 * a1) * 32 + lane], lc[(3 * a1 + 1) * 32 + lane], lc[(3 * a1 + 2) * 32 + lane],
+            for (int f = 0; f < ht.n_fixed_exact; ++f) {
+                const int kind = rt.fixed_kind[f];
+                const float mB = kind == PMP_PRIM_BOX ? ht.fixed_margin : rt.fixed_half[3 * f];
+                float core[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) core[k] = kind == PMP_PRIM_BOX ? fmaxf(rt.fixed_half[3 * f + k] - mB, 0.f) : 0.f;
+                for (int a1 = 0; a1 < A; ++a1) {
+                    const float cx = lc[(3 * a1) * 32 + lane], cy = lc[(3 * a1 + 1) * 32 + lane], cz = lc[(3 * a1 + 2) * 32 + lane];
+                    near |= pmp_prim_hit(kind, rt.fixed_R + 9 * f, rt.fixed_t + 3 * f, rt.fixed_half + 3 * f, cx, cy, cz,
                                          rt.sph_radius_outer[a1]);
+                    const float ia = rt.sph_radius_inner[a1];
+                    sure |= ia > 0.f && pmp_prim_hit(PMP_PRIM_BOX, rt.fixed_R + 9 * f, rt.fixed_t + 3 * f, core, cx, cy, cz, ia + mB);
+                }
+            }
         }
         // hull pairs with a clearance table are decided by one lookup; only its narrow band goes on to GJK
         bool tab_hit = false;
@@ -389,8 +414,9 @@ __global__ void __launch_bounds__(32 * PMP_RIGID_WARPS, 4) pmp_rigid_kernel(cons
             tab_hit |= r == 2;
             near |= r == 0;
         }
-        bool rigid = live && (lim_hit || tab_hit);
-        uint32_t todo = __ballot_sync(PMP_FULL, live && !lim_hit && !tab_hit && near);
+        bool rigid = live && (lim_hit || tab_hit || sure);
+        uint32_t todo = __ballot_sync(PMP_FULL, live && !lim_hit && !tab_hit && !sure && near);
+        PMP_STAT(0, 1); PMP_STAT(1, __popc(todo)); PMP_STAT(5, __popc(__ballot_sync(PMP_FULL, rigid)));
         // ---- narrow phase: one surviving step at a time, by the whole warp ----
         while (todo) {
             const int L = __ffs(todo) - 1;
@@ -469,6 +495,7 @@ __global__ void __launch_bounds__(32 * PMP_RIGID_WARPS, 4) pmp_rigid_kernel(cons
                     PmpGjkShape SA, SB;
                     load_hull(h1, SA);
                     load_hull(h2, SB);
+                    PMP_STAT(2, 1); PMP_STAT(16 + (pp & 31), 1);
                     hit = pmp_gjk_hit(SA, SB, ht.hull_margin[h1] + ht.hull_margin[h2]);
                 }
             }
@@ -503,10 +530,12 @@ __global__ void __launch_bounds__(32 * PMP_RIGID_WARPS, 4) pmp_rigid_kernel(cons
                         mB = rt.fixed_half[3 * f];
                         SB.half[0] = SB.half[1] = SB.half[2] = 0.f;
                     }
+                    PMP_STAT(3, 1); PMP_STAT(48 + ((f * 8 + h) & 63), 1);
                     hit = pmp_gjk_hit(SA, SB, ht.hull_margin[h] + mB);
                 }
             }
             if (lane == L) rigid = hit;
+            PMP_STAT(6, hit ? 1 : 0);
         }
         if (edge_mode) {
             const uint32_t m = __ballot_sync(PMP_FULL, rigid);

@@ -16,6 +16,10 @@
 
 #define PMP_FULL 0xffffffffu
 #define PMP_FAR 1.0e6f
+// Slack (m^2) of the rsqrt-free "can this sphere pair penetrate" test against the solve's own penetration
+// max(r + margin - d2 * rsqrt.approx(d2), 0): covers the 2^-22 relative error of the approximation and the different
+// rounding of the two distance formulas ((r + margin)^2 <= 0.04 m^2, so 1e-6 is > 25 x 2^-22 of it).
+#define PMP_CAND_SLACK 1.0e-6f
 
 // ------------------------------------------------------------------------------------------------
 // small helpers
@@ -445,7 +449,11 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
             have_sc = true;
         }
         // ---- phase 1: does any arm sphere touch the stem in its initial pose?  (exact, no rsqrt / Jacobian) ----
+        // `pairs`: sphere pairs that come within PMP_CAND_SLACK of touching (a superset of the pairs with a positive
+        // penetration in the solve's first iteration, whose distance goes through an approximate rsqrt)
         bool touch = false;
+        uint32_t pairs = 0u;
+        cpf.prep(mg, rt);
         {
             float margin = -1.f;
             const pmp_f2 nbx = pmp_bc(-b[0]), nby = pmp_bc(-b[1]), nbz = pmp_bc(-b[2]);
@@ -461,11 +469,13 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
                 const pmp_f2 ez = pmp_pk(fmaxf(fabsf(r0) - hh, 0.f), fmaxf(fabsf(r1) - hh, 0.f));
                 const pmp_f2 d2 = pmp_fma2(ex, ex, pmp_fma2(ey, ey, pmp_mul2(ez, ez)));
                 // touching <=> (r_a + margin)^2 - d2 > 0; the largest such value over all spheres decides
-                const pmp_f2 rr = pmp_add2(pmp_bc(mg), *reinterpret_cast<const pmp_f2*>(&rt.sph_radius[a]));
-                float m0, m1;
-                pmp_upk(pmp_sub2(pmp_mul2(rr, rr), d2), m0, m1);
                 // (padding spheres sit at PMP_FAR with radius -1e3: (r + mg)^2 = 1e6 against d2 = 3e12)
-                margin = fmaxf(fmaxf(margin, m0), m1);
+                const pmp_f2 nrr = cpf.nrr(a >> 1, mg, rt);
+                float m0, m1;
+                pmp_upk(pmp_fma2(nrr, nrr, pmp_neg2(d2)), m0, m1);
+                const float mm = fmaxf(m0, m1);
+                margin = fmaxf(margin, mm);
+                if (mm > -PMP_CAND_SLACK) pairs |= 1u << (a >> 1);
             }
             touch = margin > 0.f;
         }
@@ -475,7 +485,6 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
         } else if (dense || __any_sync(PMP_FULL, touch)) {
             // ---- phase 2: K damped Gauss-Newton steps (oracle plant_equilibrium) ----
             if (!have_sc) { __sincosf(th0x, &s0x, &c0x); __sincosf(th0y, &s0y, &c0y); }
-            cpf.prep(mg, rt);
             {
                 // the joint frame before the stem's own rotation: Rv = Rs M(th0)^T
                 float M0[9];
@@ -495,9 +504,9 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
                 pmp_f2 Hxx2 = pmp_bc(0.f), Hxy2 = pmp_bc(0.f), Hyy2 = pmp_bc(0.f), gx2 = pmp_bc(0.f), gy2 = pmp_bc(0.f),
                        S2 = pmp_bc(0.f);
                 const pmp_f2 nbx = pmp_bc(-b[0]), nby = pmp_bc(-b[1]), nbz = pmp_bc(-b[2]);
-#pragma unroll
-                for (int a = 0; a < A; a += 2) {
-                    const pmp_f2 ccx = cpf(a >> 1, 0), ccy = cpf(a >> 1, 1), ccz = cpf(a >> 1, 2);
+                // contribution of spheres 2 pair, 2 pair + 1 to the normal equations in the current pose
+                auto accumulate = [&](const int pair) {
+                    const pmp_f2 ccx = cpf(pair, 0), ccy = cpf(pair, 1), ccz = cpf(pair, 2);
                     const pmp_f2 px = pmp_fma2(pmp_bc(Rl[0]), ccx, pmp_fma2(pmp_bc(Rl[3]), ccy, pmp_fma2(pmp_bc(Rl[6]), ccz, nbx)));
                     const pmp_f2 py = pmp_fma2(pmp_bc(Rl[1]), ccx, pmp_fma2(pmp_bc(Rl[4]), ccy, pmp_fma2(pmp_bc(Rl[7]), ccz, nby)));
                     const pmp_f2 pz = pmp_fma2(pmp_bc(Rl[2]), ccx, pmp_fma2(pmp_bc(Rl[5]), ccy, pmp_fma2(pmp_bc(Rl[8]), ccz, nbz)));
@@ -513,7 +522,7 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
                     const pmp_f2 inv = pmp_pk(pmp_rsqrt_ftz(e0), pmp_rsqrt_ftz(e1));
                     // d2 * inv - (r_a + margin) = -(penetration)
                     float n0, n1;
-                    pmp_upk(pmp_fma2(d2, inv, cpf.nrr(a >> 1, mg, rt)), n0, n1);
+                    pmp_upk(pmp_fma2(d2, inv, cpf.nrr(pair, mg, rt)), n0, n1);
                     const pmp_f2 pen = pmp_pk(fmaxf(-n0, 0.f), fmaxf(-n1, 0.f));
                     // m = d x pf,  pf = p + zc e_z
                     const pmp_f2 pfz = pmp_add2(pz, pmp_bc(zc));
@@ -529,6 +538,37 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
                     gx2 = pmp_fma2(pen, pJx, gx2);
                     gy2 = pmp_fma2(pen, pJy, gy2);
                     S2 = pmp_add2(S2, pen);
+                };
+                if (dense) {
+#pragma unroll
+                    for (int a = 0; a < A; a += 2) accumulate(a >> 1);
+                } else {
+                    // Only pairs that can penetrate in some lane contribute: every other pair adds exact zeros to the
+                    // sums (its penetration is max(., 0) = +0), so leaving it out changes no bit.  Iteration 0 knows
+                    // the candidates from phase 1; later poses get a rsqrt-free distance test of all pairs first.
+                    if (it > 0) {
+                        pairs = 0u;
+#pragma unroll
+                        for (int a = 0; a < A; a += 2) {
+                            const pmp_f2 ccx = cpf(a >> 1, 0), ccy = cpf(a >> 1, 1), ccz = cpf(a >> 1, 2);
+                            float p0, p1, q0, q1, r0, r1;
+                            pmp_upk(pmp_fma2(pmp_bc(Rl[0]), ccx, pmp_fma2(pmp_bc(Rl[3]), ccy, pmp_fma2(pmp_bc(Rl[6]), ccz, nbx))), p0, p1);
+                            pmp_upk(pmp_fma2(pmp_bc(Rl[1]), ccx, pmp_fma2(pmp_bc(Rl[4]), ccy, pmp_fma2(pmp_bc(Rl[7]), ccz, nby))), q0, q1);
+                            pmp_upk(pmp_fma2(pmp_bc(Rl[2]), ccx, pmp_fma2(pmp_bc(Rl[5]), ccy, pmp_fma2(pmp_bc(Rl[8]), ccz, nbz))), r0, r1);
+                            const pmp_f2 ex = pmp_pk(fmaxf(fabsf(p0) - hw, 0.f), fmaxf(fabsf(p1) - hw, 0.f));
+                            const pmp_f2 ey = pmp_pk(fmaxf(fabsf(q0) - hw, 0.f), fmaxf(fabsf(q1) - hw, 0.f));
+                            const pmp_f2 ez = pmp_pk(fmaxf(fabsf(r0) - hh, 0.f), fmaxf(fabsf(r1) - hh, 0.f));
+                            const pmp_f2 d2 = pmp_fma2(ex, ex, pmp_fma2(ey, ey, pmp_mul2(ez, ez)));
+                            const pmp_f2 nrr = cpf.nrr(a >> 1, mg, rt);
+                            float m0, m1;
+                            pmp_upk(pmp_fma2(nrr, nrr, pmp_neg2(d2)), m0, m1);
+                            if (fmaxf(m0, m1) > -PMP_CAND_SLACK) pairs |= 1u << (a >> 1);
+                        }
+                    }
+                    // lanes the solve no longer moves (never touched) must not keep pairs alive
+                    uint32_t wm = __reduce_or_sync(PMP_FULL, touch ? pairs : 0u);
+#pragma unroll 1
+                    for (; wm; wm &= wm - 1) accumulate(__ffs(wm) - 1);
                 }
                 const float Hxx = pmp_hsum2(Hxx2), Hxy = pmp_hsum2(Hxy2), Hyy = pmp_hsum2(Hyy2), gx = pmp_hsum2(gx2),
                             gy = pmp_hsum2(gy2), S = pmp_hsum2(S2);

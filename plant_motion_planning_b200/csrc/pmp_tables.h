@@ -57,6 +57,7 @@ struct PmpRobotTab {
     float sph_center[PMP_MAX_SPHERES * 3];
     float sph_radius[PMP_MAX_SPHERES];
     float sph_radius_outer[PMP_MAX_SPHERES];   // covering radii (broad phase of the hull test); == sph_radius without hulls
+    float sph_radius_inner[PMP_MAX_SPHERES];   // inscribed radii (ball inside hull (+) margin; 0 = unknown): certain hits
     uint32_t self_mask[PMP_MAX_SPHERES];
     int32_t sph_joint[PMP_MAX_SPHERES];
     float fixed_R[PMP_MAX_FIXED * 9];

@@ -59,6 +59,8 @@ class HullModel:
     sph_hull: np.ndarray            # [A] hull each arm sphere approximates (-1 = none)
     sph_radius_outer: np.ndarray    # [A] radii with which a hull's spheres cover hull (+) margin (broad phase)
     fixed_margin: float = 1.0e-3    # margin carved out of static boxes
+    sph_radius_inner: Optional[np.ndarray] = None   # [A] radius of the ball around a sphere's centre that lies inside
+                                                    # hull (+) margin (0 = unknown): certain hits without GJK
 
 
 @dataclass
@@ -113,6 +115,8 @@ class RobotModel:
             d["hulls"] = {"link_names": h.link_names, "joint": arr(h.joint), "margin": arr(h.margin), "pairs": arr(h.pairs),
                           "sph_hull": arr(h.sph_hull), "sph_radius_outer": arr(h.sph_radius_outer),
                           "fixed_margin": float(h.fixed_margin)}     # vertices travel in a .npz next to the JSON
+            if h.sph_radius_inner is not None:
+                d["hulls"]["sph_radius_inner"] = arr(h.sph_radius_inner)
         return json.dumps(d, indent=1)
 
     @staticmethod
@@ -129,7 +133,8 @@ class RobotModel:
                               [np.asarray(hull_verts[n], dtype=np.float64) for n in h["link_names"]],
                               np.asarray(h["margin"], dtype=np.float64), np.asarray(h["pairs"], dtype=np.int64).reshape(-1, 2),
                               np.asarray(h["sph_hull"], dtype=np.int64), np.asarray(h["sph_radius_outer"], dtype=np.float64),
-                              float(h["fixed_margin"]))
+                              float(h["fixed_margin"]),
+                              np.asarray(h["sph_radius_inner"], dtype=np.float64) if "sph_radius_inner" in h else None)
         return RobotModel(
             name=d["name"], dof=int(d["dof"]), joint_names=list(d["joint_names"]),
             joint_R0=f("joint_R0"), joint_t0=f("joint_t0"), joint_axis=f("joint_axis"),
@@ -303,6 +308,7 @@ def compile_robot(urdf: str | UrdfTree,
     base_prims: List[FixedPrim] = []
     base_prim_link: List[int] = []
     sph_outer: List[float] = []
+    sph_inner: List[float] = []
     hull_links: List[int] = []
     hull_vert_list: List[np.ndarray] = []
     root_frame = base if base is not None else Frame()
@@ -316,7 +322,9 @@ def compile_robot(urdf: str | UrdfTree,
                     raise NotImplementedError(
                         f"link {nm!r} carries a mesh; pass its fitted spheres (mesh_spheres) and hull (mesh_hulls), "
                         "or use a URDF with primitive collision geometry")
-                for (cen, rad, rad_out) in mesh_spheres[nm]:
+                for entry in mesh_spheres[nm]:
+                    cen, rad, rad_out = entry[:3]
+                    sph_inner.append(float(entry[3]) if len(entry) > 3 else 0.0)
                     sph_joint.append(jn)
                     sph_center.append((rel @ g.origin).apply(np.asarray(cen, dtype=np.float64)))
                     sph_radius.append(float(rad))
@@ -336,6 +344,7 @@ def compile_robot(urdf: str | UrdfTree,
                 sph_radius.append(float(g.size[0]))
                 sph_link.append(l)
                 sph_outer.append(float(g.size[0]))
+                sph_inner.append(0.0)
             else:
                 w = root_frame @ pose
                 if g.kind == "box":
@@ -355,6 +364,7 @@ def compile_robot(urdf: str | UrdfTree,
     sph_radius_a = np.asarray(sph_radius, dtype=np.float64)[order]
     sph_link_a = np.asarray(sph_link, dtype=np.int64)[order]
     sph_outer_a = np.asarray(sph_outer, dtype=np.float64)[order]
+    sph_inner_a = np.asarray(sph_inner, dtype=np.float64)[order]
 
     pair_set = {frozenset(p) for p in pairs}
     mask = np.zeros((A, A), dtype=bool)
@@ -382,7 +392,8 @@ def compile_robot(urdf: str | UrdfTree,
         sph_hull = np.array([hull_links.index(int(l)) if int(l) in hull_links else -1 for l in sph_link_a], dtype=np.int64)
         hulls = HullModel([link_names[l] for l in hull_links], np.array([int(link_joint[l]) for l in hull_links]),
                           hull_vert_list, np.full(len(hull_links), float(hull_margin)),
-                          np.asarray(hp, dtype=np.int64).reshape(-1, 2), sph_hull, sph_outer_a)
+                          np.asarray(hp, dtype=np.int64).reshape(-1, 2), sph_hull, sph_outer_a,
+                          sph_radius_inner=sph_inner_a if np.any(sph_inner_a > 0) else None)
 
     return RobotModel(
         name=name or tree.name, dof=D, joint_names=active_joints,

@@ -39,7 +39,9 @@ mesh_hulls = {n: fix[f"verts_{n}"] for n in hull_names}
 SLACK = 1.0e-3      # on top of the measured under-cover (it was measured on 20 000 surface samples per link)
 mesh_spheres = {}
 for l in fit["links"]:
-    mesh_spheres[l["link"]] = [(c, r, r + l["under_cover_m"] + SLACK) for c, r in zip(l["center"], l["radius"])]
+    # (centre, fitted radius, covering radius, inscribed radius = depth of the centre in the hull + margin)
+    mesh_spheres[l["link"]] = [(c, r, r + l["under_cover_m"] + SLACK, ri)
+                               for c, r, ri in zip(l["center"], l["radius"], l["radius_inscribed"])]
 hm = compile_robot(os.path.join(URDF_DIR, "iiwa14_polytope_collision_edit.urdf"), ee_link="iiwa_link_ee", name="iiwa14_hulls",
                    mesh_spheres=mesh_spheres, mesh_hulls=mesh_hulls, hull_margin=fit["margin"])
 print("iiwa14_hulls:", hm.num_spheres, "spheres,", len(hm.hulls.verts), "hulls,", len(hm.hulls.pairs), "hull pairs,",
