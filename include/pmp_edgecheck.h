@@ -124,6 +124,44 @@ typedef struct pmp_world_desc {
     const float* boxes;      /* [W*max_boxes*PMP_BOX_STRIDE] */
 } pmp_world_desc;
 
+/* ---- plant-world sampler on the device ----------------------------------------------------
+ * Replaces, for large world counts, the per-world create_plant_params call of SinglePlantEnv.__init__
+ * (env.py:63-73; rand_gen_plants_programmatically_main.py:71-277): one launch draws W worlds of one topology and
+ * writes their stem records and base boxes into caller-owned device buffers, pmp_set_worlds_dev adopts them -- the
+ * worlds never exist on the host.  Distributions, branch-placement rule and joint layout are the reference's; the ORDER
+ * of draws is not (a world consumes a fixed block of uniforms, so it does not depend on which other worlds are drawn):
+ * the bit-for-bit seed replay of the scripts stays with the host sampler (model/plants.sample_world). */
+#define PMP_SAMPLER_MAX_STEMS 8
+#define PMP_SAMPLER_TRIES 16      /* branch-placement attempts (rand_gen...:196-213 loops until no overlap) */
+#define PMP_SAMPLER_HEAD 5        /* uniforms per world: plant x, y, base half extents */
+#define PMP_SAMPLER_PER_STEM (8 + 3 * PMP_SAMPLER_TRIES)   /* + per stem: height, angles, placement attempts */
+typedef struct pmp_sampler_desc {
+    int32_t n_stems;                           /* <= PMP_SAMPLER_MAX_STEMS, parents first */
+    int32_t parent[PMP_SAMPLER_MAX_STEMS];     /* -1 for the first stem */
+    int32_t kind[PMP_SAMPLER_MAX_STEMS];       /* 0 first, 1 stacked vertical stem, 2 branch, 3 extension */
+    int32_t ref[PMP_SAMPLER_MAX_STEMS];        /* main stem of a branch / stacked stem, previous stem of an extension */
+    int32_t flags[PMP_SAMPLER_MAX_STEMS];      /* stem-record flags (PMP_SF_*), a function of the topology */
+    int32_t pslot[PMP_SAMPLER_MAX_STEMS];      /* parent / own frame slot (tables.assign_slots) */
+    int32_t oslot[PMP_SAMPLER_MAX_STEMS];
+    int32_t n_slots;
+    int32_t gravity_sag;                       /* 1: records hold the spring / gravity rest pose (model/statics.py) */
+    double xy_lo[2], xy_hi[2];                 /* plant_pos_xy_limits (env.py:63-64) */
+    double spacing;                            /* stem_base_spacing (rand_gen...:19-20) */
+    double scaling;                            /* 0.25 (rand_gen...:18) */
+    double half_width, com_z, limit;           /* 0.025, 0.25, 1.5 (rand_gen...:74-75, 265, 307) */
+    double stem_margin;                        /* Bullet's margin carved out of the stem boxes */
+    double kp, mass, g;                        /* 500, 10, 9.8 (env.py:128; rand_gen...:255; utils.py:1218-1221) */
+} pmp_sampler_desc;
+/* stems_dev [W * n_stems * PMP_STEM_STRIDE], boxes_dev [W * PMP_BOX_STRIDE] (one base box per world).
+ * uniforms_dev: NULL = counter-based generator keyed by (seed, world, draw); else [W * n_uniforms] doubles in [0, 1)
+ * with n_uniforms >= PMP_SAMPLER_HEAD + n_stems * PMP_SAMPLER_PER_STEM (parity tests pass the draws in). */
+int pmp_sample_worlds(pmp_ctx* ctx, const pmp_sampler_desc* desc, int32_t W, uint64_t seed, const double* uniforms_dev,
+                      int32_t n_uniforms, float* stems_dev, float* boxes_dev, void* stream);
+/* Adopt W worlds whose tables are already in device memory (every world: n_stems stems, n_boxes boxes; copied device
+ * to device on `stream`, the caller may free its buffers afterwards).  The records are trusted, not validated. */
+int pmp_set_worlds_dev(pmp_ctx* ctx, int32_t W, int32_t n_stems, int32_t n_boxes, int32_t n_slots, const float* stems_dev,
+                       const float* boxes_dev, void* stream);
+
 /* Constants the reference hard-codes in closures / module scope. */
 typedef struct pmp_params {
     double resolution;       /* DEFAULT_RESOLUTION = radians(3), pybullet_tools/utils.py:3660 */

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(LIB_DIR, "libpmp_edgecheck.so")
 STAMP = os.path.join(LIB_DIR, "libpmp_edgecheck.stamp")
 SOURCES = ["pmp_edgecheck.cu", "pmp_inst_a12.cu", "pmp_inst_a16.cu", "pmp_inst_a18.cu", "pmp_inst_a20.cu", "pmp_inst_a32.cu",
            "pmp_inst_a12f.cu", "pmp_inst_a16f.cu", "pmp_inst_a18f.cu", "pmp_inst_a20f.cu", "pmp_inst_a32f.cu"]
-HEADERS = ["pmp_kernels.cuh", "pmp_tables.h", "pmp_launch.h", "pmp_launch_impl.cuh", "pmp_tree.cuh", "pmp_hull.cuh",
+HEADERS = ["pmp_kernels.cuh", "pmp_tables.h", "pmp_launch.h", "pmp_launch_impl.cuh", "pmp_tree.cuh", "pmp_hull.cuh", "pmp_sampler.cuh",
            os.path.join("..", "..", "include", "pmp_edgecheck.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

@@ -58,6 +58,20 @@ class HullDesc(C.Structure):
     ]
 
 
+SAMPLER_MAX_STEMS, SAMPLER_TRIES, SAMPLER_HEAD = 8, 16, 5
+SAMPLER_PER_STEM = 8 + 3 * SAMPLER_TRIES
+
+
+class SamplerDesc(C.Structure):
+    _I8 = C.c_int32 * SAMPLER_MAX_STEMS
+    _fields_ = [
+        ("n_stems", C.c_int32), ("parent", _I8), ("kind", _I8), ("ref", _I8), ("flags", _I8), ("pslot", _I8), ("oslot", _I8),
+        ("n_slots", C.c_int32), ("gravity_sag", C.c_int32), ("xy_lo", C.c_double * 2), ("xy_hi", C.c_double * 2),
+        ("spacing", C.c_double), ("scaling", C.c_double), ("half_width", C.c_double), ("com_z", C.c_double),
+        ("limit", C.c_double), ("stem_margin", C.c_double), ("kp", C.c_double), ("mass", C.c_double), ("g", C.c_double),
+    ]
+
+
 class LaunchInfo(C.Structure):
     _fields_ = [
         ("grid", C.c_int32), ("block", C.c_int32), ("smem_bytes", C.c_int32), ("regs_per_thread", C.c_int32),
@@ -70,7 +84,7 @@ EXPORTS = [
     "pmp_create", "pmp_destroy", "pmp_last_error", "pmp_set_robot", "pmp_set_robot_hulls", "pmp_set_worlds", "pmp_set_params",
     "pmp_num_worlds", "pmp_max_stems", "pmp_fk", "pmp_check_configs", "pmp_validate_edges",
     "pmp_validate_edges_host", "pmp_check_configs_host", "pmp_get_launch_info", "pmp_measure_fp32_peak",
-    "pmp_set_kernel_timing", "pmp_get_kernel_times",
+    "pmp_set_kernel_timing", "pmp_get_kernel_times", "pmp_sample_worlds", "pmp_set_worlds_dev",
     "pmp_nearest", "pmp_edge_points", "pmp_tree_extend",
 ]
 
@@ -120,6 +134,8 @@ def load() -> C.CDLL:
     lib.pmp_nearest.argtypes = [vp, vp, C.c_int32, vp, vp, C.c_int32, vp, vp, vp, vp]
     lib.pmp_edge_points.argtypes = [vp, vp, vp, C.c_int32, vp, C.c_int32, vp, vp]
     lib.pmp_tree_extend.argtypes = [vp, C.POINTER(Tree), C.c_int32, vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp]
+    lib.pmp_sample_worlds.argtypes = [vp, C.POINTER(SamplerDesc), C.c_int32, C.c_uint64, vp, C.c_int32, vp, vp, vp]
+    lib.pmp_set_worlds_dev.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp]
     lib.pmp_set_kernel_timing.argtypes = [vp, C.c_int32]
     lib.pmp_get_kernel_times.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     for name in EXPORTS:

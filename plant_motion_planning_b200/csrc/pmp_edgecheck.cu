@@ -13,6 +13,7 @@
 #include "pmp_launch.h"
 #include "pmp_hull.cuh"
 #include "pmp_tree.cuh"
+#include "pmp_sampler.cuh"
 
 struct pmp_ctx {
     int device = 0;
@@ -425,6 +426,66 @@ extern "C" int pmp_set_worlds(pmp_ctx* ctx, const pmp_world_desc* w) {
     return PMP_OK;
 }
 
+extern "C" int pmp_sample_worlds(pmp_ctx* ctx, const pmp_sampler_desc* d, int32_t W, uint64_t seed, const double* uniforms_dev,
+                                 int32_t n_uniforms, float* stems_dev, float* boxes_dev, void* stream) {
+    if (!ctx || !d) return fail(ctx, PMP_E_INVALID, "null argument");
+    if (W < 1 || !stems_dev || !boxes_dev) return fail(ctx, PMP_E_INVALID, "W >= 1, stems and boxes are required");
+    const int P = d->n_stems;
+    if (P < 1 || P > PMP_SAMPLER_MAX_STEMS) return fail(ctx, PMP_E_INVALID, "n_stems out of range for the device sampler");
+    if (d->n_slots < 1 || d->n_slots > 4) return fail(ctx, PMP_E_INVALID, "n_slots must be 1..4");
+    for (int s = 0; s < P; ++s) {
+        if (d->parent[s] < -1 || d->parent[s] >= s) return fail(ctx, PMP_E_INVALID, "stems must be listed parents first");
+        if ((s == 0) != (d->kind[s] == PMP_SK_FIRST) || d->kind[s] < 0 || d->kind[s] > PMP_SK_EXT)
+            return fail(ctx, PMP_E_INVALID, "bad stem kind");
+        if (s > 0 && (d->ref[s] < 0 || d->ref[s] >= s)) return fail(ctx, PMP_E_INVALID, "bad stem ref");
+        if (d->pslot[s] < -1 || d->pslot[s] >= d->n_slots || d->oslot[s] < -1 || d->oslot[s] >= d->n_slots)
+            return fail(ctx, PMP_E_INVALID, "stem frame slot out of range");
+    }
+    if (uniforms_dev && n_uniforms < PMP_SAMPLER_HEAD + P * PMP_SAMPLER_PER_STEM)
+        return fail(ctx, PMP_E_INVALID, "too few uniforms per world");
+    CK(cudaSetDevice(ctx->device));
+    PmpSamplerArgs a;
+    a.d = *d; a.W = W; a.seed = seed; a.uniforms = uniforms_dev; a.n_uniforms = n_uniforms; a.stems = stems_dev; a.boxes = boxes_dev;
+    pmp_sample_worlds_kernel<<<(W + 63) / 64, 64, 0, (cudaStream_t)stream>>>(a);
+    CK(cudaGetLastError());
+    ctx->info.kernel_launches++;
+    return PMP_OK;
+}
+
+static __global__ void pmp_fill_i32_kernel(int32_t* p, int32_t n, int32_t v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+extern "C" int pmp_set_worlds_dev(pmp_ctx* ctx, int32_t W, int32_t n_stems, int32_t n_boxes, int32_t n_slots,
+                                  const float* stems_dev, const float* boxes_dev, void* stream) {
+    if (!ctx || !stems_dev || !boxes_dev) return fail(ctx, PMP_E_INVALID, "null argument");
+    if (W < 1) return fail(ctx, PMP_E_INVALID, "n_worlds < 1");
+    if (n_stems < 1 || n_stems > PMP_MAX_STEMS) return fail(ctx, PMP_E_INVALID, "n_stems out of range");
+    if (n_boxes < 1 || n_boxes > PMP_MAX_WORLD_BOXES) return fail(ctx, PMP_E_INVALID, "n_boxes out of range");
+    if (n_slots < 1 || n_slots > 4) return fail(ctx, PMP_E_INVALID, "n_slots must be 1..4");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaStreamSynchronize(st));          // the old tables may still be in use by launches on this stream
+    free_worlds(ctx);
+    ctx->has_worlds = false;
+    const size_t sb = sizeof(float) * (size_t)W * n_stems * PMP_STEM_STRIDE;
+    const size_t bb = sizeof(float) * (size_t)W * n_boxes * PMP_BOX_STRIDE;
+    CK(cudaMalloc(&ctx->d_stems, sb));
+    CK(cudaMalloc(&ctx->d_nstems, sizeof(int32_t) * W));
+    CK(cudaMalloc(&ctx->d_boxes, bb));
+    CK(cudaMalloc(&ctx->d_nboxes, sizeof(int32_t) * W));
+    CK(cudaMemcpyAsync(ctx->d_stems, stems_dev, sb, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_boxes, boxes_dev, bb, cudaMemcpyDeviceToDevice, st));
+    pmp_fill_i32_kernel<<<(W + 255) / 256, 256, 0, st>>>(ctx->d_nstems, W, n_stems);
+    pmp_fill_i32_kernel<<<(W + 255) / 256, 256, 0, st>>>(ctx->d_nboxes, W, n_boxes);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    ctx->n_worlds = W; ctx->max_stems = n_stems; ctx->max_boxes = n_boxes; ctx->n_slots = n_slots;
+    ctx->has_worlds = true;
+    return PMP_OK;
+}
+
 extern "C" int pmp_set_params(pmp_ctx* ctx, const pmp_params* p) {
     if (!ctx || !p) return fail(ctx, PMP_E_INVALID, "null argument");
     if (!(p->resolution > 0.0)) return fail(ctx, PMP_E_INVALID, "resolution must be > 0");
@@ -547,7 +608,7 @@ static int validate_edges_impl(pmp_ctx* ctx, const float* q0, const float* q1, i
     // World tables go to shared memory when they fit, else they are read through L1.
     auto smem_for = [&](int blk, bool ws) {
         const int warps = blk / 32;
-        return sizeof(PmpRobotTab) + (ws ? world_bytes : 0) + sizeof(int32_t) * ((W + 3) & ~3) +
+        return sizeof(PmpRobotTab) + (ws ? world_bytes + sizeof(int32_t) * ((W + 3) & ~3) : 0) +
                (size_t)warps * PMP_MAX_DOF * (sizeof(double) + 3 * sizeof(float)) +
                (size_t)warps * 3 * apad * 33 * sizeof(float);          // swept-bound staging tile per warp
     };

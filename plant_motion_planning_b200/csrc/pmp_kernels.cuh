@@ -804,7 +804,7 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
     const int W = prm.n_worlds;
     const int stem_words = WSMEM ? W * prm.max_stems * PMP_STEM_STRIDE : 0;
     int32_t* sm_nstems = reinterpret_cast<int32_t*>(sm_stems + stem_words);
-    const int nstem_words = (W + 3) & ~3;
+    const int nstem_words = WSMEM ? ((W + 3) & ~3) : 0;    // stem counts ride with the tables: shared memory or L1
     // per-warp staging: q0[16] q1[16] dq[16] floats + sq[16] doubles
     const int warps = blockDim.x >> 5;
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -818,7 +818,7 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
 
     pmp_stage_words(&rt, args.robot, sizeof(PmpRobotTab) / 4);
     if (WSMEM) pmp_stage_words(sm_stems, args.stems, stem_words);
-    for (int i = threadIdx.x; i < W; i += blockDim.x) sm_nstems[i] = args.n_stems[i];
+    if (WSMEM) for (int i = threadIdx.x; i < W; i += blockDim.x) sm_nstems[i] = args.n_stems[i];
     __syncthreads();
 
     const int D = rt.dof;
@@ -973,7 +973,7 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
                 u.plant_hit = false; u.exceeded = false; u.max_defl = 0.f; u.over = 0.f;
                 if (prm.mode != PMP_MODE_IGNORE_ALL) {
                     u = pmp_world_eval<A, NSLOT, false, true>(
-                        stems_base + (size_t)w * prm.max_stems * PMP_STEM_STRIDE, sm_nstems[w],
+                        stems_base + (size_t)w * prm.max_stems * PMP_STEM_STRIDE, WSMEM ? sm_nstems[w] : __ldg(args.n_stems + w),
                         args.boxes + (size_t)w * prm.max_boxes * PMP_BOX_STRIDE,
                         prm.mode == PMP_MODE_AVOID_ALL ? args.n_boxes[w] : 0, rt, prm, cpf, nullptr, nullptr, bound);
                 }

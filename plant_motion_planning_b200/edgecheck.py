@@ -148,6 +148,48 @@ class EdgeChecker:
         d.n_boxes, d.boxes = _capi.iptr(wt.n_boxes), _capi.fptr(boxes)
         self._check(self._lib.pmp_set_worlds(self._ctx, C.byref(d)), "pmp_set_worlds")
 
+    def sample_worlds_on_device(self, n: int, branches: int = 1, vert_stems: int = 2, extensions: int = 1,
+                                plant_pos_xy_limits=((0.0, 0.35), (-0.5, 0.0)), seed: int = 0,
+                                stem_base_spacing: float = 0.0, uniforms=None) -> "DeviceWorldTables":
+        """Draw ``n`` plant worlds of one topology ON THE DEVICE (pmp_sample_worlds) and make them this checker's
+        worlds (pmp_set_worlds_dev): the tables never exist on the host.  ``uniforms``: optional [n, U] float64 array /
+        tensor of draws in [0, 1) (model/batch_sampler.uniforms_per_world; parity tests), else the counter-based
+        generator keyed by ``seed``.  Same plants as model/batch_sampler.draws_from_uniforms on the same draws."""
+        torch = self._torch()
+        from .model import batch_sampler as bs
+        from .model.plants import PLANT_JOINT_LIMIT, SCALING, STEM_COM_Z, STEM_HALF_WIDTH
+        from .model.statics import GRAVITY, SPRING_KP, STEM_MASS
+        topo = bs.sampler_topology(branches, vert_stems, extensions)
+        P = topo["n_stems"]
+        d = _capi.SamplerDesc()
+        d.n_stems, d.n_slots, d.gravity_sag = P, topo["n_slots"], 1 if self.config.gravity_sag else 0
+        for key in ("parent", "kind", "ref", "flags", "pslot", "oslot"):
+            arr = getattr(d, key)
+            for k, v in enumerate(topo[key]):
+                arr[k] = int(v)
+        (x0, x1), (y0, y1) = plant_pos_xy_limits
+        d.xy_lo[0], d.xy_lo[1], d.xy_hi[0], d.xy_hi[1] = x0, y0, x1, y1
+        d.spacing, d.scaling, d.half_width, d.com_z = stem_base_spacing, SCALING, STEM_HALF_WIDTH, STEM_COM_Z
+        d.limit, d.stem_margin, d.kp, d.mass, d.g = PLANT_JOINT_LIMIT, self.config.stem_margin, SPRING_KP, STEM_MASS, GRAVITY
+        dev = self._dev()
+        with torch.cuda.device(dev):
+            stems = torch.empty((n, P, 48), device=dev, dtype=torch.float32)
+            boxes = torch.empty((n, 1, 16), device=dev, dtype=torch.float32)
+            u_t, nu = None, 0
+            if uniforms is not None:
+                u_t = torch.as_tensor(uniforms).to(device=dev, dtype=torch.float64).contiguous()
+                if u_t.dim() != 2 or u_t.shape[0] != n:
+                    raise ValueError("uniforms must be [n, U]")
+                nu = int(u_t.shape[1])
+            self._check(self._lib.pmp_sample_worlds(self._ctx, C.byref(d), int(n), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                                    self._p(u_t), nu, self._p(stems), self._p(boxes), self._stream()),
+                        "pmp_sample_worlds")
+            self._check(self._lib.pmp_set_worlds_dev(self._ctx, int(n), P, 1, topo["n_slots"], self._p(stems),
+                                                     self._p(boxes), self._stream()), "pmp_set_worlds_dev")
+        self.worlds = None
+        self.world_tables = DeviceWorldTables(int(n), P, 1, topo["n_slots"], stems, boxes)
+        return self.world_tables
+
     def _push_params(self) -> None:
         c = self.config
         if c.mode not in MODES:
@@ -388,6 +430,36 @@ class EdgeChecker:
         self._check(self._lib.pmp_check_configs_host(self._ctx, vp(q), B, vp(out["flags"]), vp(out.get("deflection")),
                                                      vp(out.get("theta")), vp(out["ee"])), "pmp_check_configs_host")
         return out
+
+
+class DeviceWorldTables:
+    """World tables that live in device memory (EdgeChecker.sample_worlds_on_device).  Same attribute names as
+    model.tables.WorldTables; ``stems`` / ``boxes`` are downloaded on first use (tests, reports)."""
+
+    def __init__(self, n_worlds, max_stems, max_boxes, n_slots, stems_dev, boxes_dev):
+        self.n_worlds, self.max_stems, self.max_boxes, self.n_slots = n_worlds, max_stems, max_boxes, n_slots
+        self.stems_dev, self.boxes_dev = stems_dev, boxes_dev
+        self._stems = self._boxes = None
+
+    @property
+    def stems(self) -> np.ndarray:
+        if self._stems is None:
+            self._stems = self.stems_dev.cpu().numpy()
+        return self._stems
+
+    @property
+    def boxes(self) -> np.ndarray:
+        if self._boxes is None:
+            self._boxes = self.boxes_dev.cpu().numpy()
+        return self._boxes
+
+    @property
+    def n_stems(self) -> np.ndarray:
+        return np.full(self.n_worlds, self.max_stems, dtype=np.int32)
+
+    @property
+    def n_boxes(self) -> np.ndarray:
+        return np.full(self.n_worlds, self.max_boxes, dtype=np.int32)
 
 
 @dataclass

@@ -121,6 +121,103 @@ def draw_plants(n: int, branches: int, verts: int, exts: int, plant_pos_xy_limit
     return PlantDraws(parent, is_main, base_xy, base_half, hh, xyz, rpy, float(stem_base_spacing))
 
 
+# ---- the device sampler's draw layout (csrc/pmp_sampler.cuh; include/pmp_edgecheck.h PMP_SAMPLER_*) -----------------
+SAMPLER_MAX_STEMS, SAMPLER_TRIES, SAMPLER_HEAD = 8, 16, 5
+SAMPLER_PER_STEM = 8 + 3 * SAMPLER_TRIES
+KIND_CODE = {"first": 0, "stack": 1, "branch": 2, "ext": 3}
+
+
+def uniforms_per_world(n_stems: int) -> int:
+    return SAMPLER_HEAD + n_stems * SAMPLER_PER_STEM
+
+
+def splitmix_uniforms(seed: int, n: int, n_uniforms: int) -> np.ndarray:
+    """The counter-based generator of the device sampler (splitmix64 of (seed, world * n_uniforms + draw)) -> [n, n_uniforms]
+    doubles in [0, 1)."""
+    with np.errstate(over="ignore"):
+        ctr = np.arange(n * n_uniforms, dtype=np.uint64) + np.uint64(1)
+        z = np.uint64(seed & 0xFFFFFFFFFFFFFFFF) + ctr * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return ((z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)).reshape(n, n_uniforms)
+
+
+def draws_from_uniforms(U: np.ndarray, branches: int, verts: int, exts: int, plant_pos_xy_limits,
+                        stem_base_spacing: float = 0.0) -> PlantDraws:
+    """Host mirror of the device sampler: the same fixed block of uniforms per world -> the same plants
+    (distributions and placement rule of draw_plants; at most SAMPLER_TRIES placement attempts per branch)."""
+    sf = SCALING
+    parent, is_main, kinds = _topology(branches, verts, exts)
+    P = len(parent)
+    n = U.shape[0]
+    if U.shape[1] < uniforms_per_world(P):
+        raise ValueError("too few uniforms per world")
+    lerp = lambda a, b, x: a + (b - a) * x
+    (x0, x1), (y0, y1) = plant_pos_xy_limits
+    base_xy = np.stack([lerp(x0, x1, U[:, 0]), lerp(y0, y1, U[:, 1])], axis=1)
+    base_half = lerp(sf * 0.07, sf * 0.15, U[:, 2:5])
+    hh = np.zeros((n, P)); xyz = np.zeros((n, P, 3)); rpy = np.zeros((n, P, 3))
+    for k, (kind, ref) in enumerate(kinds):
+        B = SAMPLER_HEAD + k * SAMPLER_PER_STEM
+        hh[:, k] = lerp(sf * 0.7, sf * 1.0, U[:, B])
+        if kind == "first":
+            xyz[:, k, 2] = base_half[:, 2]
+        elif kind == "stack":
+            xyz[:, k, 2] = stem_base_spacing + 2.0 * hh[:, ref]
+            ang = lerp(-0.4, 0.4, U[:, B + 1])
+            pitch_side = U[:, B + 2] < 0.5
+            rpy[:, k, 1] = np.where(pitch_side, ang, 0.0)
+            rpy[:, k, 0] = np.where(pitch_side, 0.0, ang)
+            rpy[:, k, 2] = lerp(-0.4, 0.4, U[:, B + 3])
+        elif kind == "ext":
+            xyz[:, k, 2] = stem_base_spacing + 2.0 * hh[:, ref]
+            ang = lerp(sf * -0.5, sf * 0.5, U[:, B + 1])
+            roll_side = U[:, B + 2] < 0.5
+            rpy[:, k, 0] = np.where(roll_side, ang, 0.0)
+            rpy[:, k, 1] = np.where(roll_side, 0.0, ang)
+        else:
+            tol = sf * 0.2
+            x = np.zeros(n); y = np.zeros(n)
+            todo = np.ones(n, dtype=bool)
+            earlier = [j for j in range(k) if kinds[j][0] == "branch" and kinds[j][1] == ref]
+            for t in range(SAMPLER_TRIES):
+                side = U[:, B + 8 + 3 * t] < 0.5
+                fixed = np.where(U[:, B + 9 + 3 * t] < 0.5, sf * 0.2, sf * -0.2)
+                free = lerp(0.0, sf * 0.2, U[:, B + 10 + 3 * t])
+                x = np.where(todo, np.where(side, fixed, free), x)
+                y = np.where(todo, np.where(side, free, fixed), y)
+                clash = np.zeros(n, dtype=bool)
+                for j in earlier:
+                    clash |= (np.abs(x - xyz[:, j, 0]) < tol) & (np.abs(y - xyz[:, j, 1]) < tol)
+                todo &= clash
+            yaw = lerp(-0.5, 0.5, U[:, B + 1])
+            mag = lerp(0.7, 1.5, U[:, B + 2])
+            along_x = np.abs(x) > np.abs(y)
+            rpy[:, k, 1] = np.where(along_x, np.where(x > 0, mag, -mag), 0.0)
+            rpy[:, k, 0] = np.where(along_x, 0.0, np.where(y > 0, -mag, mag))
+            rpy[:, k, 2] = yaw
+            xyz[:, k, 0], xyz[:, k, 1] = x, y
+            xyz[:, k, 2] = stem_base_spacing + U[:, B + 3] * 2.0 * hh[:, ref]
+    return PlantDraws(parent, is_main, base_xy, base_half, hh, xyz, rpy, float(stem_base_spacing))
+
+
+def sampler_topology(branches: int, verts: int, exts: int) -> dict:
+    """Topology arrays of the device sampler's descriptor (pmp_sampler_desc): parent, kind, ref, flags, frame slots."""
+    parent, is_main, kinds = _topology(branches, verts, exts)
+    P = len(parent)
+    if P > SAMPLER_MAX_STEMS:
+        raise ValueError(f"{P} stems > {SAMPLER_MAX_STEMS}: the device sampler handles small topologies; use "
+                         "sample_world_tables (host) for this one")
+    template = PlantWorld(stems=[Stem(parent=int(p), origin=Frame(), half_height=0.1, z_offset=0.0) for p in parent],
+                          base_boxes=[])
+    par, own, n_slots = assign_slots(template)
+    flags = [(F_PLANT_START if k == 0 else 0) | (F_IS_MAIN if is_main[k] else 0) |
+             (F_HAS_PARENT if parent[k] >= 0 else F_OBS_ROOT) for k in range(P)]
+    return {"n_stems": P, "parent": [int(p) for p in parent], "kind": [KIND_CODE[k] for k, _ in kinds],
+            "ref": [max(int(r), 0) for _, r in kinds], "flags": flags, "pslot": par, "oslot": own, "n_slots": n_slots}
+
+
 def _rpy_matrices(rpy: np.ndarray) -> np.ndarray:
     """Rz(yaw) Ry(pitch) Rx(roll) for arrays [..., 3] -> [..., 3, 3] (model/transforms.rpy_to_matrix)."""
     r, p, y = rpy[..., 0], rpy[..., 1], rpy[..., 2]
