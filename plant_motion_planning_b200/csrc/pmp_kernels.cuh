@@ -451,10 +451,13 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
         // ---- phase 1: does any arm sphere touch the stem in its initial pose?  (exact, no rsqrt / Jacobian) ----
         // `pairs`: sphere pairs that come within PMP_CAND_SLACK of touching (a superset of the pairs with a positive
         // penetration in the solve's first iteration, whose distance goes through an approximate rsqrt)
+        // The dense (roofline) launch skips this phase: its first Gauss-Newton pass computes the same p, d and |d|^2 for
+        // every pair anyway and derives `touch` from them with the same arithmetic (|p| - h and p - clamp(p) have the
+        // same square), so that executed work == algorithmic work there and the results stay bit-identical.
         bool touch = false;
         uint32_t pairs = 0u;
         cpf.prep(mg, rt);
-        {
+        if (!(dense && solve)) {
             float margin = -1.f;
             const pmp_f2 nbx = pmp_bc(-b[0]), nby = pmp_bc(-b[1]), nbz = pmp_bc(-b[2]);
 #pragma unroll
@@ -467,7 +470,7 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
                 const pmp_f2 ex = pmp_pk(fmaxf(fabsf(p0) - hw, 0.f), fmaxf(fabsf(p1) - hw, 0.f));
                 const pmp_f2 ey = pmp_pk(fmaxf(fabsf(q0) - hw, 0.f), fmaxf(fabsf(q1) - hw, 0.f));
                 const pmp_f2 ez = pmp_pk(fmaxf(fabsf(r0) - hh, 0.f), fmaxf(fabsf(r1) - hh, 0.f));
-                const pmp_f2 d2 = pmp_fma2(ex, ex, pmp_fma2(ey, ey, pmp_mul2(ez, ez)));
+                const pmp_f2 d2 = pmp_fma2(ex, ex, pmp_fma2(ey, ey, pmp_fma2(ez, ez, pmp_bc(1e-24f))));
                 // touching <=> (r_a + margin)^2 - d2 > 0; the largest such value over all spheres decides
                 // (padding spheres sit at PMP_FAR with radius -1e3: (r + mg)^2 = 1e6 against d2 = 3e12)
                 const pmp_f2 nrr = cpf.nrr(a >> 1, mg, rt);
@@ -505,7 +508,8 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
                        S2 = pmp_bc(0.f);
                 const pmp_f2 nbx = pmp_bc(-b[0]), nby = pmp_bc(-b[1]), nbz = pmp_bc(-b[2]);
                 // contribution of spheres 2 pair, 2 pair + 1 to the normal equations in the current pose
-                auto accumulate = [&](const int pair) {
+                float margin0 = -1.f;      // dense launch, first pass: the contact test's running maximum
+                auto accumulate = [&](const int pair, const bool with_test) {
                     const pmp_f2 ccx = cpf(pair, 0), ccy = cpf(pair, 1), ccz = cpf(pair, 2);
                     const pmp_f2 px = pmp_fma2(pmp_bc(Rl[0]), ccx, pmp_fma2(pmp_bc(Rl[3]), ccy, pmp_fma2(pmp_bc(Rl[6]), ccz, nbx)));
                     const pmp_f2 py = pmp_fma2(pmp_bc(Rl[1]), ccx, pmp_fma2(pmp_bc(Rl[4]), ccy, pmp_fma2(pmp_bc(Rl[7]), ccz, nby)));
@@ -522,8 +526,14 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
                     const pmp_f2 inv = pmp_pk(pmp_rsqrt_ftz(e0), pmp_rsqrt_ftz(e1));
                     // d2 * inv - (r_a + margin) = -(penetration)
                     float n0, n1;
-                    pmp_upk(pmp_fma2(d2, inv, cpf.nrr(pair, mg, rt)), n0, n1);
+                    const pmp_f2 nrr = cpf.nrr(pair, mg, rt);
+                    pmp_upk(pmp_fma2(d2, inv, nrr), n0, n1);
                     const pmp_f2 pen = pmp_pk(fmaxf(-n0, 0.f), fmaxf(-n1, 0.f));
+                    if (with_test) {
+                        float m0, m1;
+                        pmp_upk(pmp_fma2(nrr, nrr, pmp_neg2(d2)), m0, m1);
+                        margin0 = fmaxf(margin0, fmaxf(m0, m1));
+                    }
                     // m = d x pf,  pf = p + zc e_z
                     const pmp_f2 pfz = pmp_add2(pz, pmp_bc(zc));
                     const pmp_f2 mx = pmp_fma2(dy, pfz, pmp_mul2(pmp_neg2(dz), py));
@@ -540,8 +550,15 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
                     S2 = pmp_add2(S2, pen);
                 };
                 if (dense) {
+                    // (two unrolled copies: one loop with a run-time "first pass" flag measured 3 % slower)
+                    if (it == 0) {
 #pragma unroll
-                    for (int a = 0; a < A; a += 2) accumulate(a >> 1);
+                        for (int a = 0; a < A; a += 2) accumulate(a >> 1, true);
+                        touch = margin0 > 0.f;
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < A; a += 2) accumulate(a >> 1, false);
+                    }
                 } else {
                     // Only pairs that can penetrate in some lane contribute: every other pair adds exact zeros to the
                     // sums (its penetration is max(., 0) = +0), so leaving it out changes no bit.  Iteration 0 knows
@@ -568,7 +585,7 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
                     // lanes the solve no longer moves (never touched) must not keep pairs alive
                     uint32_t wm = __reduce_or_sync(PMP_FULL, touch ? pairs : 0u);
 #pragma unroll 1
-                    for (; wm; wm &= wm - 1) accumulate(__ffs(wm) - 1);
+                    for (; wm; wm &= wm - 1) accumulate(__ffs(wm) - 1, false);
                 }
                 const float Hxx = pmp_hsum2(Hxx2), Hxy = pmp_hsum2(Hxy2), Hyy = pmp_hsum2(Hyy2), gx = pmp_hsum2(gx2),
                             gy = pmp_hsum2(gy2), S = pmp_hsum2(S2);
