@@ -1,0 +1,59 @@
+"""The stated tolerance of the quasi-static plant model against a time-stepped restatement of the reference's procedure
+(oracle/dynamic_oracle.py: env.py:127-172, 212-227 -- springs as external link torques that load ancestor joints,
+gravity, joint damping, 50 sub-steps of 1/240 s per interpolation step, velocity-level contacts, the arm lagging behind
+its command).  DESIGN.md section 4 quotes these numbers; this test keeps them true.  Neither side is PyBullet (it
+cannot run here): the dynamic model is itself a restatement, which is why the deflection row stays "partial".
+
+Measured (tools/dynamic_gap_report.py, profiles/r02_dynamic_gap.json and the runs below):
+  contact-free path (multi_world_avoid_all plan):  |dynamic - quasi-static| median 0.003, p99 0.034, max 0.037 rad,
+      identical over-limit decisions at limit 0.30 -- the residue is sway and arm lag, an order below the limit;
+  path that pushes through the plants (multi_world_our_method plan, found with limit 2.0): median 0.05, p90 0.18,
+      max 0.44 rad, and the dynamic model reports "over 0.30" on 37 % of the waypoints where the quasi-static one
+      reports none: the stateless minimum-norm response under-estimates a stem that is dragged along by the arm.
+"""
+import json
+import os
+
+import numpy as np
+
+from oracle import edgecheck_oracle as O
+from oracle.dynamic_oracle import DynamicEnv, DynParams
+from plant_motion_planning_b200 import load_iiwa14
+from plant_motion_planning_b200.scenarios import START, script_worlds
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIMIT = 0.30
+
+
+def _both(scene, stride, count, n_worlds):
+    model = load_iiwa14()
+    with open(os.path.join(HERE, "golden", "reference_rrt.json")) as fp:
+        gold = json.load(fp)
+    worlds, _ = script_worlds(scene)
+    worlds = worlds[:n_worlds]
+    path = [tuple(q) for q in gold[scene]["smoothed"]][::stride][:count]
+    Q = np.asarray(path, dtype=np.float64)
+    qs = O.check_configs(model, worlds, Q, O.OracleParams(), Q_limits=Q).deflection
+    env = DynamicEnv(model, worlds, DynParams())
+    env.reset(START, 3000)
+    dyn = []
+    for q in path:
+        env.step(q)
+        dyn.append(np.stack(env.deflections()))
+    return np.stack(dyn), qs
+
+
+def test_contact_free_path_agrees_within_a_sixth_of_the_limit():
+    dyn, qs = _both("multi_world_avoid_all_seed37", 2, 16, 2)
+    d = np.abs(dyn - qs)
+    assert np.median(d) < 0.01 and d.max() < 0.05, (np.median(d), d.max())
+    assert np.array_equal(np.any(dyn > LIMIT, axis=2), np.any(qs > LIMIT, axis=2))
+
+
+def test_in_contact_gap_stays_at_its_measured_size():
+    dyn, qs = _both("multi_world_our_method", 2, 24, 1)
+    d = np.abs(dyn - qs)
+    assert np.median(d) < 0.08 and np.percentile(d, 90) < 0.30 and d.max() < 0.6, (np.median(d), np.percentile(d, 90), d.max())
+    # the gap is one-sided where it matters: the quasi-static model never reports MORE over-limit waypoints
+    ex_d, ex_q = np.any(dyn > LIMIT, axis=2), np.any(qs > LIMIT, axis=2)
+    assert ex_q.sum() <= ex_d.sum()
