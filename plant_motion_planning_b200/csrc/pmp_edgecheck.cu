@@ -358,7 +358,7 @@ extern "C" int pmp_set_robot_hulls(pmp_ctx* ctx, const pmp_hull_desc* h) {
 static int launch_rigid(pmp_ctx* ctx, const float* q0, const float* q1, int32_t E, int32_t max_steps, int32_t backward,
                         uint32_t* rigid_pre, const float* q, int32_t B, uint8_t* rigid_flags, cudaStream_t st) {
     PmpRigidArgs a;
-    a.robot = ctx->d_robot; a.hulls = ctx->d_hulls; a.hull_verts = ctx->d_hull_verts; a.prm = ctx->prm;
+    a.robot = ctx->d_robot; a.hulls = ctx->has_hulls ? ctx->d_hulls : nullptr; a.hull_verts = ctx->d_hull_verts; a.prm = ctx->prm;
     a.pair_tables = ctx->d_pair_tables;
     a.q0 = q0; a.q1 = q1; a.E = E; a.max_steps = max_steps; a.backward = backward ? 1 : 0; a.rigid_pre = rigid_pre;
     a.q = q; a.B = B; a.rigid_flags = rigid_flags;
@@ -574,9 +574,10 @@ static int validate_edges_impl(pmp_ctx* ctx, const float* q0, const float* q1, i
     CK(cudaSetDevice(ctx->device));
     PmpEdgeArgs a;
     a.rigid_pre = nullptr;
-    if (ctx->has_hulls) {
-        // exact self / obstacle test on the hulls: one bit per step, consumed by the edge kernel below.  The scratch
-        // belongs to the context (or to the caller's chunk); launches of one context are ordered by their stream.
+    {
+        // limits | self | obstacles of every step: one bit per step from the pre-pass (exact GJK test on the hulls, or
+        // the arm's sphere model when the robot has none), consumed by the edge kernel below.  The scratch belongs to
+        // the context (or to the caller's chunk); launches of one context are ordered by their stream.
         uint32_t* pre = rigid_pre_scratch;
         if (!pre) {
             rc = ensure_rigid_scratch(ctx, sizeof(uint32_t) * (size_t)E * ((max_steps + 31) / 32));
@@ -588,8 +589,6 @@ static int validate_edges_impl(pmp_ctx* ctx, const float* q0, const float* q1, i
         if (rc) return rc;
         if (ctx->timing) { CK(cudaEventRecord(ctx->ev[1], (cudaStream_t)stream)); ctx->timed_rigid = true; }
         a.rigid_pre = pre;
-    } else {
-        ctx->timed_rigid = false;
     }
     a.robot = ctx->d_robot; a.stems = ctx->d_stems; a.n_stems = ctx->d_nstems; a.boxes = ctx->d_boxes;
     a.n_boxes = ctx->d_nboxes; a.prm = ctx->prm; a.q0 = q0; a.q1 = q1; a.E = E; a.max_steps = max_steps;
@@ -683,7 +682,7 @@ extern "C" int pmp_check_configs(pmp_ctx* ctx, const float* q, int32_t B, uint8_
     a.robot = ctx->d_robot; a.stems = ctx->d_stems; a.n_stems = ctx->d_nstems; a.boxes = ctx->d_boxes;
     a.n_boxes = ctx->d_nboxes; a.prm = ctx->prm; a.q = q; a.B = B; a.flags = flags; a.defl = defl; a.theta = theta; a.ee = ee;
     a.rigid_pre = nullptr;
-    if (ctx->has_hulls) {
+    {
         rc = ensure_rigid_scratch(ctx, (size_t)B);
         if (rc) return rc;
         rc = launch_rigid(ctx, nullptr, nullptr, 0, 32, 0, nullptr, q, B, (uint8_t*)ctx->d_rigid_scratch, (cudaStream_t)stream);
@@ -747,7 +746,7 @@ extern "C" int pmp_validate_edges_host(pmp_ctx* ctx, const float* q0, const floa
     const int CE = (E + n_chunks - 1) / n_chunks;               // edges per chunk
     const size_t bq = up256(sizeof(float) * (size_t)CE * D), bi = up256(sizeof(int32_t) * (size_t)CE),
                  bw = up256(sizeof(float) * (size_t)CE * W), bm = up256(sizeof(uint32_t) * (size_t)CE * W * C);
-    const size_t bp = ctx->has_hulls ? up256(sizeof(uint32_t) * (size_t)CE * C) : 0;     // hull pre-pass bits
+    const size_t bp = up256(sizeof(uint32_t) * (size_t)CE * C);     // pre-pass bits
     const size_t per = 2 * bq + 2 * bi + (max_defl ? bw : 0) + (over ? bw : 0) + (ee_len ? bi : 0) + (cost ? bi : 0) +
                        (rigid_mask ? bm : 0) + (exceed_mask ? bm : 0) + bp;
     rc = ensure_scratch(ctx, (n_chunks > 1 ? 2 : 1) * per);

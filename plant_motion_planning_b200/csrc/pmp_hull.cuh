@@ -286,8 +286,11 @@ __global__ void __launch_bounds__(32 * PMP_RIGID_WARPS, 4) pmp_rigid_kernel(cons
     __shared__ float sm_qL_all[PMP_RIGID_WARPS][PMP_MAX_DOF];
     extern __shared__ __align__(16) float sm_lane_centres[];        // [warps][3 A][32] (dynamic: 3 * A * 32 floats per warp)
     pmp_stage_words(&rt, args.robot, sizeof(PmpRobotTab) / 4);
-    pmp_stage_words(&ht, args.hulls, sizeof(PmpHullTab) / 4);
+    if (args.hulls) pmp_stage_words(&ht, args.hulls, sizeof(PmpHullTab) / 4);
     __syncthreads();
+    // Without hulls (args.hulls == nullptr) the arm's SPHERE model decides: sphere pairs named by self_mask, spheres
+    // against the static primitives named by fixed_mask, exact radii (oracle rigid_hit) -- the same bit per step.
+    const bool hull_mode = args.hulls != nullptr;
     const PmpKernelParams prm = args.prm;
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* sm_sq = sm_sq_all[wid];
@@ -298,7 +301,7 @@ __global__ void __launch_bounds__(32 * PMP_RIGID_WARPS, 4) pmp_rigid_kernel(cons
     float (*sc)[3] = sm_sc_all[wid];
     float* qL = sm_qL_all[wid];
     float* lc = sm_lane_centres + (size_t)wid * 3 * rt.n_spheres * 32;
-    const int D = rt.dof, A = rt.n_spheres, H = ht.n_hulls;
+    const int D = rt.dof, A = rt.n_spheres, H = hull_mode ? ht.n_hulls : 0;
     const bool edge_mode = args.q == nullptr;
     const int C = (args.max_steps + 31) >> 5;
     const int n_items = edge_mode ? args.E * C : (args.B + 31) >> 5;
@@ -371,10 +374,33 @@ __global__ void __launch_bounds__(32 * PMP_RIGID_WARPS, 4) pmp_rigid_kernel(cons
                     lc[(3 * a) * 32 + lane] = x + pp[0]; lc[(3 * a + 1) * 32 + lane] = y + pp[1]; lc[(3 * a + 2) * 32 + lane] = z + pp[2];
                 }
             }
+            if (!hull_mode) {
+#pragma unroll 1
+                for (int a1 = 0; a1 < A; ++a1) {
+                    const uint32_t m = rt.self_mask[a1];
+                    for (int b1 = a1 + 1; b1 < A; ++b1) {
+                        if (!((m >> b1) & 1u)) continue;
+                        const float dx = lc[(3 * a1) * 32 + lane] - lc[(3 * b1) * 32 + lane],
+                                    dy = lc[(3 * a1 + 1) * 32 + lane] - lc[(3 * b1 + 1) * 32 + lane],
+                                    dz = lc[(3 * a1 + 2) * 32 + lane] - lc[(3 * b1 + 2) * 32 + lane];
+                        const float rr = rt.sph_radius[a1] + rt.sph_radius[b1];
+                        sure |= fmaf(dx, dx, fmaf(dy, dy, dz * dz)) <= rr * rr;
+                    }
+                }
+#pragma unroll 1
+                for (int f = 0; f < rt.n_fixed; ++f) {
+                    const uint32_t m = rt.fixed_mask[f];
+                    for (int a1 = 0; a1 < A; ++a1)
+                        if ((m >> a1) & 1u)
+                            sure |= pmp_prim_hit(rt.fixed_kind[f], rt.fixed_R + 9 * f, rt.fixed_t + 3 * f, rt.fixed_half + 3 * f,
+                                                 lc[(3 * a1) * 32 + lane], lc[(3 * a1 + 1) * 32 + lane], lc[(3 * a1 + 2) * 32 + lane],
+                                                 rt.sph_radius[a1]);
+                }
+            }
             // covering spheres of the hull pairs without a clearance table; the INSCRIBED balls of the same spheres
             // (inside hull (+) margin) decide a certain hit right here when two of them overlap
 #pragma unroll 1
-            for (int p = 0; p < ht.n_pairs; ++p) {
+            for (int p = 0; hull_mode && p < ht.n_pairs; ++p) {
                 if (ht.tab_off[p] >= 0) continue;
                 const int h1 = ht.pairs[2 * p], h2 = ht.pairs[2 * p + 1];
                 for (int a1 = ht.sph_lo[h1]; a1 < ht.sph_hi[h1]; ++a1)
@@ -391,7 +417,7 @@ __global__ void __launch_bounds__(32 * PMP_RIGID_WARPS, 4) pmp_rigid_kernel(cons
             }
             // ... and against the obstacles (Bullet's box = core box (half - margin) (+) margin; sphere = point (+) radius)
 #pragma unroll 1
-            for (int f = 0; f < ht.n_fixed_exact; ++f) {
+            for (int f = 0; hull_mode && f < ht.n_fixed_exact; ++f) {
                 const int kind = rt.fixed_kind[f];
                 const float mB = kind == PMP_PRIM_BOX ? ht.fixed_margin : rt.fixed_half[3 * f];
                 float core[3];
@@ -408,7 +434,7 @@ __global__ void __launch_bounds__(32 * PMP_RIGID_WARPS, 4) pmp_rigid_kernel(cons
         }
         // hull pairs with a clearance table are decided by one lookup; only its narrow band goes on to GJK
         bool tab_hit = false;
-        for (int p = 0; p < ht.n_pairs; ++p) {
+        for (int p = 0; hull_mode && p < ht.n_pairs; ++p) {
             if (ht.tab_off[p] < 0) continue;
             const int r = pmp_pair_table(ht, args.pair_tables, p, q_geo(ht.tab_ja[p]), q_geo(ht.tab_jb[p]));
             tab_hit |= r == 2;

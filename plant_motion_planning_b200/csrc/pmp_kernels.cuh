@@ -335,7 +335,7 @@ struct PmpCentresTile {
     }
 };
 
-template <int A, int NSLOT, bool DETAIL, bool CULL, class CPF>
+template <int A, int NSLOT, bool DETAIL, bool CULL, bool DENSE, class CPF>
 __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ wt, int n_stems,
                                                       const float* __restrict__ boxes, int n_boxes,
                                                       const PmpRobotTab& rt, const PmpKernelParams& prm,
@@ -354,7 +354,7 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
         FT[k][0] = FT[k][1] = FT[k][2] = 0.f;
     }
     const bool solve = prm.mode == PMP_MODE_OUR_METHOD;
-    const bool dense = prm.dense != 0;
+    constexpr bool dense = DENSE;     // roofline launches: no data-dependent skipping (prm.dense selects the instantiation)
     const int K = prm.iterations;
     float last = 0.f;
     static_assert(A % 2 == 0, "sphere loops work on pairs");
@@ -797,7 +797,7 @@ struct PmpEdgeArgs {
                                // worlds w = part, part + split, ... (1 otherwise)
     int32_t edge_base;         // index of edge 0 in the caller's batch (the host entry point launches in chunks);
                                // enters the on-device gate's hash so that chunking does not change decisions
-    const uint32_t* rigid_pre; // [E, C] or null: limits | self | fixed decided by the hull pre-pass (bit = step)
+    const uint32_t* rigid_pre; // [E, C] limits | self | fixed decided by the pre-pass kernel (bit = step)
 };
 
 // Edge-batch kernel.  Persistent CTAs; warp = edge, lane = step.
@@ -812,7 +812,7 @@ struct PmpEdgeArgs {
 // that both access patterns are conflict-free -- a lane reading its own pairs as 64-bit words (the world loop) and
 // lane la reading sphere la of another step (the swept bounds).  3 * A * 33 floats per warp.
 #define PMP_TILE_AT(a, k, step) (((((a) >> 1) * 3 + (k)) * 66) + (step) * 2 + ((a) & 1))
-template <int A, int NSLOT, bool WSMEM, bool FIRST>
+template <int A, int NSLOT, bool WSMEM, bool FIRST, bool DENSE = false>
 __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(const PmpEdgeArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PmpRobotTab& rt = *reinterpret_cast<PmpRobotTab*>(smem_raw);
@@ -893,8 +893,9 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
                            : ((at_end && !((circ >> j) & 1u)) ? sm_q1[j] : fmaf(sm_dq[j], t, sm_q0[j]));
             };
             // with hulls, the pre-pass kernel decided limits | self | fixed (one bit per step)
-            bool rigid0 = pmp_config_eval<A>(rt, args.rigid_pre == nullptr, q_geo, q_cmd, c, ee, rt.sph_radius);
-            if (args.rigid_pre) rigid0 = (args.rigid_pre[(size_t)e * C + chunk] >> lane) & 1u;
+            // limits | self | obstacles were decided by the pre-pass kernel (one bit per step)
+            pmp_config_eval<A>(rt, false, q_geo, q_cmd, c, ee, rt.sph_radius);
+            bool rigid0 = (args.rigid_pre[(size_t)e * C + chunk] >> lane) & 1u;
             rigid0 &= live;
             if (!live) {
 #pragma unroll
@@ -989,7 +990,7 @@ __global__ void __launch_bounds__(PMP_EDGE_MAXT, PMP_EDGE_MINB) pmp_edge_kernel(
                 PmpUnitOut u;
                 u.plant_hit = false; u.exceeded = false; u.max_defl = 0.f; u.over = 0.f;
                 if (prm.mode != PMP_MODE_IGNORE_ALL) {
-                    u = pmp_world_eval<A, NSLOT, false, true>(
+                    u = pmp_world_eval<A, NSLOT, false, true, DENSE>(
                         stems_base + (size_t)w * prm.max_stems * PMP_STEM_STRIDE, WSMEM ? sm_nstems[w] : __ldg(args.n_stems + w),
                         args.boxes + (size_t)w * prm.max_boxes * PMP_BOX_STRIDE,
                         prm.mode == PMP_MODE_AVOID_ALL ? args.n_boxes[w] : 0, rt, prm, cpf, nullptr, nullptr, bound);
@@ -1065,7 +1066,7 @@ struct PmpConfigArgs {
     float* theta;              // [B, W, max_stems, 2] or null
     float* ee;                 // [B, 3] or null
     int32_t worlds_per_cta;    // blockIdx.y handles worlds [y * worlds_per_cta, (y + 1) * worlds_per_cta)
-    const uint8_t* rigid_pre;  // [B] or null: limits | self | fixed decided by the hull pre-pass
+    const uint8_t* rigid_pre;  // [B] limits | self | fixed decided by the pre-pass kernel
 };
 
 // Explicit-configuration kernel: thread = configuration, blockIdx.y = chunk of worlds.  Parity / scalar-adapter path.
@@ -1083,8 +1084,8 @@ __global__ void __launch_bounds__(128, 2) pmp_config_kernel(const PmpConfigArgs 
     float c[A][3], ee[3];
     const float* q = args.q + (size_t)bb * D;
     auto qs = [&](int j) { return __ldg(q + j); };
-    bool rigid0 = pmp_config_eval<A>(rt, args.rigid_pre == nullptr, qs, qs, c, ee, rt.sph_radius);
-    if (args.rigid_pre) rigid0 = args.rigid_pre[bb] != 0;
+    pmp_config_eval<A>(rt, false, qs, qs, c, ee, rt.sph_radius);
+    const bool rigid0 = args.rigid_pre[bb] != 0;
     if (!live) {
 #pragma unroll
         for (int a = 0; a < A; ++a) { c[a][0] = PMP_FAR; c[a][1] = PMP_FAR; c[a][2] = PMP_FAR; }
@@ -1104,7 +1105,7 @@ __global__ void __launch_bounds__(128, 2) pmp_config_kernel(const PmpConfigArgs 
         float* tptr = (live && args.theta) ? args.theta + bw * P * 2 : nullptr;
         const int ns = args.n_stems[w];
         if (prm.mode != PMP_MODE_IGNORE_ALL) {
-            u = pmp_world_eval<A, NSLOT, true, false>(args.stems + (size_t)w * P * PMP_STEM_STRIDE, ns,
+            u = pmp_world_eval<A, NSLOT, true, false, false>(args.stems + (size_t)w * P * PMP_STEM_STRIDE, ns,
                                                args.boxes + (size_t)w * prm.max_boxes * PMP_BOX_STRIDE,
                                                prm.mode == PMP_MODE_AVOID_ALL ? args.n_boxes[w] : 0, rt, prm, cpf, dptr, tptr);
         } else {
