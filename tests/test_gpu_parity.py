@@ -363,6 +363,29 @@ def test_device_gate_matches_host_recomputation(ctx):
     assert abs((h < np.uint32(int(0.95 * 2 ** 32))).mean() - 0.95) < 0.005
 
 
+def test_device_gate_does_not_depend_on_sharding(ctx):
+    """The on-device gate hashes the GLOBAL edge index (edge_base): shards of a batch -- what ShardedEdgeChecker hands
+    every rank -- decide exactly like the unsplit batch, and the chunked host entry point like the device one."""
+    from plant_motion_planning_b200 import EdgeCheckConfig, EdgeChecker
+    from plant_motion_planning_b200.distributed import shard_bounds
+    from plant_motion_planning_b200.workloads import random_edges
+    torch, model, worlds = ctx["torch"], ctx["model"], ctx["worlds"]
+    q0, q1 = random_edges(model, 1537, seed=23)
+    chk = EdgeChecker(model, worlds, EdgeCheckConfig(device_gate_seed=9, gate_probability=0.5))
+    a, b = torch.from_numpy(q0).cuda(), torch.from_numpy(q1).cuda()
+    whole = chk.validate_edges(a, b).first_hit.cpu().numpy()
+    for ws in (2, 3):
+        parts = []
+        for r in range(ws):
+            lo, hi = shard_bounds(len(q0), r, ws)
+            parts.append(chk.validate_edges(a[lo:hi], b[lo:hi], edge_base=lo).first_hit.cpu().numpy())
+        assert np.array_equal(np.concatenate(parts), whole)
+    lo, hi = shard_bounds(len(q0), 1, 2)
+    assert not np.array_equal(chk.validate_edges(a[lo:hi], b[lo:hi]).first_hit.cpu().numpy(), whole[lo:hi]), \
+        "without edge_base the shard must see other gate draws (else this test proves nothing)"
+    assert np.array_equal(chk.validate_edges_host(q0, q1)["first_hit"], whole)
+
+
 def test_non_finite_inputs_are_rejected_not_crashed(ctx):
     torch, chk = ctx["torch"], ctx["chk"]
     q0 = np.zeros((4, 7), np.float32)
