@@ -80,9 +80,14 @@ def dense_chain(checker, tree: dict, chain: Sequence[int]) -> Tuple[np.ndarray, 
 
 def batched_rrt_connect(checker, start: Sequence[float], goal: Sequence[float], *, batch: int = 256,
                         max_iterations: int = 200, seed: int = 0, capacity: Optional[int] = None,
-                        max_steps: Optional[int] = None) -> Optional[BatchedPlan]:
+                        max_steps: Optional[int] = None, sync_every: int = 4) -> Optional[BatchedPlan]:
     """Plan start -> goal; returns None if ``max_iterations`` batches did not connect the trees.
-    Raises ValueError if start or goal is invalid (the reference exits there, pybullet_tools/utils.py:4364-4380)."""
+    Raises ValueError if start or goal is invalid (the reference exits there, pybullet_tools/utils.py:4364-4380).
+    ``sync_every``: the host reads the 16-byte termination records of up to this many iterations at once (1, 1, 2, 4,
+    ... iterations per read: easy scenes connect in the first batch and must not pay for queued ones), so the launches
+    of the next iterations are queued while the current ones run.  The trees meet at the first connecting iteration
+    either way; at most ``sync_every - 1`` further batches are appended to the trees before the host notices, and
+    the returned path does not depend on it."""
     robot = checker.robot
     start32 = np.asarray(start, dtype=np.float32)
     goal32 = np.asarray(goal, dtype=np.float32)
@@ -101,20 +106,41 @@ def batched_rrt_connect(checker, start: Sequence[float], goal: Sequence[float], 
     log: List[dict] = []
     hit = None
     it = 0
-    for it in range(1, max_iterations + 1):
+    sync_every = max(1, int(sync_every))
+    chunk, reads = 1, 0                                 # iterations per host read: 1, 1, 2, 4, ... <= sync_every
+    pending = []                                        # (iteration, ext_a, ext_b, tree a, tree b) not yet looked at
+    for nxt in range(1, max_iterations + 1):
         targets = sample_targets(robot, rng, batch)
         targets[0] = roots[id(tb)]                      # one proposal per batch aims at the other root
         ext_a = checker.tree_extend(ta, targets, max_steps)
         ext_b = checker.tree_extend(tb, ext_a.new_config, max_steps)     # rows without a new node are NaN: inert
-        sa, sb = _np(ext_a.stats), _np(ext_b.stats)     # the only synchronisation of the iteration
-        log.append({"iteration": it, "appended": (int(sa[0]), int(sb[0])), "connected": int(sb[1])})
-        if sa[3] or sb[3]:
-            raise RuntimeError("tree capacity exhausted")
-        if sb[1] > 0:
-            e = int(sb[2])
-            hit = (int(_np(ext_a.new_index)[e]), int(_np(ext_b.new_index)[e]))
-            break
+        pending.append((nxt, ext_a, ext_b, ta, tb))
         ta, tb = tb, ta
+        if len(pending) < chunk and nxt < max_iterations:
+            continue
+        reads += 1
+        if reads >= 2:
+            chunk = min(2 * chunk, sync_every)
+        # the only synchronisation: 2 x 16 bytes per pending iteration in one copy
+        if hasattr(pending[0][1].stats, "detach"):
+            import torch
+            stats = _np(torch.stack([torch.stack([p[1].stats, p[2].stats]) for p in pending]))
+        else:
+            stats = np.stack([np.stack([np.asarray(p[1].stats), np.asarray(p[2].stats)]) for p in pending])
+        for (j, ea, eb, tja, tjb), (sa, sb) in zip(pending, stats):
+            log.append({"iteration": j, "appended": (int(sa[0]), int(sb[0])), "connected": int(sb[1])})
+            if sa[3] or sb[3]:
+                raise RuntimeError("tree capacity exhausted")
+            if sb[1] > 0:
+                e = int(sb[2])
+                hit = (int(_np(ea.new_index)[e]), int(_np(eb.new_index)[e]))
+                it, ta, tb = j, tja, tjb
+                break
+        pending = []
+        if hit is not None:
+            break
+    else:
+        it = max_iterations
     if hit is None:
         return None
     da, db = ta.download(), tb.download()

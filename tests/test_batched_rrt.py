@@ -104,9 +104,9 @@ def test_batched_planner_on_oracle_backend(name):
     assert plan is not None
     P = _check_plan(plan, ck, robot, S.START, S.GOAL)
     assert not ck.check_configs_host(P.astype(np.float32), detail=False)["flags"].any()
-    again = batched_rrt_connect(ck, S.START, S.GOAL, batch=16, max_iterations=40, seed=0)
-    assert again.path == plan.path and again.iterations == plan.iterations        # deterministic for a seed
-    assert plan.edges_validated == 2 * 16 * plan.iterations
+    again = batched_rrt_connect(ck, S.START, S.GOAL, batch=16, max_iterations=40, seed=0, sync_every=1)
+    assert again.path == plan.path and again.iterations == plan.iterations        # deterministic for a seed, and
+    assert plan.edges_validated == 2 * 16 * plan.iterations                       # independent of the sync cadence
 
 
 def test_batched_planner_rejects_invalid_ends_and_gives_up():
@@ -260,8 +260,8 @@ def test_batched_planner_on_gpu_is_valid_under_the_oracle(gpu, name):
     oracle_flags = OracleChecker(robot, worlds, ec).check_configs_host(P.astype(np.float32), detail=False)["flags"]
     assert oracle_flags.mean() <= 0.005
     assert not chk.check_configs_host(P.astype(np.float32), detail=False)["flags"].any()
-    again = batched_rrt_connect(chk, S.START, S.GOAL, batch=256, max_iterations=50, seed=0)
-    assert again.path == plan.path
+    again = batched_rrt_connect(chk, S.START, S.GOAL, batch=256, max_iterations=50, seed=0, sync_every=1)
+    assert again.path == plan.path and again.iterations == plan.iterations
 
 
 def test_extend_many_equals_per_edge_gate_replay():
