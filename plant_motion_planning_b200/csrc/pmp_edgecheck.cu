@@ -364,9 +364,12 @@ static int launch_rigid(pmp_ctx* ctx, const float* q0, const float* q1, int32_t 
     a.q = q; a.B = B; a.rigid_flags = rigid_flags;
     const long long items = q ? (B + 31) / 32 : (long long)E * ((max_steps + 31) / 32);
     long long grid = (items + PMP_RIGID_WARPS - 1) / PMP_RIGID_WARPS;
-    const long long cap = (long long)ctx->sm_count * 8;
+    const long long cap = (long long)ctx->sm_count * PMP_RIGID_MINB;            // the resident CTAs; items are claimed dynamically
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
+    if (!ctx->d_work_counter) CK(cudaMalloc(&ctx->d_work_counter, 64 * sizeof(int32_t)));
+    a.work_counter = ctx->d_work_counter + (ctx->work_slot++ & 63u);
+    CK(cudaMemsetAsync(a.work_counter, 0, sizeof(int32_t), st));
     const size_t smem = sizeof(float) * (size_t)PMP_RIGID_WARPS * 3 * ctx->h_robot.n_spheres * 32;   // <= 48 KB
     static int optin[16] = {0};
     if (!optin[ctx->device & 15]) {

@@ -61,22 +61,19 @@ __device__ __noinline__ PmpV3 pmp_gjk_support(const PmpGjkShape& S, PmpV3 d) {
     float vx, vy, vz;
     if (S.verts) {
         const int lane = threadIdx.x & 31;
-        float best = -3.0e38f;
-        int bi = 0;
+        float best = -3.0e38f, bx = 0.f, by = 0.f, bz = 0.f;
 #pragma unroll 4
         for (int i = lane; i < S.n; i += 32) {
             const float4 v = __ldg(S.verts + i);
             const float val = fmaf(v.x, lx, fmaf(v.y, ly, v.z * lz));
-            if (val > best) { best = val; bi = i; }
+            if (val > best) { best = val; bx = v.x; by = v.y; bz = v.z; }
         }
-        // order-preserving map float -> uint, one warp max, the first lane holding it publishes its vertex index
+        // order-preserving map float -> uint, one warp max, the first lane holding it publishes its vertex
         const uint32_t u = __float_as_uint(best);
         const uint32_t key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
         const uint32_t mx = __reduce_max_sync(PMP_FULL, key);
         const int src = __ffs(__ballot_sync(PMP_FULL, key == mx)) - 1;
-        bi = __shfl_sync(PMP_FULL, bi, src);
-        const float4 v = __ldg(S.verts + bi);
-        vx = v.x; vy = v.y; vz = v.z;
+        vx = __shfl_sync(PMP_FULL, bx, src); vy = __shfl_sync(PMP_FULL, by, src); vz = __shfl_sync(PMP_FULL, bz, src);
     } else {
         vx = copysignf(S.half[0], lx); vy = copysignf(S.half[1], ly); vz = copysignf(S.half[2], lz);
     }
@@ -215,6 +212,7 @@ struct PmpRigidArgs {
     const float* q;
     int32_t B;
     uint8_t* rigid_flags;
+    int32_t* work_counter;     // next unclaimed warp item (zeroed before the launch)
 };
 
 // Clearance-table lookup of hull pair p at joint values (qa, qb): 1 = certainly free, 2 = certainly colliding, 0 = ask GJK.
@@ -276,7 +274,10 @@ __global__ void __launch_bounds__(128) pmp_pair_table_kernel(const PmpPairTableA
 }
 
 #define PMP_RIGID_WARPS 4
-__global__ void __launch_bounds__(32 * PMP_RIGID_WARPS, 4) pmp_rigid_kernel(const PmpRigidArgs args) {
+#ifndef PMP_RIGID_MINB
+#define PMP_RIGID_MINB 4
+#endif
+__global__ void __launch_bounds__(32 * PMP_RIGID_WARPS, PMP_RIGID_MINB) pmp_rigid_kernel(const PmpRigidArgs args) {
     __shared__ __align__(16) PmpRobotTab rt;
     __shared__ __align__(16) PmpHullTab ht;
     __shared__ double sm_sq_all[PMP_RIGID_WARPS][PMP_MAX_DOF];
@@ -302,12 +303,36 @@ __global__ void __launch_bounds__(32 * PMP_RIGID_WARPS, 4) pmp_rigid_kernel(cons
     float* qL = sm_qL_all[wid];
     float* lc = sm_lane_centres + (size_t)wid * 3 * rt.n_spheres * 32;
     const int D = rt.dof, A = rt.n_spheres, H = hull_mode ? ht.n_hulls : 0;
+    // Ball around all SPHERE obstacles (the block's eight corner contact spheres): steps whose covering spheres stay
+    // clear of it skip those obstacles in the broad phase altogether (exact: the ball contains them).
+    float gcx = 0.f, gcy = 0.f, gcz = 0.f, gR = -1.f;
+    if (hull_mode) {
+        int cnt = 0;
+        for (int f = 0; f < ht.n_fixed_exact; ++f)
+            if (rt.fixed_kind[f] == PMP_PRIM_SPHERE) { gcx += rt.fixed_t[3 * f]; gcy += rt.fixed_t[3 * f + 1]; gcz += rt.fixed_t[3 * f + 2]; ++cnt; }
+        if (cnt) {
+            const float inv = 1.f / (float)cnt;
+            gcx *= inv; gcy *= inv; gcz *= inv;
+            for (int f = 0; f < ht.n_fixed_exact; ++f)
+                if (rt.fixed_kind[f] == PMP_PRIM_SPHERE) {
+                    const float dx = rt.fixed_t[3 * f] - gcx, dy = rt.fixed_t[3 * f + 1] - gcy, dz = rt.fixed_t[3 * f + 2] - gcz;
+                    gR = fmaxf(gR, sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz))) + rt.fixed_half[3 * f]);
+                }
+            gR = gR * 1.00001f + 1.0e-5f;
+        }
+    }
     const bool edge_mode = args.q == nullptr;
     const int C = (args.max_steps + 31) >> 5;
     const int n_items = edge_mode ? args.E * C : (args.B + 31) >> 5;
     const uint32_t circ = rt.circular_mask;
     const bool lag = prm.lag_kappa > 0.f;
-    for (int item = blockIdx.x * PMP_RIGID_WARPS + wid; item < n_items; item += gridDim.x * PMP_RIGID_WARPS) {
+    // Items are claimed one at a time: an item whose steps reach the narrow phase costs tens of times one that does not,
+    // and with a static stride the CTAs' warps finished far apart (8.5 of 16 resident warps active on average).
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(args.work_counter, 1);
+        item = __shfl_sync(PMP_FULL, item, 0);
+        if (item >= n_items) break;
         bool live, at_end = false;
         float t = 0.f, tg = 0.f;
         int cfg = 0;
@@ -416,9 +441,19 @@ __global__ void __launch_bounds__(32 * PMP_RIGID_WARPS, 4) pmp_rigid_kernel(cons
                     }
             }
             // ... and against the obstacles (Bullet's box = core box (half - margin) (+) margin; sphere = point (+) radius)
+            bool grp = false;
+            if (hull_mode && gR >= 0.f) {
+                for (int a1 = 0; a1 < A; ++a1) {
+                    const float dx = lc[(3 * a1) * 32 + lane] - gcx, dy = lc[(3 * a1 + 1) * 32 + lane] - gcy, dz = lc[(3 * a1 + 2) * 32 + lane] - gcz;
+                    const float rr = rt.sph_radius_outer[a1] + gR;
+                    grp |= fmaf(dx, dx, fmaf(dy, dy, dz * dz)) <= rr * rr;
+                }
+                grp = __any_sync(PMP_FULL, grp);
+            }
 #pragma unroll 1
             for (int f = 0; hull_mode && f < ht.n_fixed_exact; ++f) {
                 const int kind = rt.fixed_kind[f];
+                if (kind == PMP_PRIM_SPHERE && !grp) continue;
                 const float mB = kind == PMP_PRIM_BOX ? ht.fixed_margin : rt.fixed_half[3 * f];
                 float core[3];
 #pragma unroll
