@@ -197,8 +197,9 @@ def run_reference(args, rank: int) -> None:
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "CPU restatement (oracle/edgecheck_oracle.c built in float32, -O3 -march=native, pthreads over edges, the "
-                "same per-stem early exit as the GPU path), not PyBullet: pybullet is not installable here",
+        "note": "CPU restatement (oracle/edgecheck_oracle.c built in float32 with its sphere loop vectorised -- AVX2 with "
+                "-march=native -fopenmp-simd --, pthreads over edges, the same per-stem early exit as the GPU path), not "
+                "PyBullet: pybullet is not installable here",
     }
     print(json.dumps(line), flush=True)
 
@@ -480,7 +481,8 @@ def main() -> None:
         ref = co64.validate_edges(q0[:n64], q1[:n64], max_steps=args.edge_steps, want_masks=True)
         el64 = time.perf_counter() - t0
         cpu_baseline = {"value": n * args.edge_steps * W / el, "unit": UNIT, "cores": co32.max_threads, "kind": "port",
-                        "arithmetic": "float32 (oracle/edgecheck_oracle.c built with -DPMP_REAL=float, -O3 -march=native, pthreads)",
+                        "arithmetic": "float32, sphere loop vectorised (oracle/edgecheck_oracle.c built with -DPMP_REAL=float -DPMP_SIMD_BASELINE "
+                                      "-O3 -march=native -fopenmp-simd: AVX2 on this host), pthreads over edges",
                         "sample": f"first {n} edges of the same sweep x {args.edge_steps} steps x {W} worlds, {el:.1f} s",
                         "single_core_value": n1 * args.edge_steps * W / el1,
                         "single_core_sample": f"first {n1} edges, {el1:.1f} s",

@@ -290,6 +290,32 @@ static void world_eval(const pmp_robot_desc* rb, const pmp_world_desc* wd, const
             mat_mul(Rv, M, Rl);
             real Hxx = 0, Hxy = 0, Hyy = 0, gx = 0, gy = 0, S = 0;
             int any = 0;
+#ifdef PMP_SIMD_BASELINE
+            /* The timed float32 baseline: the same sums, branch-free over the spheres so that the compiler vectorises
+             * the loop (AVX2 / AVX-512 with -march=native -fopenmp-simd); a sphere that does not penetrate adds zeros. */
+            const real tvx = tv[0], tvy = tv[1], tvz = tv[2];
+            const real r0 = Rl[0], r1 = Rl[1], r2 = Rl[2], r3 = Rl[3], r4 = Rl[4], r5 = Rl[5], r6 = Rl[6], r7 = Rl[7], r8 = Rl[8];
+            const real (*cc)[3] = cf->c;
+            const float* rad = rb->sph_radius;
+#pragma omp simd reduction(+ : Hxx, Hxy, Hyy, gx, gy, S) reduction(| : any)
+            for (int a = 0; a < A; ++a) {
+                const real wx = cc[a][0] - tvx, wy = cc[a][1] - tvy, wz = cc[a][2] - tvz;
+                const real pfx = r0 * wx + r3 * wy + r6 * wz, pfy = r1 * wx + r4 * wy + r7 * wz, pfz = r2 * wx + r5 * wy + r8 * wz;
+                const real pz = pfz - zc;
+                const real qx = pfx < -hw ? -hw : (pfx > hw ? hw : pfx), qy = pfy < -hw ? -hw : (pfy > hw ? hw : pfy),
+                           qz = pz < -hh ? -hh : (pz > hh ? hh : pz);
+                const real dx = pfx - qx, dy = pfy - qy, dz = pz - qz;
+                const real dist = sqrtf(dx * dx + dy * dy + dz * dz);
+                const real pe = (real)rad[a] + mg - dist;
+                const real pen = pe > 0 ? pe : 0;
+                any |= pe > 0;
+                const real inv = (real)1.0 / (dist > (real)1e-12 ? dist : (real)1e-12);
+                const real mx = dy * pfz - dz * pfy, my = dz * pfx - dx * pfz, mz = dx * pfy - dy * pfx;
+                const real Jx = inv * (cy * mx + sy * mz), Jy = inv * my;
+                Hxx += pen * Jx * Jx; Hxy += pen * Jx * Jy; Hyy += pen * Jy * Jy;
+                gx += pen * pen * Jx; gy += pen * pen * Jy; S += pen;
+            }
+#else
             for (int a = 0; a < A; ++a) {
                 const real wv[3] = {cf->c[a][0] - tv[0], cf->c[a][1] - tv[1], cf->c[a][2] - tv[2]};
                 real pf[3];
@@ -307,6 +333,7 @@ static void world_eval(const pmp_robot_desc* rb, const pmp_world_desc* wd, const
                 Hxx += pen * Jx * Jx; Hxy += pen * Jx * Jy; Hyy += pen * Jy * Jy;
                 gx += pen * pen * Jx; gy += pen * pen * Jy; S += pen;
             }
+#endif
             if (it == 0) touch = any;
             if (!solve) { if (any) out->plant_hit = 1; break; }
             if (!touch || !(S > 0)) { if (prm->dense) continue; else break; }
