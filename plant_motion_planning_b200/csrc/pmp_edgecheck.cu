@@ -362,14 +362,23 @@ static int launch_rigid(pmp_ctx* ctx, const float* q0, const float* q1, int32_t 
     a.pair_tables = ctx->d_pair_tables;
     a.q0 = q0; a.q1 = q1; a.E = E; a.max_steps = max_steps; a.backward = backward ? 1 : 0; a.rigid_pre = rigid_pre;
     a.q = q; a.B = B; a.rigid_flags = rigid_flags;
-    const long long items = q ? (B + 31) / 32 : (long long)E * ((max_steps + 31) / 32);
+    // configuration mode: as few configurations per warp item as keeps every SM busy
+    a.cfgs_per_item = 32;
+    if (q) {
+        const long long warps = (long long)ctx->sm_count * PMP_RIGID_MINB * PMP_RIGID_WARPS;
+        a.cfgs_per_item = B >= 32 * warps ? 32 : (B >= 8 * warps ? 8 : (B >= 2 * warps ? 2 : 1));
+    }
+    const long long items = q ? (B + a.cfgs_per_item - 1) / a.cfgs_per_item : (long long)E * ((max_steps + 31) / 32);
     long long grid = (items + PMP_RIGID_WARPS - 1) / PMP_RIGID_WARPS;
     const long long cap = (long long)ctx->sm_count * PMP_RIGID_MINB;            // the resident CTAs; items are claimed dynamically
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
-    if (!ctx->d_work_counter) CK(cudaMalloc(&ctx->d_work_counter, 64 * sizeof(int32_t)));
-    a.work_counter = ctx->d_work_counter + (ctx->work_slot++ & 63u);
-    CK(cudaMemsetAsync(a.work_counter, 0, sizeof(int32_t), st));
+    a.work_counter = nullptr;
+    if (!q) {               // edge mode: items differ by an order of magnitude in cost, claim them dynamically
+        if (!ctx->d_work_counter) CK(cudaMalloc(&ctx->d_work_counter, 64 * sizeof(int32_t)));
+        a.work_counter = ctx->d_work_counter + (ctx->work_slot++ & 63u);
+        CK(cudaMemsetAsync(a.work_counter, 0, sizeof(int32_t), st));
+    }                       // configuration mode strides statically over the grid: no counter to clear on the scalar path
     const size_t smem = sizeof(float) * (size_t)PMP_RIGID_WARPS * 3 * ctx->h_robot.n_spheres * 32;   // <= 48 KB
     static int optin[16] = {0};
     if (!optin[ctx->device & 15]) {

@@ -212,7 +212,10 @@ struct PmpRigidArgs {
     const float* q;
     int32_t B;
     uint8_t* rigid_flags;
-    int32_t* work_counter;     // next unclaimed warp item (zeroed before the launch)
+    int32_t* work_counter;     // next unclaimed warp item (zeroed before the launch); null: static stride over the grid
+    int32_t cfgs_per_item;     // configuration mode: configurations per warp item (1 .. 32).  Small batches (the
+                               // scalar collision_fn adapter) use few, so that their narrow-phase steps -- resolved one
+                               // at a time by a whole warp -- spread over many warps instead of queueing in one
 };
 
 // Clearance-table lookup of hull pair p at joint values (qa, qb): 1 = certainly free, 2 = certainly colliding, 0 = ask GJK.
@@ -323,15 +326,20 @@ __global__ void __launch_bounds__(32 * PMP_RIGID_WARPS, PMP_RIGID_MINB) pmp_rigi
     }
     const bool edge_mode = args.q == nullptr;
     const int C = (args.max_steps + 31) >> 5;
-    const int n_items = edge_mode ? args.E * C : (args.B + 31) >> 5;
+    const int cpi = args.cfgs_per_item;
+    const int n_items = edge_mode ? args.E * C : (args.B + cpi - 1) / cpi;
     const uint32_t circ = rt.circular_mask;
     const bool lag = prm.lag_kappa > 0.f;
     // Items are claimed one at a time: an item whose steps reach the narrow phase costs tens of times one that does not,
     // and with a static stride the CTAs' warps finished far apart (8.5 of 16 resident warps active on average).
-    for (;;) {
+    for (int round = 0;; ++round) {
         int item = 0;
-        if (lane == 0) item = atomicAdd(args.work_counter, 1);
-        item = __shfl_sync(PMP_FULL, item, 0);
+        if (args.work_counter) {
+            if (lane == 0) item = atomicAdd(args.work_counter, 1);
+            item = __shfl_sync(PMP_FULL, item, 0);
+        } else {
+            item = (blockIdx.x + round * gridDim.x) * PMP_RIGID_WARPS + wid;
+        }
         if (item >= n_items) break;
         bool live, at_end = false;
         float t = 0.f, tg = 0.f;
@@ -352,8 +360,8 @@ __global__ void __launch_bounds__(32 * PMP_RIGID_WARPS, PMP_RIGID_MINB) pmp_rigi
             at_end = (num == n);
             tg = pmp_lagged_t(prm, i, t, inv_n);
         } else {
-            cfg = item * 32 + lane;
-            live = cfg < args.B;
+            cfg = item * cpi + lane;
+            live = lane < cpi && cfg < args.B;
             if (!live) cfg = 0;
         }
         auto q_cmd = [&](int j) {
