@@ -386,6 +386,33 @@ def test_device_gate_does_not_depend_on_sharding(ctx):
     assert np.array_equal(chk.validate_edges_host(q0, q1)["first_hit"], whole)
 
 
+def test_per_kernel_timing_through_the_c_abi(ctx):
+    """pmp_set_kernel_timing / pmp_get_kernel_times: what bench.py's roofline leg reads (CUDA events recorded by the
+    library on the launching stream, around the pre-pass and around the edge kernel)."""
+    from plant_motion_planning_b200.workloads import random_edges
+    torch, chk, model = ctx["torch"], ctx["chk"], ctx["model"]
+    q0, q1 = random_edges(model, 4096, seed=3)
+    a, b = torch.from_numpy(q0).cuda(), torch.from_numpy(q1).cuda()
+    with pytest.raises(RuntimeError):
+        chk.kernel_times()                      # timing is off by default
+    chk.set_kernel_timing(True)
+    try:
+        ref = chk.validate_edges(a, b)
+        rigid_ms, edge_ms = chk.kernel_times()
+        assert 0.0 < rigid_ms < 100.0 and 0.0 < edge_ms < 1000.0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        chk.validate_edges(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        r2, k2 = chk.kernel_times()
+        assert r2 + k2 <= e0.elapsed_time(e1) * 1.05 + 0.05      # the two kernels are the call
+    finally:
+        chk.set_kernel_timing(False)
+    again = chk.validate_edges(a, b)
+    assert torch.equal(again.first_hit, ref.first_hit)
+
+
 def test_non_finite_inputs_are_rejected_not_crashed(ctx):
     torch, chk = ctx["torch"], ctx["chk"]
     q0 = np.zeros((4, 7), np.float32)
