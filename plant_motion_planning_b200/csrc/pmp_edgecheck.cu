@@ -356,8 +356,10 @@ extern "C" int pmp_set_robot_hulls(pmp_ctx* ctx, const pmp_hull_desc* h) {
 
 // hull pre-pass: limits | self | fixed of every step (edge mode) or configuration, on `stream`
 static int launch_rigid(pmp_ctx* ctx, const float* q0, const float* q1, int32_t E, int32_t max_steps, int32_t backward,
-                        uint32_t* rigid_pre, const float* q, int32_t B, uint8_t* rigid_flags, cudaStream_t st) {
+                        uint32_t* rigid_pre, const float* q, int32_t B, uint8_t* rigid_flags, cudaStream_t st,
+                        bool first_bit_only = false) {
     PmpRigidArgs a;
+    a.first_bit_only = first_bit_only ? 1 : 0;
     a.robot = ctx->d_robot; a.hulls = ctx->has_hulls ? ctx->d_hulls : nullptr; a.hull_verts = ctx->d_hull_verts; a.prm = ctx->prm;
     a.pair_tables = ctx->d_pair_tables;
     a.q0 = q0; a.q1 = q1; a.E = E; a.max_steps = max_steps; a.backward = backward ? 1 : 0; a.rigid_pre = rigid_pre;
@@ -368,7 +370,16 @@ static int launch_rigid(pmp_ctx* ctx, const float* q0, const float* q1, int32_t 
         const long long warps = (long long)ctx->sm_count * PMP_RIGID_MINB * PMP_RIGID_WARPS;
         a.cfgs_per_item = B >= 32 * warps ? 32 : (B >= 8 * warps ? 8 : (B >= 2 * warps ? 2 : 1));
     }
-    const long long items = q ? (B + a.cfgs_per_item - 1) / a.cfgs_per_item : (long long)E * ((max_steps + 31) / 32);
+    // edge mode: short items for small batches (see PmpRigidArgs::steps_per_item)
+    a.steps_per_item = 32;
+    if (!q) {
+        const long long warps = (long long)ctx->sm_count * PMP_RIGID_MINB * PMP_RIGID_WARPS;
+        const long long words = (long long)E * ((max_steps + 31) / 32);
+        a.steps_per_item = words >= 8 * warps ? 32 : (words >= 2 * warps ? 8 : 4);
+        if (a.steps_per_item < 32) CK(cudaMemsetAsync(rigid_pre, 0, sizeof(uint32_t) * (size_t)words, st));
+    }
+    const long long items = q ? (B + a.cfgs_per_item - 1) / a.cfgs_per_item
+                              : (long long)E * ((max_steps + 31) / 32) * (32 / a.steps_per_item);
     long long grid = (items + PMP_RIGID_WARPS - 1) / PMP_RIGID_WARPS;
     const long long cap = (long long)ctx->sm_count * PMP_RIGID_MINB;            // the resident CTAs; items are claimed dynamically
     if (grid > cap) grid = cap;
@@ -597,7 +608,9 @@ static int validate_edges_impl(pmp_ctx* ctx, const float* q0, const float* q1, i
             pre = (uint32_t*)ctx->d_rigid_scratch;
         }
         if (ctx->timing) CK(cudaEventRecord(ctx->ev[0], (cudaStream_t)stream));
-        rc = launch_rigid(ctx, q0, q1, E, max_steps, backward, pre, nullptr, 0, nullptr, (cudaStream_t)stream);
+        // without a rigid step mask in the outputs only the first rigid bit of every 32-step word is ever read
+        rc = launch_rigid(ctx, q0, q1, E, max_steps, backward, pre, nullptr, 0, nullptr, (cudaStream_t)stream,
+                          /*first_bit_only=*/rigid_mask == nullptr);
         if (rc) return rc;
         if (ctx->timing) { CK(cudaEventRecord(ctx->ev[1], (cudaStream_t)stream)); ctx->timed_rigid = true; }
         a.rigid_pre = pre;

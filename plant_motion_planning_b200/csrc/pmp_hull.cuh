@@ -213,6 +213,15 @@ struct PmpRigidArgs {
     int32_t B;
     uint8_t* rigid_flags;
     int32_t* work_counter;     // next unclaimed warp item (zeroed before the launch); null: static stride over the grid
+    int32_t first_bit_only;    // edge mode: 1 = the caller reads only the FIRST set bit of every 32-step word (no rigid
+                               // step mask was requested: first_hit = first violating step, and every other output is
+                               // independent of the rigid bits), so steps after the first certain hit of a word skip the
+                               // narrow phase and the word may lack later bits
+    int32_t steps_per_item;    // edge mode: interpolation steps per warp item (32, 8 or 4).  Small batches (a planner's few
+                               // hundred proposals) use short items: the narrow phase resolves an item's surviving steps
+                               // one after the other, and one 32-step item gliding along an obstacle would otherwise
+                               // be the whole kernel's makespan.  Items shorter than 32 steps OR their bits into the
+                               // word (which the host zeroes first).
     int32_t cfgs_per_item;     // configuration mode: configurations per warp item (1 .. 32).  Small batches (the
                                // scalar collision_fn adapter) use few, so that their narrow-phase steps -- resolved one
                                // at a time by a whole warp -- spread over many warps instead of queueing in one
@@ -327,7 +336,8 @@ __global__ void __launch_bounds__(32 * PMP_RIGID_WARPS, PMP_RIGID_MINB) pmp_rigi
     const bool edge_mode = args.q == nullptr;
     const int C = (args.max_steps + 31) >> 5;
     const int cpi = args.cfgs_per_item;
-    const int n_items = edge_mode ? args.E * C : (args.B + cpi - 1) / cpi;
+    const int spi = edge_mode ? args.steps_per_item : 32, subs = 32 / spi;
+    const int n_items = edge_mode ? args.E * C * subs : (args.B + cpi - 1) / cpi;
     const uint32_t circ = rt.circular_mask;
     const bool lag = prm.lag_kappa > 0.f;
     // Items are claimed one at a time: an item whose steps reach the narrow phase costs tens of times one that does not,
@@ -345,15 +355,16 @@ __global__ void __launch_bounds__(32 * PMP_RIGID_WARPS, PMP_RIGID_MINB) pmp_rigi
         float t = 0.f, tg = 0.f;
         int cfg = 0;
         if (edge_mode) {
-            const int e = item / C, chunk = item - e * C;
+            const int word = item / subs, sub = item - word * subs;
+            const int e = word / C, chunk = word - e * C;
             const int n = pmp_edge_setup(rt, prm, args.q0, args.q1, e, lane, sm_sq, sm_q0, sm_q1, sm_dq);
             const int nc = min(n, args.max_steps);
-            if (chunk * 32 >= nc) {
-                if (lane == 0) args.rigid_pre[item] = 0u;
+            if (chunk * 32 + sub * spi >= nc) {
+                if (lane == 0 && subs == 1) args.rigid_pre[word] = 0u;
                 continue;
             }
-            const int i = chunk * 32 + lane;
-            live = i < nc;
+            const int i = chunk * 32 + sub * spi + lane;
+            live = lane < spi && i < nc;
             const int num = i + (args.backward ? 0 : 1);
             const float inv_n = 1.0f / (float)n;
             t = (float)num * inv_n;
@@ -485,6 +496,11 @@ __global__ void __launch_bounds__(32 * PMP_RIGID_WARPS, PMP_RIGID_MINB) pmp_rigi
         }
         bool rigid = live && (lim_hit || tab_hit || sure);
         uint32_t todo = __ballot_sync(PMP_FULL, live && !lim_hit && !tab_hit && !sure && near);
+        const bool first_bit_only = edge_mode && args.first_bit_only != 0;
+        if (first_bit_only) {
+            const uint32_t known = __ballot_sync(PMP_FULL, rigid);
+            if (known) todo &= (1u << (__ffs(known) - 1)) - 1u;          // only steps before the first certain hit matter
+        }
         PMP_STAT(0, 1); PMP_STAT(1, __popc(todo)); PMP_STAT(5, __popc(__ballot_sync(PMP_FULL, rigid)));
         // ---- narrow phase: one surviving step at a time, by the whole warp ----
         while (todo) {
@@ -605,10 +621,14 @@ __global__ void __launch_bounds__(32 * PMP_RIGID_WARPS, PMP_RIGID_MINB) pmp_rigi
             }
             if (lane == L) rigid = hit;
             PMP_STAT(6, hit ? 1 : 0);
+            if (first_bit_only && hit) break;                              // later steps of the word cannot be first
         }
         if (edge_mode) {
             const uint32_t m = __ballot_sync(PMP_FULL, rigid);
-            if (lane == 0) args.rigid_pre[item] = m;
+            if (lane == 0) {
+                if (subs == 1) args.rigid_pre[item] = m;
+                else if (m) atomicOr(args.rigid_pre + item / subs, m << ((item % subs) * spi));
+            }
         } else if (live) {
             args.rigid_flags[cfg] = rigid ? 1 : 0;
         }
