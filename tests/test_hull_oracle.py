@@ -179,3 +179,22 @@ def test_script_seed19_start_touches_the_fourth_plant():
     sc = H.HullScene(H.HullArm(), boxes)
     d = sc.distances(np.array([START]), sc.fixed_pairs, far=1.0)
     assert -0.001 < d.min() < -0.0005          # 0.7 mm inside the margins, even before gravity sag
+
+
+@pytest.mark.gpu
+def test_gpu_rigid_flags_equal_the_independent_hull_oracle_at_scale():
+    """50 000 random configurations: the CUDA hull pre-pass (float32 GJK, clearance tables, covering / inscribed balls)
+    against the independent float64 oracle with its own forward kinematics -- identical outside the oracle's 1e-5 m
+    decision band (tools/rigid_parity_report.py runs the same comparison on 2 x 10^6 configurations:
+    profiles/r02_rigid_parity.json, one mismatch, 3e-7 m from the boundary)."""
+    import torch
+    from plant_motion_planning_b200 import EdgeCheckConfig, EdgeChecker
+    from plant_motion_planning_b200.workloads import synthetic_worlds
+    model = load_iiwa14()
+    chk = EdgeChecker(model, synthetic_worlds(1), EdgeCheckConfig(mode="ignore_all"))
+    Q = np.random.RandomState(7).uniform(model.lower, model.upper, size=(50000, 7)).astype(np.float32)
+    gpu = (chk.check_configs(torch.from_numpy(Q), detail=False).flags.cpu().numpy()[:, 0] & 1) > 0
+    ref = H.HullScene().rigid(Q.astype(np.float64))
+    mis = gpu != ref["hit"]
+    assert not np.any(mis & (np.abs(ref["clearance"]) > 1e-5))
+    assert mis.sum() <= 5 and 0.1 < ref["hit"].mean() < 0.3
