@@ -262,7 +262,7 @@ class DynamicEnv:
 def static_rest_pose(world, prm: Optional[DynParams] = None, tol: float = 1e-11) -> np.ndarray:
     """The pose in which springs and gravity balance (no contact): root of this module's own generalized force by
     Newton with a finite-difference Jacobian.  Independent of plant_motion_planning_b200/model/statics.py (different
-    kinematics / Jacobian code); the two must agree (tests/test_dynamics_gap.py)."""
+    kinematics / Jacobian code); the two must agree (tests/test_dynamic_gap.py)."""
     prm = prm or DynParams()
     w = DynamicPlantWorld(world, np.zeros(1), DynParams(**{**prm.__dict__, "kd": 0.0, "joint_damping": 0.0}))
     P = w.P

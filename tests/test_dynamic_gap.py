@@ -57,3 +57,19 @@ def test_in_contact_gap_stays_at_its_measured_size():
     # the gap is one-sided where it matters: the quasi-static model never reports MORE over-limit waypoints
     ex_d, ex_q = np.any(dyn > LIMIT, axis=2), np.any(qs > LIMIT, axis=2)
     assert ex_q.sum() <= ex_d.sum()
+
+
+def test_rest_pose_of_the_product_equals_the_oracles_own_statics():
+    """model/statics.py (the product's gravity / spring balance, which the stem records and the device sampler carry) and
+    oracle/dynamic_oracle.static_rest_pose (root of the dynamic restatement's own generalized force: other kinematics,
+    other Jacobian code) find the same pose."""
+    from oracle.dynamic_oracle import static_rest_pose
+    from plant_motion_planning_b200.model.statics import rest_pose
+    from plant_motion_planning_b200.workloads import synthetic_worlds
+    worst = 0.0
+    for w in synthetic_worlds(6) + script_worlds("multi_world_our_method")[0]:
+        a, b = rest_pose(w), static_rest_pose(w)
+        assert a.shape == b.shape
+        worst = max(worst, float(np.abs(a - b).max()))
+        assert 0.005 < np.abs(a).max() < 0.3          # a real sag, far from buckling
+    assert worst < 1e-8, worst
