@@ -362,6 +362,9 @@ def main() -> None:
                 "executes all K iterations on every stem, so executed FP32 work == algorithmic work.  The production "
                 "launch (dense=0) skips iterations that are provably no-ops (no lane of the warp touches the stem); "
                 "results are identical.",
+        "instruction_mix_ceiling": {"tflops": 60.3, "frac_of_peak": 0.83, "measured_in_this_run": False,
+                                    "source": "tools/probes/mix_probe.cu on a B200 (profiles/r02_experiments.md): the pair loop's "
+                                              "mix of FFMA2 / FMUL2 / FADD2 / FMNMX / MUFU on independent chains at full occupancy"},
         "production_ms": k_ms,
         "hull_prepass_ms": rigid_ms,
         "edge_kernel_share_of_step": k_ms / ms if ms > 0 else None,
