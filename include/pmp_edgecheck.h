@@ -172,7 +172,9 @@ typedef struct pmp_params {
     int32_t iterations;      /* K Gauss-Newton steps per stem */
     int32_t mode;            /* PMP_MODE_* */
     int32_t dense;           /* 1 = disable data-dependent early exits (every unit runs all K iterations
-                                on every stem: results identical, used to measure the FP32 roofline) */
+                                on every stem: results identical, used to measure the FP32 roofline).  Applies to
+                                full-output pmp_validate_edges launches whose world tables fit shared memory (its own
+                                kernel instantiation); every other shape runs the production kernel */
     uint32_t gate_seed;      /* seed of the on-device gate (below) */
     float gate_probability;  /* 0 = off.  Otherwise first_hit treats "deflection exceeded" at (edge e, step s,
                                 world w) as a violation only if hash32(gate_seed, e, s, w) < gate_probability * 2^32:

@@ -14,6 +14,13 @@
 // hull's vertices is strided over the lanes (coalesced float4 loads) and finished with a warp arg-max; the simplex
 // logic is executed redundantly (uniform data, no divergence).  Oracle: oracle/hull_gjk.c (float64) through
 // oracle/edgecheck_oracle.c config_eval.
+//
+// Around that core: INSCRIBED balls of the same spheres decide certain hits in the broad phase (exact: they lie inside
+// hull (+) margin); hull pairs two joints apart are read from clearance tables built at set-up; warp items are claimed
+// from a global counter (an item that reaches the narrow phase costs tens of times one that does not); small batches
+// use items of 8 or 4 steps, so that one item gliding along an obstacle is not the kernel's makespan; a caller that
+// asked for no rigid step mask reads only the first set bit of every 32-step word, so steps behind the first certain
+// hit skip the narrow phase.  Robots without hulls run the same kernel in sphere mode (pair masks, static primitives).
 #pragma once
 #include "pmp_kernels.cuh"
 

@@ -1,11 +1,15 @@
 // Edge-validation kernels for sm_100a (FP32 CUDA cores; no tensor cores -- 3x3 transforms and
-// sphere/capsule distances are not dense contractions).
+// sphere/box distances are not dense contractions).
 //
 // Mapping (BASELINE.json north_star): one warp = one edge, lane = interpolation step (32-step chunks);
-// each lane runs the arm FK of its configuration once, keeps the A sphere centres in registers and
-// loops over all W worlds, whose stem tables are staged in shared memory (every lane of every warp
-// reads the same record at the same time -> conflict-free broadcast LDS).  Per-world results are
-// reduced over the 32 steps with warp votes / shuffles and written coalesced (lane = world).
+// each lane runs the arm FK of its configuration once and parks the A sphere centres in a per-warp
+// shared-memory tile (read back two spheres per 64-bit load for the packed FP32 sphere loops; the warp's
+// swept bounds are built from the same tile), then loops over all W worlds, whose stem tables are staged
+// in shared memory (every lane of every warp reads the same record at the same time -> conflict-free
+// broadcast LDS).  Per-world results are reduced over the 32 steps with warp votes / shuffles and written
+// coalesced (lane = world).  Limits, self and obstacle collisions come from the pre-pass kernel
+// (pmp_hull.cuh) as one bit per step.  DENSE instantiations (pmp_params.dense) switch every
+// data-dependent skip off: the roofline shape, with identical results.
 //
 // The arithmetic is the float32 twin of oracle/edgecheck_oracle.py (float64); every device function
 // names the oracle function it mirrors, and through it the reference lines.
