@@ -36,3 +36,33 @@ def test_native_arm_fails_loudly_without_a_gpu():
                           "--no-cpu-baseline"], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode != 0
     assert not [l for l in out.stdout.splitlines() if l.startswith("{")]
+
+
+def test_parity_block_counts_bits_over_live_steps_only():
+    """bench.py's parity_on_sample / decision_workload blocks: mismatches are counted over the live (edge, world, step) bits
+    (steps beyond an edge's n_steps are not evidence), percentiles over the per-(edge, world) reductions."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    E, W, C = 3, 2, 2
+    n = np.array([5, 40, 64], dtype=np.int32)
+    ref = {"n_steps": n, "first_hit": np.array([5, 7, 64], np.int32),
+           "rigid_mask": np.zeros((E, W, C), np.uint32), "exceed_mask": np.zeros((E, W, C), np.uint32),
+           "max_deflection": np.zeros((E, W)), "over_limit": np.zeros((E, W)), "ee_len": np.ones(E)}
+    ref["rigid_mask"][1, 0, 0] = 1 << 7
+    got = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in ref.items()}
+    got["max_deflection"] = got["max_deflection"].astype(np.float32)
+    got["over_limit"] = got["over_limit"].astype(np.float32)
+    got["ee_len"] = got["ee_len"].astype(np.float32)
+    got["rigid_mask"][0, 1, 0] |= 1 << 9           # beyond edge 0's 5 steps: not counted
+    got["exceed_mask"][1, 1, 1] |= 1 << 3          # step 35 of edge 1 (40 steps): counted
+    got["exceed_mask"][1, 1, 1] |= 1 << 20         # step 52 of edge 1: beyond its steps, not counted
+    got["first_hit"][2] = 10
+    got["max_deflection"][2, 1] = 0.25
+    r = bench.compare_with_oracle(got, ref, 64)
+    assert r["step_world_bits"] == (5 + 40 + 64) * W and r["n_steps_identical"]
+    assert r["rigid_bits_set_in_oracle"] == 1 and r["rigid_bit_mismatches"] == 0
+    assert r["exceed_bit_mismatches"] == 1
+    assert abs(r["mask_bit_agreement"] - (1 - 1 / (2 * 218))) < 1e-12
+    assert abs(r["first_hit_agreement"] - 2 / 3) < 1e-12
+    assert r["max_deflection_abs_err_rad"]["max"] == 0.25 and r["ee_len_abs_err_m"]["max"] == 0.0
