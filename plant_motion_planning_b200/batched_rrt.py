@@ -154,9 +154,8 @@ def batched_rrt_connect(checker, start: Sequence[float], goal: Sequence[float], 
     dense = _drop_repeats(np.concatenate([first, second[::-1][1:]], axis=0))
     way = _drop_repeats(np.concatenate([first[m1], second[m2][::-1][1:]], axis=0))
     to_conf = lambda q: tuple(float(v) for v in q)
-    return BatchedPlan([to_conf(q) for q in dense], [to_conf(q) for q in way], it,
-                       (len(_np(t_start.download()["parent"])), len(_np(t_goal.download()["parent"]))),
-                       2 * batch * it, log)
+    sizes = (len(da["parent"]), len(db["parent"])) if ta is t_start else (len(db["parent"]), len(da["parent"]))
+    return BatchedPlan([to_conf(q) for q in dense], [to_conf(q) for q in way], it, sizes, 2 * batch * it, log)
 
 
 @dataclass

@@ -999,7 +999,9 @@ static int launch_nearest(pmp_ctx* ctx, const float* nodes, int T, const int32_t
         pmp_nearest_min_kernel<DP, TG, CI><<<grid, PMP_NN_BLOCK, 0, st>>>(a);    \
         pmp_nearest_kernel<DP, TG, CI><<<grid, PMP_NN_BLOCK, 0, st>>>(a);        \
     } while (0)
-    if (a.D <= 8) { if (circ) PMP_NN_LAUNCH(8, 8, true); else PMP_NN_LAUNCH(8, 8, false); }
+    if (a.D == 7) { if (circ) PMP_NN_LAUNCH(7, 8, true); else PMP_NN_LAUNCH(7, 8, false); }        // no padding term
+    else if (a.D == 6) { if (circ) PMP_NN_LAUNCH(6, 8, true); else PMP_NN_LAUNCH(6, 8, false); }
+    else if (a.D <= 8) { if (circ) PMP_NN_LAUNCH(8, 8, true); else PMP_NN_LAUNCH(8, 8, false); }
     else { if (circ) PMP_NN_LAUNCH(16, 4, true); else PMP_NN_LAUNCH(16, 4, false); }
 #undef PMP_NN_LAUNCH
     pmp_nearest_finish_kernel<<<(B + 127) / 128, 128, 0, st>>>(a);

@@ -4,9 +4,11 @@
 //   pmp_nearest_min_kernel / pmp_nearest_kernel / pmp_nearest_finish_kernel
 //        nearest tree node of every target under the reference metric -- argmin over the tree of
 //        distance_fn(node, target) with the first minimum winning (motion_planners/motion_planners/utils.py:47-53,
-//        primitives.py:207; pybullet_tools/utils.py:3604-3627).  A float32 pass finds the minimum up to its rounding
-//        error; every node inside that error band is then evaluated in float64 on the float32 node/target data in
-//        a fixed summation order, so the chosen INDEX (and distance) is bit-identical to the float64 oracle.
+//        primitives.py:207; pybullet_tools/utils.py:3604-3627).  A float32 pass over every PMP_NN_SUB-th block of
+//        the tree gives an upper bound of the minimum (any sampled node is one); the full float32 pass then sends
+//        every node at or below that bound (plus the filter's rounding band) -- about PMP_NN_SUB per target -- to a
+//        float64 evaluation on the float32 node/target data in a fixed summation order, so the chosen INDEX (and
+//        distance) is bit-identical to the float64 oracle while the tree is scanned 1 + 1/PMP_NN_SUB times.
 //   pmp_edge_points_kernel
 //        configuration number step[e] of edge e, the same arithmetic as the edge kernel's interpolation.
 //   pmp_tree_append_kernel
@@ -20,6 +22,7 @@
 
 #define PMP_NN_TGT_MAX 8      // targets per CTA: 8 for D <= 8, 4 above (targets and running minima live in registers)
 #define PMP_NN_BLOCK 256
+#define PMP_NN_SUB 8          // pass 1 looks at every 8th block of PMP_NN_BLOCK nodes of a CTA's slice
 
 struct PmpNearestArgs {
     const float* nodes;        // [T, D]
@@ -91,10 +94,12 @@ __device__ __forceinline__ void pmp_nn_range(const PmpNearestArgs& a, int& lo, i
     hi = min(T, lo + per);
 }
 
-// Pass 1: smallest float32 squared distance of each target over the whole tree (atomicMin on the float bits: the
-// values are non-negative).  DP = DOF padding (8 or 16), TGT targets per CTA, all in registers; CIRC = the robot has
-// continuous joints (their wrap costs three instructions per term, so arms without one get a kernel without it).
-// Padding joints have target = node = 0 and contribute nothing.
+// Pass 1: smallest float32 squared distance of each target over a sample of the tree -- the first block of every
+// slice and every PMP_NN_SUB-th after it, so node 0 is always in -- (atomicMin on the float bits: the values are
+// non-negative).  Pass 2 only needs a bound that the true nearest node passes, which the distance of ANY node is; the
+// tighter the bound the fewer float64 evaluations.  DP = DOF or its padding (6, 7, 8 or 16), TGT targets per CTA, all
+// in registers; CIRC = the robot has continuous joints (their wrap costs three instructions per term, so arms
+// without one get a kernel without it).  Padding joints have target = node = 0 and contribute nothing.
 template <int DP, int TGT, bool CIRC>
 __global__ void __launch_bounds__(PMP_NN_BLOCK, 2) pmp_nearest_min_kernel(const PmpNearestArgs a) {
     const int D = a.D;
@@ -112,7 +117,7 @@ __global__ void __launch_bounds__(PMP_NN_BLOCK, 2) pmp_nearest_min_kernel(const 
     float best[TGT];
 #pragma unroll
     for (int t = 0; t < TGT; ++t) best[t] = 3.0e38f;
-    for (int n = lo + threadIdx.x; n < hi; n += PMP_NN_BLOCK) {
+    for (int n = lo + threadIdx.x; n < hi; n += PMP_NN_BLOCK * PMP_NN_SUB) {
         float q[DP];
 #pragma unroll
         for (int j = 0; j < DP; ++j) q[j] = j < D ? a.nodes[(size_t)n * D + j] : 0.f;
@@ -133,8 +138,10 @@ __global__ void __launch_bounds__(PMP_NN_BLOCK, 2) pmp_nearest_min_kernel(const 
     }
 }
 
-// Pass 2: every node whose float32 distance is within the filter's error band of the pass-1 minimum is evaluated
-// exactly in float64; the lexicographic minimum of (distance, index) over those is the reference's argmin.
+// Pass 2 (the whole tree): every node whose float32 distance is within the filter's error band of the pass-1 bound is
+// evaluated exactly in float64; the lexicographic minimum of (distance, index) over those is the reference's argmin.
+// (The node n* of the exact minimum passes: its float32 value is at most its exact value plus the band, which is at
+// most the exact value of the node behind the bound plus the band, which is at most the bound plus two bands.)
 template <int DP, int TGT, bool CIRC>
 __global__ void __launch_bounds__(PMP_NN_BLOCK, 2) pmp_nearest_kernel(const PmpNearestArgs a) {
     __shared__ double sm_r[PMP_NN_BLOCK / 32][TGT];
@@ -173,7 +180,7 @@ __global__ void __launch_bounds__(PMP_NN_BLOCK, 2) pmp_nearest_kernel(const PmpN
             pmp_upk(pmp_nn_s32x2<DP, CIRC>(tg[t2 >> 1], q, a.circular_mask), sq[t2], sq[t2 + 1]);
             any |= (sq[t2] <= thr[t2]) | (sq[t2 + 1] <= thr[t2 + 1]);
         }
-        if (any) {                                   // rare: about one node per target passes the filter
+        if (any) {                                   // rare: about PMP_NN_SUB nodes per target pass the filter
 #pragma unroll
             for (int t = 0; t < TGT; ++t) {
                 if (sq[t] <= thr[t] && t0 + t < a.B) {

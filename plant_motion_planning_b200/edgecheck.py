@@ -481,14 +481,17 @@ class DeviceTree:
         self.capacity = int(capacity)
         dev = checker._dev()
         D = checker.dof
-        self.nodes = torch.zeros((self.capacity, D), device=dev, dtype=torch.float32)
-        self.parent = torch.full((self.capacity,), -1, device=dev, dtype=torch.int32)
-        self.via = torch.zeros((self.capacity, D), device=dev, dtype=torch.float32)
-        self.via_steps = torch.zeros((self.capacity,), device=dev, dtype=torch.int32)
+        # only rows below `size` are ever read (the append kernel writes every field of a new node): no fills
+        self.nodes = torch.empty((self.capacity, D), device=dev, dtype=torch.float32)
+        self.parent = torch.empty((self.capacity,), device=dev, dtype=torch.int32)
+        self.via = torch.empty((self.capacity, D), device=dev, dtype=torch.float32)
+        self.via_steps = torch.empty((self.capacity,), device=dev, dtype=torch.int32)
         self.size = torch.ones((1,), device=dev, dtype=torch.int32)
-        root_t = torch.as_tensor(np.asarray(root, dtype=np.float32)).to(dev)
+        root_t = torch.as_tensor(np.asarray(root, dtype=np.float32).reshape(D)).to(dev)
         self.nodes[0] = root_t
         self.via[0] = root_t
+        self.parent[:1] = -1
+        self.via_steps[:1] = 0
         self.size_bound = 1            # host upper bound of the live node count (no synchronisation needed)
         self._desc = _capi.Tree(self.nodes.data_ptr(), self.parent.data_ptr(), self.via.data_ptr(),
                                 self.via_steps.data_ptr(), self.size.data_ptr(), self.capacity, 0)

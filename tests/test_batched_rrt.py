@@ -165,6 +165,29 @@ def test_nearest_indices_bit_identical(gpu, which, T, B):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("which", ["iiwa", "synth9"])
+def test_nearest_with_an_ordered_tree_and_ties(gpu, which):
+    """The float32 bound of pass 1 comes from a sample of the tree (the first 256-node block of every slice and every
+    8th after it); the answer may not depend on it.  A tree sorted along joint 0 makes the sample as unrepresentative
+    as it gets, duplicated nodes (in unsampled blocks, before and after a sampled one) exercise the first-minimum rule,
+    and targets that ARE tree nodes give distance 0."""
+    robot, chk = gpu[which]
+    torch = gpu["torch"]
+    rng = np.random.RandomState(11)
+    nodes, targets = _random_tree(robot, rng, 120000, 96)
+    nodes = nodes[np.argsort(nodes[:, 0], kind="stable")]
+    dup = rng.randint(300, 119000, size=40)
+    nodes[dup + 517] = nodes[dup]                  # a later copy of the same node: the earlier index must win
+    targets[:20] = nodes[dup[:20] + 517]           # exact hits, distance 0
+    targets[20:40] = nodes[dup[20:]] + np.float32(1e-4)
+    idx, dist = chk.nearest(torch.from_numpy(nodes), torch.from_numpy(targets))
+    oi, od = O.nearest(robot, nodes, targets)
+    assert np.array_equal(idx.cpu().numpy(), oi)
+    assert np.array_equal(dist.cpu().numpy(), od)
+    assert np.all(od[:20] == 0.0) and np.all(oi[:20] <= dup[:20])
+
+
+@pytest.mark.gpu
 def test_nearest_live_count_nan_and_gather(gpu):
     robot, chk = gpu["iiwa"]
     torch = gpu["torch"]
