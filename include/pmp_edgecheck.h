@@ -69,7 +69,7 @@ typedef struct pmp_robot_desc {
     const float* base_t;      /* [3] */
     const int32_t* sph_joint; /* [A] joint the sphere rides on */
     const float* sph_center;  /* [A*3] in that joint's frame */
-    const float* sph_radius;  /* [A] */
+    const float* sph_radius;  /* [A], each in (0, 0.5] m */
     const uint32_t* self_mask;/* [A] bit b (b > a) set => test sphere pair (a, b) */
     const int32_t* link_joint;/* [L] joint the link rides on, -1 = welded to the base */
     const float* link_R;      /* [L*9] link frame in the joint frame (or root frame) */
@@ -149,7 +149,7 @@ typedef struct pmp_sampler_desc {
     double spacing;                            /* stem_base_spacing (rand_gen...:19-20) */
     double scaling;                            /* 0.25 (rand_gen...:18) */
     double half_width, com_z, limit;           /* 0.025, 0.25, 1.5 (rand_gen...:74-75, 265, 307) */
-    double stem_margin;                        /* Bullet's margin carved out of the stem boxes */
+    double stem_margin;                        /* Bullet's margin carved out of the stem boxes, in [0, 0.4] m */
     double kp, mass, g;                        /* 500, 10, 9.8 (env.py:128; rand_gen...:255; utils.py:1218-1221) */
 } pmp_sampler_desc;
 /* stems_dev [W * n_stems * PMP_STEM_STRIDE], boxes_dev [W * PMP_BOX_STRIDE] (one base box per world).

@@ -155,7 +155,11 @@ extern "C" int pmp_set_robot(pmp_ctx* ctx, const pmp_robot_desc* r) {
     memcpy(t.sph_radius_outer, r->sph_radius, sizeof(float) * A);
     memcpy(t.self_mask, r->self_mask, sizeof(uint32_t) * A);
     memcpy(t.sph_joint, r->sph_joint, sizeof(int32_t) * A);
-    for (int a = A; a < PMP_MAX_SPHERES; ++a) { t.sph_joint[a] = -1; t.sph_radius[a] = -1.0e3f; t.sph_radius_outer[a] = -1.0e3f; }
+    // padding spheres: parked at PMP_FAR by the kernels; radius + stem margin stays negative and small (the contact sums
+    // saturate distances at 1 m, pmp_kernels.cuh pmp_outside)
+    for (int a = A; a < PMP_MAX_SPHERES; ++a) { t.sph_joint[a] = -1; t.sph_radius[a] = -0.5f; t.sph_radius_outer[a] = -1.0e3f; }
+    for (int a = 0; a < A; ++a)
+        if (!(t.sph_radius[a] > 0.f && t.sph_radius[a] <= 0.5f)) return fail(ctx, PMP_E_INVALID, "sph_radius outside (0, 0.5] m");
     for (int a = 0; a < A; ++a) {
         if (t.sph_joint[a] < 0 || t.sph_joint[a] >= D) return fail(ctx, PMP_E_INVALID, "sph_joint out of range");
         if (a && t.sph_joint[a] < t.sph_joint[a - 1]) return fail(ctx, PMP_E_INVALID, "spheres must be sorted by joint");
@@ -430,6 +434,9 @@ extern "C" int pmp_set_worlds(pmp_ctx* ctx, const pmp_world_desc* w) {
             memcpy(&os, rec + PMP_S_OSLOT, 4);
             if (ps < -1 || ps >= w->n_slots || os < -1 || os >= w->n_slots)
                 return fail(ctx, PMP_E_INVALID, "stem frame slot out of range");
+            // sphere radius (<= 0.5) + margin < 1 m: the contact sums saturate distances there (pmp_outside)
+            if (!(rec[PMP_S_MARGIN] >= 0.f && rec[PMP_S_MARGIN] <= 0.4f))
+                return fail(ctx, PMP_E_INVALID, "stem margin outside [0, 0.4] m");
         }
     }
     CK(cudaSetDevice(ctx->device));
@@ -464,6 +471,7 @@ extern "C" int pmp_sample_worlds(pmp_ctx* ctx, const pmp_sampler_desc* d, int32_
         if (d->pslot[s] < -1 || d->pslot[s] >= d->n_slots || d->oslot[s] < -1 || d->oslot[s] >= d->n_slots)
             return fail(ctx, PMP_E_INVALID, "stem frame slot out of range");
     }
+    if (!(d->stem_margin >= 0.0 && d->stem_margin <= 0.4)) return fail(ctx, PMP_E_INVALID, "stem_margin outside [0, 0.4] m");
     if (uniforms_dev && n_uniforms < PMP_SAMPLER_HEAD + P * PMP_SAMPLER_PER_STEM)
         return fail(ctx, PMP_E_INVALID, "too few uniforms per world");
     CK(cudaSetDevice(ctx->device));

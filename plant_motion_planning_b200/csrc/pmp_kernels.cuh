@@ -50,6 +50,11 @@ __device__ __forceinline__ void pmp_mat_mul(const float* __restrict__ X, const f
     }
 }
 __device__ __forceinline__ float pmp_clamp(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+// v - clamp(v, -h, h) while |v| - h <= 1 (the same float: the subtraction is the same up to sign), +-1 beyond, and a
+// signed zero inside: one FADD.SAT and one LOP3 instead of two FMNMX and a subtraction.  For the stem contact sums
+// only: a component a metre outside the box means no contact either way, because sphere radius + stem margin < 1 m
+// (pmp_set_robot / pmp_set_params enforce 0.5 m and 0.4 m; padding spheres carry radius -0.5 for the same reason).
+__device__ __forceinline__ float pmp_outside(float v, float h) { return copysignf(__saturatef(fabsf(v) - h), v); }
 // One MUFU.RSQ: the argument is clamped to >= 1e-24 by the caller, so the denormal pre/post-scaling that rsqrtf()
 // emits without -ftz (FSETP + FMUL + FSEL + FMUL per call) is dead weight in the innermost loop.
 __device__ __forceinline__ float pmp_rcp_ftz(float x) {
@@ -476,7 +481,8 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
                 const pmp_f2 ez = pmp_pk(fmaxf(fabsf(r0) - hh, 0.f), fmaxf(fabsf(r1) - hh, 0.f));
                 const pmp_f2 d2 = pmp_fma2(ex, ex, pmp_fma2(ey, ey, pmp_fma2(ez, ez, pmp_bc(1e-24f))));
                 // touching <=> (r_a + margin)^2 - d2 > 0; the largest such value over all spheres decides
-                // (padding spheres sit at PMP_FAR with radius -1e3: (r + mg)^2 = 1e6 against d2 = 3e12)
+                // (padding spheres sit at PMP_FAR with radius -0.5: (r + mg)^2 <= 0.25 against d2 = 3e12, or >= 1 where
+                // the contact sums saturate it)
                 const pmp_f2 nrr = cpf.nrr(a >> 1, mg, rt);
                 float m0, m1;
                 pmp_upk(pmp_fma2(nrr, nrr, pmp_neg2(d2)), m0, m1);
@@ -520,9 +526,11 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
                     const pmp_f2 pz = pmp_fma2(pmp_bc(Rl[2]), ccx, pmp_fma2(pmp_bc(Rl[5]), ccy, pmp_fma2(pmp_bc(Rl[8]), ccz, nbz)));
                     float p0, p1, q0, q1, r0, r1;
                     pmp_upk(px, p0, p1); pmp_upk(py, q0, q1); pmp_upk(pz, r0, r1);
-                    const pmp_f2 dx = pmp_sub2(px, pmp_pk(pmp_clamp(p0, -hw, hw), pmp_clamp(p1, -hw, hw)));
-                    const pmp_f2 dy = pmp_sub2(py, pmp_pk(pmp_clamp(q0, -hw, hw), pmp_clamp(q1, -hw, hw)));
-                    const pmp_f2 dz = pmp_sub2(pz, pmp_pk(pmp_clamp(r0, -hh, hh), pmp_clamp(r1, -hh, hh)));
+                    // component of (p - nearest box point): FADD.SAT + LOP3 each instead of two FMNMX and a subtraction
+                    // (saturated at 1 m -- then d2 >= 1 > (r + margin)^2 and the penetration below is an exact 0 as before)
+                    const pmp_f2 dx = pmp_pk(pmp_outside(p0, hw), pmp_outside(p1, hw));
+                    const pmp_f2 dy = pmp_pk(pmp_outside(q0, hw), pmp_outside(q1, hw));
+                    const pmp_f2 dz = pmp_pk(pmp_outside(r0, hh), pmp_outside(r1, hh));
                     // + 1e-24 > 0: rsqrt stays finite
                     const pmp_f2 d2 = pmp_fma2(dx, dx, pmp_fma2(dy, dy, pmp_fma2(dz, dz, pmp_bc(1e-24f))));
                     float e0, e1;

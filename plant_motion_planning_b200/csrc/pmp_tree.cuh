@@ -169,10 +169,20 @@ __global__ void __launch_bounds__(PMP_NN_BLOCK, 2) pmp_nearest_kernel(const PmpN
     int best_i[TGT];
 #pragma unroll
     for (int t = 0; t < TGT; ++t) { best_r[t] = inf; best_i[t] = 0x7fffffff; }
-    for (int n = lo + threadIdx.x; n < hi; n += PMP_NN_BLOCK) {
-        float q[DP];
+    float q[DP];
+    {
+        const int n0 = min(lo + (int)threadIdx.x, a.T - 1);
 #pragma unroll
-        for (int j = 0; j < DP; ++j) q[j] = j < D ? a.nodes[(size_t)n * D + j] : 0.f;
+        for (int j = 0; j < DP; ++j) q[j] = j < D ? a.nodes[(size_t)n0 * D + j] : 0.f;
+    }
+    for (int n = lo + threadIdx.x; n < hi; n += PMP_NN_BLOCK) {
+        // the next node's loads are in flight while this one's distances are computed
+        float qn[DP];
+        {
+            const int nn = min(n + PMP_NN_BLOCK, a.T - 1);
+#pragma unroll
+            for (int j = 0; j < DP; ++j) qn[j] = j < D ? a.nodes[(size_t)nn * D + j] : 0.f;
+        }
         float sq[TGT];
         bool any = false;
 #pragma unroll
@@ -190,6 +200,8 @@ __global__ void __launch_bounds__(PMP_NN_BLOCK, 2) pmp_nearest_kernel(const PmpN
                 }
             }
         }
+#pragma unroll
+        for (int j = 0; j < DP; ++j) q[j] = qn[j];
     }
     // block reduction of (distance, index)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;

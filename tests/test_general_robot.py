@@ -98,3 +98,58 @@ def test_gpu_parity_general_robot(setup):
     for e in range(5):
         n = O.num_steps(m, q0[e].astype(np.float64), q1[e].astype(np.float64), np.radians(3))
         assert n == ce["n_steps"][e]
+
+
+@pytest.mark.gpu
+def test_padding_spheres_and_far_stems_in_both_kernel_shapes():
+    """A 14-sphere arm runs in the A = 16 instantiation with two padding spheres, and two of the four worlds stand
+    5 m from the arm: every sphere is more than a metre outside those stems' boxes, where the contact sums saturate their
+    distance components (pmp_outside).  Neither may register: production and dense launches agree bit for bit and
+    match the oracle, far worlds stay at their rest observers."""
+    import torch
+    from plant_motion_planning_b200 import EdgeCheckConfig, EdgeChecker
+    from plant_motion_planning_b200.model.plants import sample_world
+    import random
+    m = synthetic_robot(n_joints=6, spheres_per_link=2)
+    assert m.num_spheres == 14
+    near, far_x, far_y = ((0.0, 0.35), (-0.5, 0.0)), ((5.0, 5.0), (-0.5, 0.0)), ((0.0, 0.35), (5.0, 5.0))
+    worlds = [sample_world(1, 2, 1, lim, np_random=np.random.RandomState(5 + k), py_random=random.Random(5 + k))
+              for k, lim in enumerate([near, far_x, near, far_y])]
+    rng = np.random.RandomState(2)
+    lo, hi = np.where(m.circular, -np.pi, m.lower), np.where(m.circular, np.pi, m.upper)
+    Q = rng.uniform(lo, hi, size=(2048, m.dof)).astype(np.float32)
+    chk = EdgeChecker(m, worlds, EdgeCheckConfig(max_steps=64))
+    g = chk.check_configs(torch.from_numpy(Q))
+    assert chk.launch_info()["n_sphere_pad"] == 16
+    c = COracle(m, worlds).check_configs(Q)
+    d = g.deflection.cpu().numpy()
+    assert np.percentile(np.abs(d - c["deflection"]), 99.9) <= 1e-4
+    rest = chk.check_configs(torch.from_numpy(Q[:1] * 0 + np.float32(0.0))).deflection.cpu().numpy()
+    for far in (1, 3):                                   # nothing reaches a plant 5 m away
+        assert np.array_equal(d[:, far], np.broadcast_to(rest[0, far], d[:, far].shape))
+        assert np.abs(c["deflection"][:, far] - d[:, far]).max() <= 1e-5
+    assert (np.abs(d[:, 0] - rest[0, 0]) > 1e-3).any()   # ... and the near ones are pushed
+    a, b = torch.from_numpy(Q[:1024]), torch.from_numpy(Q[1024:])
+    r1 = chk.validate_edges(a, b, want_masks=True)
+    chk.set_config(dense=True)
+    r2 = chk.validate_edges(a, b, want_masks=True)
+    chk.set_config(dense=False)
+    assert torch.equal(r1.first_hit, r2.first_hit) and torch.equal(r1.exceed_mask, r2.exceed_mask)
+    assert torch.equal(r1.rigid_mask, r2.rigid_mask)
+    assert (r1.max_deflection - r2.max_deflection).abs().max().item() <= 2e-6
+    assert torch.equal(r1.max_deflection[:, 1], r2.max_deflection[:, 1])
+    chk.close()
+
+
+@pytest.mark.gpu
+def test_radius_and_margin_limits_are_enforced(setup):
+    """pmp_set_robot / pmp_set_worlds reject sphere radii above 0.5 m and stem margins above 0.4 m (their sum must stay
+    below the metre at which the contact sums saturate)."""
+    import dataclasses
+    from plant_motion_planning_b200 import EdgeCheckConfig, EdgeChecker
+    m, worlds, _ = setup
+    big = dataclasses.replace(m, sph_radius=np.where(np.arange(m.num_spheres) == 3, 0.6, m.sph_radius))
+    with pytest.raises(RuntimeError, match="sph_radius"):
+        EdgeChecker(big, worlds, EdgeCheckConfig())
+    with pytest.raises(RuntimeError, match="margin"):
+        EdgeChecker(m, worlds, EdgeCheckConfig(stem_margin=0.45))
