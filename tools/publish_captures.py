@@ -58,7 +58,7 @@ iu = {"build_digest": dig,
       "warps_eligible_per_scheduler": {"production": g("edge_kernel_production", ELI), "dense": g("edge_kernel_dense", ELI)},
       "hull_prepass_issue_active": g("rigid_prepass_production", ISS) / 100,
       "hull_prepass_ms_per_2^15_edges": g("rigid_prepass_production", "gpu__time_duration.sum"),
-      "note": "dense: FMA-pipe bound (34 packed FP32 instructions = 68 pipe cycles per sphere pair and iteration against 48 issue "
+      "note": "dense: FMA-pipe bound (31 packed + 6 scalar FP32 instructions = 68 pipe cycles per sphere pair and iteration against 52 issue "
               "slots); production: issue bound on a flat profile"}
 json.dump(iu, open(os.path.join(P, "issue_utilization.json"), "w"), indent=1)
 r = line["roofline"]
