@@ -463,6 +463,8 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
         // The dense (roofline) launch skips this phase: its first Gauss-Newton pass computes the same p, d and |d|^2 for
         // every pair anyway and derives `touch` from them with the same arithmetic (|p| - h and p - clamp(p) have the
         // same square), so that executed work == algorithmic work there and the results stay bit-identical.
+        // (Here too the exterior components are sat(|p| - h): one FADD.SAT instead of FADD + FMNMX; a saturated component
+        // makes d2 >= 1 > (r + margin)^2, i.e. "apart", as the unsaturated value would.)
         bool touch = false;
         uint32_t pairs = 0u;
         cpf.prep(mg, rt);
@@ -476,9 +478,9 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
                 pmp_upk(pmp_fma2(pmp_bc(Rs[0]), cx, pmp_fma2(pmp_bc(Rs[3]), cy, pmp_fma2(pmp_bc(Rs[6]), cz, nbx))), p0, p1);
                 pmp_upk(pmp_fma2(pmp_bc(Rs[1]), cx, pmp_fma2(pmp_bc(Rs[4]), cy, pmp_fma2(pmp_bc(Rs[7]), cz, nby))), q0, q1);
                 pmp_upk(pmp_fma2(pmp_bc(Rs[2]), cx, pmp_fma2(pmp_bc(Rs[5]), cy, pmp_fma2(pmp_bc(Rs[8]), cz, nbz))), r0, r1);
-                const pmp_f2 ex = pmp_pk(fmaxf(fabsf(p0) - hw, 0.f), fmaxf(fabsf(p1) - hw, 0.f));
-                const pmp_f2 ey = pmp_pk(fmaxf(fabsf(q0) - hw, 0.f), fmaxf(fabsf(q1) - hw, 0.f));
-                const pmp_f2 ez = pmp_pk(fmaxf(fabsf(r0) - hh, 0.f), fmaxf(fabsf(r1) - hh, 0.f));
+                const pmp_f2 ex = pmp_pk(__saturatef(fabsf(p0) - hw), __saturatef(fabsf(p1) - hw));
+                const pmp_f2 ey = pmp_pk(__saturatef(fabsf(q0) - hw), __saturatef(fabsf(q1) - hw));
+                const pmp_f2 ez = pmp_pk(__saturatef(fabsf(r0) - hh), __saturatef(fabsf(r1) - hh));
                 const pmp_f2 d2 = pmp_fma2(ex, ex, pmp_fma2(ey, ey, pmp_fma2(ez, ez, pmp_bc(1e-24f))));
                 // touching <=> (r_a + margin)^2 - d2 > 0; the largest such value over all spheres decides
                 // (padding spheres sit at PMP_FAR with radius -0.5: (r + mg)^2 <= 0.25 against d2 = 3e12, or >= 1 where
@@ -584,9 +586,9 @@ __device__ __forceinline__ PmpUnitOut pmp_world_eval(const float* __restrict__ w
                             pmp_upk(pmp_fma2(pmp_bc(Rl[0]), ccx, pmp_fma2(pmp_bc(Rl[3]), ccy, pmp_fma2(pmp_bc(Rl[6]), ccz, nbx))), p0, p1);
                             pmp_upk(pmp_fma2(pmp_bc(Rl[1]), ccx, pmp_fma2(pmp_bc(Rl[4]), ccy, pmp_fma2(pmp_bc(Rl[7]), ccz, nby))), q0, q1);
                             pmp_upk(pmp_fma2(pmp_bc(Rl[2]), ccx, pmp_fma2(pmp_bc(Rl[5]), ccy, pmp_fma2(pmp_bc(Rl[8]), ccz, nbz))), r0, r1);
-                            const pmp_f2 ex = pmp_pk(fmaxf(fabsf(p0) - hw, 0.f), fmaxf(fabsf(p1) - hw, 0.f));
-                            const pmp_f2 ey = pmp_pk(fmaxf(fabsf(q0) - hw, 0.f), fmaxf(fabsf(q1) - hw, 0.f));
-                            const pmp_f2 ez = pmp_pk(fmaxf(fabsf(r0) - hh, 0.f), fmaxf(fabsf(r1) - hh, 0.f));
+                            const pmp_f2 ex = pmp_pk(__saturatef(fabsf(p0) - hw), __saturatef(fabsf(p1) - hw));
+                            const pmp_f2 ey = pmp_pk(__saturatef(fabsf(q0) - hw), __saturatef(fabsf(q1) - hw));
+                            const pmp_f2 ez = pmp_pk(__saturatef(fabsf(r0) - hh), __saturatef(fabsf(r1) - hh));
                             const pmp_f2 d2 = pmp_fma2(ex, ex, pmp_fma2(ey, ey, pmp_mul2(ez, ez)));
                             const pmp_f2 nrr = cpf.nrr(a >> 1, mg, rt);
                             float m0, m1;
