@@ -24,6 +24,11 @@ for src, dst in ((f"bench_n1_{tag}.json", "r02_bench_n1.json"), (f"bench_ref_{ta
 subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), os.path.join(G, f"prof_{tag}.ncu-rep"),
                 os.path.join(P, "r02_edge_rigid_ncu.csv"), "rigid_prepass_production", "edge_kernel_production",
                 "rigid_prepass_dense", "edge_kernel_dense"], check=True, stdout=subprocess.DEVNULL)
+if os.path.exists(os.path.join(G, f"planner_bench_{tag}.json")):          # FULL=1 captures
+    shutil.copy(os.path.join(G, f"planner_bench_{tag}.json"), os.path.join(P, "r02_planner_bench.json"))
+if os.path.exists(os.path.join(G, f"tree_{tag}.ncu-rep")):
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), os.path.join(G, f"tree_{tag}.ncu-rep"),
+                    os.path.join(P, "r02_tree_kernels_ncu.csv")], check=True, stdout=subprocess.DEVNULL)
 rows = [r for r in csv.reader(open(os.path.join(G, f"traffic_{tag}.csv"))) if len(r) > 10 and r[0] == "0"]
 m = {r[12]: float(r[14]) for r in rows}
 E, W = 1 << 20, 64
