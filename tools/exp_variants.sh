@@ -5,7 +5,7 @@ set -e
 cd "$(dirname "$0")/.."
 C=plant_motion_planning_b200/csrc
 OUT=plant_motion_planning_b200/_lib/variants
-BASE=/tmp/pmp_base_obj
+BASE=$OUT/obj          # scratch objects next to the variant libraries (git-ignored; delete _lib/variants before a gpurun snapshot you do not need them in)
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xptxas -v"
 mkdir -p $OUT $BASE
 for f in pmp_inst_a12 pmp_inst_a16 pmp_inst_a20 pmp_inst_a32 pmp_inst_a12f pmp_inst_a16f pmp_inst_a20f pmp_inst_a32f; do
